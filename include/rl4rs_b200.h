@@ -1,0 +1,151 @@
+/*
+ * rl4rs_b200.h -- C-ABI of the B200-native RL4RS hot path (librl4rs_b200.so).
+ *
+ * The reference has no FFI: its "operator API" for this path is the Python protocol
+ * RecEnvBase / RecSimBase / RecState (rl4rs/env/base.py:26-57,111-175,178-273).  Each entry
+ * point below names the reference interface it replaces (file:line under /root/reference).
+ * The Python mirror of those classes (rl4rs_b200/env/) binds this library through ctypes
+ * (rl4rs_b200/_capi.py); INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); return 0 on success, a negative
+ * r4_status otherwise, r4_last_error() gives the message; nothing throws across the ABI.
+ * "dev" pointers are device memory owned by the CALLER (allocated by torch on the Python side);
+ * the library only borrows them for the work it enqueues on `stream` (a cudaStream_t passed as
+ * void*; NULL = legacy default stream).  Every call is asynchronous on that stream.  One r4_env
+ * per device, not thread-safe (the reference is single-threaded, base.py:119-130); distinct
+ * handles are independent.
+ */
+#ifndef RL4RS_B200_H
+#define RL4RS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct r4_env r4_env;
+
+typedef enum {
+  R4_OK = 0,
+  R4_ERR_ARG = -1,      /* bad argument / unsupported configuration */
+  R4_ERR_STATE = -2,    /* call out of order (e.g. step before reset, step past max_steps) */
+  R4_ERR_CUDA = -3,     /* CUDA runtime error (message holds cudaGetErrorString) */
+  R4_ERR_NOMEM = -4
+} r4_status;
+
+/* config['...'] flags read by the reference via config.get (slate.py:22,92,98,153,245,250,299) */
+enum {
+  R4_FLAG_RLLIB_MASK = 1,     /* support_rllib_mask */
+  R4_FLAG_D3RL_MASK = 2,      /* support_d3rl_mask */
+  R4_FLAG_CONTI = 4,          /* support_conti_env */
+  R4_FLAG_ONEHOT = 8,         /* support_onehot_action (action_emb = eye(action_size)) */
+  R4_FLAG_RAWSTATE = 16,      /* rawstate_as_obs: no simulator forward for observations */
+  R4_FLAG_INFO_FETCH = 32     /* simulator_info_fetch: expose per-item click probabilities */
+};
+
+enum { R4_ENV_SLATE = 0, R4_ENV_SEQSLATE = 1 };   /* rl4rs/__init__.py:10-18 */
+
+/* The config dict of the reference scripts (simulator_eval.py:9-12, modelfree_train.py:32-37). */
+typedef struct {
+  int32_t env_kind;             /* R4_ENV_SLATE | R4_ENV_SEQSLATE */
+  int32_t flags;                /* R4_FLAG_* */
+  int32_t batch_size;
+  int32_t max_steps;            /* 9 (Slate) / 27 or 36 (SeqSlate) */
+  int32_t page_items;           /* 9 */
+  int32_t action_size;          /* 284 */
+  int32_t action_emb_size;      /* 32 (ignored with R4_FLAG_ONEHOT) */
+  int32_t maxlen;               /* 64 */
+  int32_t seq_num;              /* 2 */
+  int32_t dense_feature_num;    /* 432 */
+  int32_t category_feature_num; /* 21 */
+  int32_t category_hash_size;   /* 100000 */
+  int32_t emb_size;             /* 128 */
+  int32_t hidden_units;         /* 128 */
+  int32_t max_rows_per_pass;    /* 0 = default; bound on simulator rows per launch group */
+} r4_config;
+
+/* Per-call output buffers (device, caller-owned).  NULL = not wanted.
+ * Replaces the return values of RecSimBase._step / sample (base.py:157-175) and
+ * SlateRecEnv.obs_fn (slate.py:244-279). */
+typedef struct {
+  float*   obs;          /* f32 [B,256]   simulator_obs layer (dien.py:35); NULL with RAWSTATE */
+  uint8_t* action_mask;  /* u8  [B,A]     action_mask & location_mask & special_mask (slate.py:93-97) */
+  double*  reward;       /* f64 [B]       slate.py:281-308 / seqslate.py:136-160 */
+  uint8_t* done;         /* u8  [B]       base.py:165-168 */
+  int32_t* chosen;       /* i32 [B]       item ids actually placed (kNN result in conti mode) */
+  int32_t* cat;          /* i32 [B,21]    category_feature of the new state (datautil.py:59-65) */
+  float*   dense;        /* f32 [B,432]   dense_feature (datautil.py:52-58) */
+  int32_t* seq;          /* i32 [B,2,64]  sequence_feature (datautil.py:43-47) */
+  float*   click_p;      /* f32 [B,9]     probs[:,1] of the reward pass (slate.py:298-301); written
+                                          only on steps that compute a reward */
+  int32_t* masked_actions; /* i32 [B,9|max_steps] d3rl 'masked_actions' (slate.py:98-104, seqslate.py:18-23) */
+} r4_out;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+/* SlateRecEnv.__init__/RecSimBase.__init__ (slate.py:223-237, base.py:114-131) */
+int r4_create(const r4_config* cfg, int device, r4_env** out);
+void r4_destroy(r4_env* env);
+const char* r4_last_error(const r4_env* env);   /* env may be NULL: error of the last failed r4_create */
+
+/* ---- static data ------------------------------------------------------------------------- */
+/* SlateState.get_iteminfo_from_file / get_mask_from_file (slate.py:28-65).  HOST pointers,
+ * n = action_size rows, row 0 = the implicit padding item.  special[i] != 0 marks the ids whose
+ * special column == 2.  action_emb is f64 [n, emb_dim] (slate.py:47-52; eye(n) with ONEHOT). */
+int r4_load_items(r4_env* env, const double* item_vec, int vec_dim, const double* price,
+                  const uint8_t* special, const double* action_emb, int emb_dim, int n);
+
+/* tf.train.Saver.restore (base.py:148-151): one named f32 tensor of the W-table;
+ * `data` may be a host or a device pointer.  r4_finalize_weights derives the fused layouts. */
+int r4_load_weight(r4_env* env, const char* name, const float* data, const int64_t* shape, int rank);
+int r4_finalize_weights(r4_env* env, void* stream);
+
+/* RecDataBase (base.py:60-108): the parsed log, structure-of-arrays, DEVICE pointers that must
+ * stay valid until the next r4_load_log / r4_destroy.  user_seq is pre-padded/truncated to maxlen
+ * (datautil.py:43-46).  n_slots = 9 (dataset A) or 36 (b3 trajectories). */
+int r4_load_log(r4_env* env, const int32_t* user_cat /*[N,10]*/, const float* user_dense /*[N,32]*/,
+                const int32_t* user_seq /*[N,maxlen]*/, const int32_t* logged_items /*[N,n_slots]*/,
+                const uint8_t* feedback /*[N,n_slots]*/, int64_t n_rows, int n_slots);
+
+/* ---- episode ----------------------------------------------------------------------------- */
+/* RecEnvBase.reset -> RecSimBase.sample (base.py:265-269,172-175): row_idx i32[B] (device) are
+ * the log rows RecDataBase.sample chose (base.py:92-100). */
+int r4_reset(r4_env* env, const int32_t* row_idx, const r4_out* out, void* stream);
+
+/* RecEnvBase.step -> RecSimBase._step (base.py:256-263,157-170) -> SlateState.act
+ * (slate.py:193-214 / seqslate.py:92-126).  action: i32[B] item ids, or with R4_FLAG_CONTI
+ * f32[B,emb] (action_is_f64 = 0) / f64[B,emb] (action_is_f64 = 1) embeddings resolved by
+ * get_nearest_neighbor_with_mask (slate.py:186-191). */
+int r4_step(r4_env* env, const void* action, int action_is_f64, const r4_out* out, void* stream);
+
+/* SlateState.offline_action / offline_reward (slate.py:149-174, seqslate.py:71-86).
+ * items: i32[B]; emb (conti mode, may be NULL): f64[B,emb_dim]; reward: f64[B]. */
+int r4_offline_action(r4_env* env, int32_t* items, double* emb, void* stream);
+int r4_offline_reward(r4_env* env, double* reward, void* stream);
+
+/* SlateState.get_violation (slate.py:133-147 / seqslate.py:52-69): i32[B] of 0/1. */
+int r4_violation(r4_env* env, int32_t* out, void* stream);
+
+/* SlateState.get_nearest_neighbor (static, unmasked; slate.py:180-184; tutorial.ipynb:251-254) */
+int r4_nearest_neighbor(r4_env* env, const void* action, int action_is_f64, int n, int32_t* out,
+                        void* stream);
+
+/* ---- introspection ----------------------------------------------------------------------- */
+int r4_cur_steps(const r4_env* env);                 /* SlateState.cur_steps */
+const int32_t* r4_prev_actions(const r4_env* env);   /* device i32[B,max_steps] (SlateState.prev_actions) */
+int r4_copy_prev_actions(r4_env* env, int32_t* out /*dev i32[B,max_steps]*/, void* stream);
+/* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int64_t r4_launch_count(const r4_env* env);
+/* algorithmic constants of the build */
+int r4_abi_version(void);
+
+/* ---- the simulator alone (nets/dien.py:8-45), for parity tests and kernel benchmarks ------- */
+/* seq i32[R,2,64], dense f32[R,432], cat i32[R,21] (device) -> obs f32[R,256], probs f32[R,2]
+ * (either may be NULL).  Runs the uncached path: GRU-1 is recomputed for every row. */
+int r4_dien_forward(r4_env* env, const int32_t* seq, const float* dense, const int32_t* cat,
+                    int n_rows, float* obs, float* probs, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL4RS_B200_H */

@@ -1,0 +1,657 @@
+// r4_capi.cu -- host side of librl4rs_b200.so: the C-ABI of include/rl4rs_b200.h over the
+// kernels of r4_kernels.cuh.  No torch, no Python: plain CUDA runtime.  See DESIGN.md.
+#include "../../include/rl4rs_b200.h"
+#include "r4_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace r4;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+struct SeqCache {   // one cached (sequence, weight-set): GRU-1 outputs + AUGRU/attention input halves
+  DevBuf H;         // f32 [n, 64, 128]
+  DevBuf XK;        // f32 [n, 64, 832]
+  int n = 0;
+};
+
+struct PerSeq {
+  float *gru_wx = nullptr, *gru_bx = nullptr, *gru_wgh = nullptr, *gru_wch = nullptr;
+  float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
+  float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
+  float abk = 0.f;
+};
+
+}  // namespace
+
+struct r4_env {
+  r4_config cfg;
+  int device = 0;
+  std::string err;
+  int64_t launches = 0;
+  int A = 0, words = 0, T = 0, P = 0, B = 0, seq = 0, emb_dim = 0, hash = 0;
+  int max_rows = 0;
+  // item tables
+  float* item_vec = nullptr;
+  double* price = nullptr;
+  uint8_t* special = nullptr;
+  double* action_emb = nullptr;
+  bool items_ready = false;
+  // weights
+  std::map<std::string, std::vector<float>> hw;
+  float *emb_cat = nullptr, *emb_seq = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
+  float *wo = nullptr, *bo = nullptr, *wr = nullptr, *br = nullptr;
+  PerSeq ps[2];
+  bool weights_ready = false;
+  std::vector<void*> owned;
+  // log (borrowed device pointers)
+  const int32_t* log_cat = nullptr;
+  const float* log_dense = nullptr;
+  const int32_t* log_seq = nullptr;
+  const int32_t* log_items = nullptr;
+  const uint8_t* log_fb = nullptr;
+  int64_t log_n = 0;
+  int log_slots = 0;
+  // episode state
+  int32_t* row_idx = nullptr;
+  int32_t* prev_actions = nullptr;
+  uint32_t* amask = nullptr;
+  uint8_t* sflag = nullptr;
+  int cur_steps = 0;
+  bool has_reset = false;
+  // caches
+  SeqCache c0, c1const, c1page;
+  bool c1_is_page = false;
+  // workspaces
+  DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1;
+};
+
+namespace {
+
+int fail(r4_env* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_error = msg;
+  return code;
+}
+
+#define R4_CUDA(e, call)                                                                   \
+  do {                                                                                     \
+    cudaError_t _st = (call);                                                              \
+    if (_st != cudaSuccess)                                                                \
+      return fail((e), R4_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_st)); \
+  } while (0)
+
+#define R4_LAUNCH_CHECK(e, name)                                                          \
+  do {                                                                                     \
+    (e)->launches++;                                                                       \
+    cudaError_t _st = cudaGetLastError();                                                  \
+    if (_st != cudaSuccess)                                                                \
+      return fail((e), R4_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_st));  \
+  } while (0)
+
+int reserve(r4_env* e, DevBuf& b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return R4_OK;
+  if (b.p) { R4_CUDA(e, cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+  cudaError_t st = cudaMalloc(&b.p, bytes);
+  if (st != cudaSuccess) return fail(e, R4_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(st));
+  b.bytes = bytes;
+  return R4_OK;
+}
+
+template <typename T>
+int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
+  void* p = nullptr;
+  cudaError_t st = cudaMalloc(&p, std::max<size_t>(h.size(), 1) * sizeof(T));
+  if (st != cudaSuccess) return fail(e, R4_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(st));
+  R4_CUDA(e, cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  e->owned.push_back(p);
+  *dptr = reinterpret_cast<T*>(p);
+  return R4_OK;
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+int gemm(r4_env* e, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
+         const float* W, const float* bias, float* C, int ldc, cudaStream_t st) {
+  if (M <= 0) return R4_OK;
+  if ((N & 3) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
+  dim3 grid((M + 127) / 128, (N + 127) / 128);
+  if (act) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, gather, W, bias, C, ldc);
+  else k_gemm<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, gather, W, bias, C, ldc);
+  R4_LAUNCH_CHECK(e, "k_gemm");
+  return R4_OK;
+}
+
+constexpr int SMEM_RECUR_128 = (128 * 64 * 2 + 64 * 64) * 4;
+constexpr int SMEM_RECUR_256 = (256 * 32 * 2 + 32 * 64) * 4;
+constexpr int SMEM_SCORES = SC_SMEM_FLOATS * 4;
+constexpr int SMEM_CAT = 4 * (NCAT * CAT_LD + NCAT * 24) * 4;
+
+// GRU-1 + input projections of one sequence set (nets/utils.py:113,120 and the x-halves of
+// :121-124).  ids: i32 [n,64] device.  Chunked so the input-projection scratch stays bounded.
+int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaStream_t st) {
+  int rc;
+  if ((rc = reserve(e, c.H, (size_t)n * MAXLEN * EMB * 4))) return rc;
+  if ((rc = reserve(e, c.XK, (size_t)n * MAXLEN * XK_LD * 4))) return rc;
+  c.n = n;
+  const PerSeq& w = e->ps[si];
+  const int chunk = 8192;
+  if ((rc = reserve(e, e->ws_xin, (size_t)std::min(n, chunk) * MAXLEN * XIN_LD * 4))) return rc;
+  float* xin = reinterpret_cast<float*>(e->ws_xin.p);
+  for (int s0 = 0; s0 < n; s0 += chunk) {
+    int ns = std::min(chunk, n - s0);
+    float* Hc = reinterpret_cast<float*>(c.H.p) + (size_t)s0 * MAXLEN * EMB;
+    float* XKc = reinterpret_cast<float*>(c.XK.p) + (size_t)s0 * MAXLEN * XK_LD;
+    // x_t [Wgx | Wcx] + [bg | bc] with the Embedding gather fused into the A operand
+    if ((rc = gemm(e, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx,
+                   w.gru_bx, xin, XIN_LD, st))) return rc;
+    RecurParams p{};
+    p.s[0].X = xin; p.s[0].Wgh = w.gru_wgh; p.s[0].Wch = w.gru_wch; p.s[0].scores = nullptr;
+    p.s[0].out = Hc; p.s[0].shared = 0;
+    p.R = ns; p.row0 = 0; p.div = 1; p.xld = XIN_LD; p.xoff_g = 0; p.xoff_c = 2 * EMB; p.out_ld = 0;
+    k_recur<128, false, true><<<dim3((ns + 63) / 64, 1), 256, SMEM_RECUR_128, st>>>(p);
+    R4_LAUNCH_CHECK(e, "k_recur<128>");
+    // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]
+    if ((rc = gemm(e, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx, w.au_bx, XKc, XK_LD, st))) return rc;
+  }
+  return R4_OK;
+}
+
+// One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
+int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const float* dense,
+                 const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
+                 float* p1_out, float* probs_out, cudaStream_t st) {
+  int rc;
+  if ((rc = reserve(e, e->ws_scores, (size_t)2 * R * MAXLEN * 4))) return rc;
+  if ((rc = reserve(e, e->ws_allf, (size_t)R * ALLF * 4))) return rc;
+  if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
+  float* scores = reinterpret_cast<float*>(e->ws_scores.p);
+  float* allf = reinterpret_cast<float*>(e->ws_allf.p);
+  float* tmp = reinterpret_cast<float*>(e->ws_tmp.p);
+  const SeqCache* cs[2] = {&c0, &c1};
+  int sh[2] = {shared0, shared1};
+  ScoreParams sp{};
+  RecurParams rp{};
+  for (int i = 0; i < 2; ++i) {
+    const PerSeq& w = e->ps[i];
+    ScoreSeq& s = sp.s[i];
+    s.H = reinterpret_cast<const float*>(cs[i]->H.p);
+    s.XK = reinterpret_cast<const float*>(cs[i]->XK.p);
+    s.Wqd = w.wqd; s.Wp = w.wp; s.b1 = w.ab1; s.W2 = w.aw2; s.b2 = w.ab2; s.kv = w.akv; s.bk = w.abk;
+    s.scores = scores + (size_t)i * R * MAXLEN;
+    s.shared = sh[i];
+    RecurSeq& q = rp.s[i];
+    q.X = s.XK; q.Wgh = w.au_wgh; q.Wch = w.au_wch; q.scores = s.scores;
+    q.out = allf + i * AUH; q.shared = sh[i];
+  }
+  sp.R = R; sp.row0 = row0; sp.div = div;
+  rp.R = R; rp.row0 = row0; rp.div = div; rp.xld = XK_LD; rp.xoff_g = 0; rp.xoff_c = XK_C; rp.out_ld = ALLF;
+  k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq);
+  R4_LAUNCH_CHECK(e, "k_scores");
+  k_recur<256, true, false><<<dim3((R + 31) / 32, 2), 256, SMEM_RECUR_256, st>>>(rp);
+  R4_LAUNCH_CHECK(e, "k_recur<256>");
+  k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, st>>>(R, cat, e->emb_cat, allf);
+  R4_LAUNCH_CHECK(e, "k_cat_attn");
+  if ((rc = gemm(e, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1, e->b1, tmp, HU, st))) return rc;
+  if ((rc = gemm(e, 1, R, HU, HU, tmp, HU, nullptr, e->w2, e->b2, allf + 2 * AUH, ALLF, st))) return rc;
+  float* obs = obs_out;
+  if (!obs) {
+    if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
+    obs = reinterpret_cast<float*>(e->ws_obs.p);
+  }
+  if ((rc = gemm(e, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo, e->bo, obs, OBSD, st))) return rc;
+  if (p1_out || probs_out) {
+    k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out);
+    R4_LAUNCH_CHECK(e, "k_reward_head");
+  }
+  return R4_OK;
+}
+
+int assemble(r4_env* e, int mode, int step, int rpe, int row0, int nrows, int32_t* cat, float* dense,
+             cudaStream_t st) {
+  AsmParams p{mode, e->B, e->T, e->P, e->seq, step, rpe, row0, nrows};
+  k_assemble<<<(nrows + 3) / 4, 128, 0, st>>>(p, e->row_idx, e->log_cat, e->log_dense, e->item_vec,
+                                               e->prev_actions, cat, dense);
+  R4_LAUNCH_CHECK(e, "k_assemble");
+  return R4_OK;
+}
+
+const SeqCache& seq1_cache(const r4_env* e) { return e->c1_is_page ? e->c1page : e->c1const; }
+
+// obs pass for the current state (mode 0 after reset, mode 1 after act at `step`)
+int obs_pass(r4_env* e, int mode, int step, const r4_out* out, cudaStream_t st) {
+  int rc;
+  const int B = e->B;
+  bool raw = (e->cfg.flags & R4_FLAG_RAWSTATE) != 0;
+  bool need_obs = out && out->obs && !raw;
+  bool need_feat = out && (out->cat || out->dense);
+  if (!need_obs && !need_feat) return R4_OK;
+  int chunk = need_obs ? std::min(B, e->max_rows) : B;
+  for (int r0 = 0; r0 < B; r0 += chunk) {
+    int nr = std::min(chunk, B - r0);
+    int32_t* cat = (out && out->cat) ? out->cat + (size_t)r0 * NCAT : nullptr;
+    float* dense = (out && out->dense) ? out->dense + (size_t)r0 * NDENSE : nullptr;
+    if (!cat) { if ((rc = reserve(e, e->ws_cat, (size_t)chunk * NCAT * 4))) return rc; cat = (int32_t*)e->ws_cat.p; }
+    if (!dense) { if ((rc = reserve(e, e->ws_dense, (size_t)chunk * NDENSE * 4))) return rc; dense = (float*)e->ws_dense.p; }
+    if ((rc = assemble(e, mode, step, 1, r0, nr, cat, dense, st))) return rc;
+    if (need_obs) {
+      const SeqCache& c1 = seq1_cache(e);
+      if ((rc = forward_rows(e, nr, r0, 1, cat, dense, e->c0, 0, c1, e->c1_is_page ? 0 : 1,
+                             out->obs + (size_t)r0 * OBSD, nullptr, nullptr, st))) return rc;
+    }
+  }
+  return R4_OK;
+}
+
+// reward pass: rpe rows per env row (slate.py:286-302 / seqslate.py:138-153)
+int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st) {
+  int rc;
+  const int B = e->B;
+  const int rpe = e->seq ? e->P : e->T;
+  if ((rc = reserve(e, e->ws_p1, (size_t)B * rpe * 4))) return rc;
+  float* p1 = reinterpret_cast<float*>(e->ws_p1.p);
+  int envs_per_chunk = std::max(1, e->max_rows / rpe);
+  for (int b0 = 0; b0 < B; b0 += envs_per_chunk) {
+    int nb = std::min(envs_per_chunk, B - b0);
+    int nr = nb * rpe;
+    if ((rc = reserve(e, e->ws_cat, (size_t)std::max(nr, 1) * NCAT * 4))) return rc;
+    if ((rc = reserve(e, e->ws_dense, (size_t)std::max(nr, 1) * NDENSE * 4))) return rc;
+    int32_t* cat = (int32_t*)e->ws_cat.p;
+    float* dense = (float*)e->ws_dense.p;
+    if ((rc = assemble(e, 2, cur_after, rpe, b0 * rpe, nr, cat, dense, st))) return rc;
+    const SeqCache& c1 = seq1_cache(e);
+    if ((rc = forward_rows(e, nr, b0 * rpe, rpe, cat, dense, e->c0, 0, c1, e->c1_is_page ? 0 : 1, nullptr,
+                           p1 + (size_t)b0 * rpe, nullptr, st))) return rc;
+  }
+  int zero = 1;                                                   // slate.py:303 `if 1:`
+  if (e->seq) zero = (e->cfg.flags & (R4_FLAG_RLLIB_MASK | R4_FLAG_D3RL_MASK)) ? 1 : 0;   // seqslate.py:154-157
+  float* click = (out && out->click_p && (e->cfg.flags & R4_FLAG_INFO_FETCH)) ? out->click_p : nullptr;
+  k_reward<<<(B + 127) / 128, 128, 0, st>>>(B, e->T, e->P, e->seq, cur_after, zero, e->prev_actions, e->special,
+                                             e->price, p1, rpe, out->reward, click);
+  R4_LAUNCH_CHECK(e, "k_reward");
+  return R4_OK;
+}
+
+int write_masked_actions(r4_env* e, const r4_out* out, cudaStream_t st) {
+  if (!out || !out->masked_actions) return R4_OK;
+  int w0 = 0, W = e->T;
+  if (e->seq) {                                                   // seqslate.py:20-22
+    int p0 = e->cur_steps / e->P * e->P;
+    int pe = std::min(p0 + e->P - 1, e->T - 1);
+    w0 = pe + 1 - e->P; W = e->P;
+  }
+  k_masked_actions<<<(e->B * W + 255) / 256, 256, 0, st>>>(e->B, e->T, w0, W, e->prev_actions, out->masked_actions);
+  R4_LAUNCH_CHECK(e, "k_masked_actions");
+  return R4_OK;
+}
+
+const float* hw_get(r4_env* e, const std::string& name, size_t n) {
+  auto it = e->hw.find(name);
+  if (it == e->hw.end() || it->second.size() != n) return nullptr;
+  return it->second.data();
+}
+
+}  // namespace
+
+extern "C" {
+
+int r4_abi_version(void) { return 1; }
+
+const char* r4_last_error(const r4_env* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
+
+int r4_create(const r4_config* cfg, int device, r4_env** out) {
+  if (!cfg || !out) return fail(nullptr, R4_ERR_ARG, "r4_create: null argument");
+  *out = nullptr;
+  if (cfg->maxlen != MAXLEN || cfg->seq_num != 2 || cfg->dense_feature_num != NDENSE ||
+      cfg->category_feature_num != NCAT || cfg->emb_size != EMB || cfg->hidden_units != HU ||
+      cfg->page_items != PAGE)
+    return fail(nullptr, R4_ERR_ARG,
+                "r4_create: this build is specialised for maxlen=64 seq_num=2 dense_feature_num=432 "
+                "category_feature_num=21 emb_size=128 hidden_units=128 page_items=9");
+  if (cfg->batch_size < 1 || cfg->max_steps < 3 || cfg->action_size < 149 || cfg->action_size > 32 * MAX_WORDS)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: need batch_size>=1, max_steps>=3, 149<=action_size<=512");
+  if (cfg->env_kind == R4_ENV_SLATE && cfg->max_steps > 11)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: SlateRecEnv needs max_steps<=11 (location_mask has 4 layers, slate.py:60-64,93)");
+  if (cfg->env_kind == R4_ENV_SEQSLATE && cfg->max_steps % cfg->page_items != 0)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: SeqSlateRecEnv needs max_steps to be a multiple of page_items");
+  if (cfg->category_hash_size < cfg->action_size)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: category_hash_size must cover the item ids");
+  cudaError_t st = cudaSetDevice(device);
+  if (st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(st));
+  r4_env* e = new r4_env();
+  e->cfg = *cfg;
+  e->device = device;
+  e->A = cfg->action_size; e->words = (e->A + 31) / 32; e->T = cfg->max_steps; e->P = cfg->page_items;
+  e->B = cfg->batch_size; e->seq = cfg->env_kind == R4_ENV_SEQSLATE; e->hash = cfg->category_hash_size;
+  e->max_rows = cfg->max_rows_per_pass > 0 ? cfg->max_rows_per_pass : 36864;
+  bool ok = cudaMalloc(&e->row_idx, (size_t)e->B * 4) == cudaSuccess &&
+            cudaMalloc(&e->prev_actions, (size_t)e->B * e->T * 4) == cudaSuccess &&
+            cudaMalloc(&e->amask, (size_t)e->B * e->words * 4) == cudaSuccess &&
+            cudaMalloc(&e->sflag, (size_t)e->B) == cudaSuccess;
+  if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
+  cudaFuncSetAttribute(k_recur<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_128);
+  cudaFuncSetAttribute(k_recur<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_256);
+  cudaFuncSetAttribute(k_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SCORES);
+  cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
+  st = cudaGetLastError();
+  if (st != cudaSuccess) { r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(st)); }
+  *out = e;
+  return R4_OK;
+}
+
+void r4_destroy(r4_env* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->owned) cudaFree(p);
+  void* own[] = {e->row_idx, e->prev_actions, e->amask, e->sflag, e->item_vec, e->price, e->special, e->action_emb};
+  for (void* p : own) if (p) cudaFree(p);
+  DevBuf* bufs[] = {&e->c0.H, &e->c0.XK, &e->c1const.H, &e->c1const.XK, &e->c1page.H, &e->c1page.XK,
+                    &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
+                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1};
+  for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  delete e;
+}
+
+int r4_load_items(r4_env* e, const double* item_vec, int vec_dim, const double* price, const uint8_t* special,
+                  const double* action_emb, int emb_dim, int n) {
+  if (!e || !item_vec || !price || !special || !action_emb) return fail(e, R4_ERR_ARG, "r4_load_items: null argument");
+  if (n != e->A) return fail(e, R4_ERR_ARG, "r4_load_items: n must equal action_size");
+  if (vec_dim != VEC) return fail(e, R4_ERR_ARG, "r4_load_items: item vectors must have 40 dims");
+  int want = (e->cfg.flags & R4_FLAG_ONEHOT) ? e->A : e->cfg.action_emb_size;
+  if (emb_dim != want) return fail(e, R4_ERR_ARG, "r4_load_items: emb_dim does not match the config");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  std::vector<float> v32((size_t)n * VEC);
+  for (size_t i = 0; i < v32.size(); ++i) v32[i] = (float)item_vec[i];     // f64 text -> f32 (datautil.py:52-58)
+  void* olds[] = {e->item_vec, e->price, e->special, e->action_emb};
+  for (void* p : olds) if (p) cudaFree(p);
+  e->item_vec = nullptr; e->price = nullptr; e->special = nullptr; e->action_emb = nullptr;
+  R4_CUDA(e, cudaMalloc(&e->item_vec, v32.size() * 4));
+  R4_CUDA(e, cudaMalloc(&e->price, (size_t)n * 8));
+  R4_CUDA(e, cudaMalloc(&e->special, (size_t)n));
+  R4_CUDA(e, cudaMalloc(&e->action_emb, (size_t)n * emb_dim * 8));
+  R4_CUDA(e, cudaMemcpy(e->item_vec, v32.data(), v32.size() * 4, cudaMemcpyHostToDevice));
+  R4_CUDA(e, cudaMemcpy(e->price, price, (size_t)n * 8, cudaMemcpyHostToDevice));
+  R4_CUDA(e, cudaMemcpy(e->special, special, (size_t)n, cudaMemcpyHostToDevice));
+  R4_CUDA(e, cudaMemcpy(e->action_emb, action_emb, (size_t)n * emb_dim * 8, cudaMemcpyHostToDevice));
+  e->emb_dim = emb_dim;
+  e->items_ready = true;
+  return R4_OK;
+}
+
+int r4_load_weight(r4_env* e, const char* name, const float* data, const int64_t* shape, int rank) {
+  if (!e || !name || !data || !shape || rank < 1) return fail(e, R4_ERR_ARG, "r4_load_weight: bad argument");
+  size_t n = 1;
+  for (int i = 0; i < rank; ++i) n *= (size_t)shape[i];
+  R4_CUDA(e, cudaSetDevice(e->device));
+  std::vector<float>& v = e->hw[name];
+  v.resize(n);
+  R4_CUDA(e, cudaMemcpy(v.data(), data, n * 4, cudaMemcpyDefault));
+  e->weights_ready = false;
+  return R4_OK;
+}
+
+int r4_finalize_weights(r4_env* e, void* stream) {
+  if (!e) return R4_ERR_ARG;
+  R4_CUDA(e, cudaSetDevice(e->device));
+  const size_t Hh = (size_t)e->hash;
+  struct Need { const char* n; size_t sz; };
+  std::vector<Need> need = {{"emb_cat", Hh * EMB}, {"emb_seq", Hh * EMB}, {"dense_w1", (size_t)NDENSE * HU},
+                            {"dense_b1", HU}, {"dense_w2", (size_t)HU * HU}, {"dense_b2", HU},
+                            {"obs_w", (size_t)ALLF * OBSD}, {"obs_b", OBSD}, {"rew_w", OBSD * 2}, {"rew_b", 2}};
+  for (auto& nd : need)
+    if (!hw_get(e, nd.n, nd.sz)) return fail(e, R4_ERR_ARG, std::string("r4_finalize_weights: missing or mis-shaped ") + nd.n);
+  for (void* p : e->owned) cudaFree(p);
+  e->owned.clear();
+  int rc;
+#define UP(dst, nm) if ((rc = upload(e, e->hw[nm], &(dst)))) return rc;
+  UP(e->emb_cat, "emb_cat"); UP(e->emb_seq, "emb_seq"); UP(e->w1, "dense_w1"); UP(e->b1, "dense_b1");
+  UP(e->w2, "dense_w2"); UP(e->b2, "dense_b2"); UP(e->wo, "obs_w"); UP(e->bo, "obs_b");
+  UP(e->wr, "rew_w"); UP(e->br, "rew_b");
+#undef UP
+  for (int i = 0; i < 2; ++i) {
+    std::string si = std::to_string(i);
+    const float* gwg = hw_get(e, "gru" + si + "_wg", (size_t)2 * EMB * 2 * EMB);
+    const float* gbg = hw_get(e, "gru" + si + "_bg", 2 * EMB);
+    const float* gwc = hw_get(e, "gru" + si + "_wc", (size_t)2 * EMB * EMB);
+    const float* gbc = hw_get(e, "gru" + si + "_bc", EMB);
+    const float* aw1 = hw_get(e, "att" + si + "_w1", (size_t)4 * EMB * AH1);
+    const float* ab1 = hw_get(e, "att" + si + "_b1", AH1);
+    const float* aw2 = hw_get(e, "att" + si + "_w2", (size_t)AH1 * AH2);
+    const float* ab2 = hw_get(e, "att" + si + "_b2", AH2);
+    const float* akv = hw_get(e, "att" + si + "_k", AH2);
+    const float* abk = hw_get(e, "att" + si + "_b", 1);
+    const float* uwg = hw_get(e, "augru" + si + "_wg", (size_t)(EMB + AUH) * 2 * AUH);
+    const float* ubg = hw_get(e, "augru" + si + "_bg", 2 * AUH);
+    const float* uwc = hw_get(e, "augru" + si + "_wc", (size_t)(EMB + AUH) * AUH);
+    const float* ubc = hw_get(e, "augru" + si + "_bc", AUH);
+    if (!gwg || !gbg || !gwc || !gbc || !aw1 || !ab1 || !aw2 || !ab2 || !akv || !abk || !uwg || !ubg || !uwc || !ubc)
+      return fail(e, R4_ERR_ARG, "r4_finalize_weights: missing or mis-shaped per-sequence weight (seq " + si + ")");
+    PerSeq& w = e->ps[i];
+    // GRU-1 (TF1 GRUCell): gate kernel [x;h] x [r|u], candidate kernel [x;h] x c
+    std::vector<float> wx((size_t)EMB * XIN_LD), bx(XIN_LD), wgh((size_t)EMB * 2 * EMB), wch((size_t)EMB * EMB);
+    for (int k = 0; k < EMB; ++k) {
+      for (int n = 0; n < 2 * EMB; ++n) wx[(size_t)k * XIN_LD + n] = gwg[(size_t)k * 2 * EMB + n];
+      for (int n = 0; n < EMB; ++n) wx[(size_t)k * XIN_LD + 2 * EMB + n] = gwc[(size_t)k * EMB + n];
+      for (int n = 0; n < 2 * EMB; ++n) wgh[(size_t)k * 2 * EMB + n] = gwg[(size_t)(EMB + k) * 2 * EMB + n];
+      for (int n = 0; n < EMB; ++n) wch[(size_t)k * EMB + n] = gwc[(size_t)(EMB + k) * EMB + n];
+    }
+    for (int n = 0; n < 2 * EMB; ++n) bx[n] = gbg[n];
+    for (int n = 0; n < EMB; ++n) bx[2 * EMB + n] = gbc[n];
+    // AUGRU (VecAttGRUCell) input halves + attention key half
+    std::vector<float> awx((size_t)EMB * XK_LD), abx(XK_LD, 0.f), awgh((size_t)AUH * 2 * AUH), awch((size_t)AUH * AUH);
+    std::vector<float> wqd((size_t)EMB * AH1), wp((size_t)EMB * AH1);
+    for (int k = 0; k < EMB; ++k) {
+      for (int n = 0; n < 2 * AUH; ++n) awx[(size_t)k * XK_LD + n] = uwg[(size_t)k * 2 * AUH + n];
+      for (int n = 0; n < AUH; ++n) awx[(size_t)k * XK_LD + XK_C + n] = uwc[(size_t)k * AUH + n];
+      for (int n = 0; n < AH1; ++n) {
+        float wq = aw1[(size_t)k * AH1 + n], wk = aw1[(size_t)(EMB + k) * AH1 + n];
+        float wd = aw1[(size_t)(2 * EMB + k) * AH1 + n], wpp = aw1[(size_t)(3 * EMB + k) * AH1 + n];
+        awx[(size_t)k * XK_LD + XK_K + n] = wk - wd;        // keys * (Wk - Wd)
+        wqd[(size_t)k * AH1 + n] = wq + wd;                 // query * (Wq + Wd)
+        wp[(size_t)k * AH1 + n] = wpp;                      // (query*keys) * Wp
+      }
+    }
+    for (int n = 0; n < 2 * AUH; ++n) abx[n] = ubg[n];
+    for (int n = 0; n < AUH; ++n) abx[XK_C + n] = ubc[n];
+    for (int k = 0; k < AUH; ++k) {
+      for (int n = 0; n < 2 * AUH; ++n) awgh[(size_t)k * 2 * AUH + n] = uwg[(size_t)(EMB + k) * 2 * AUH + n];
+      for (int n = 0; n < AUH; ++n) awch[(size_t)k * AUH + n] = uwc[(size_t)(EMB + k) * AUH + n];
+    }
+    std::vector<float> vb1(ab1, ab1 + AH1), vw2(aw2, aw2 + AH1 * AH2), vb2(ab2, ab2 + AH2), vkv(akv, akv + AH2);
+    if ((rc = upload(e, wx, &w.gru_wx)) || (rc = upload(e, bx, &w.gru_bx)) || (rc = upload(e, wgh, &w.gru_wgh)) ||
+        (rc = upload(e, wch, &w.gru_wch)) || (rc = upload(e, awx, &w.au_wx)) || (rc = upload(e, abx, &w.au_bx)) ||
+        (rc = upload(e, awgh, &w.au_wgh)) || (rc = upload(e, awch, &w.au_wch)) || (rc = upload(e, wqd, &w.wqd)) ||
+        (rc = upload(e, wp, &w.wp)) || (rc = upload(e, vb1, &w.ab1)) || (rc = upload(e, vw2, &w.aw2)) ||
+        (rc = upload(e, vb2, &w.ab2)) || (rc = upload(e, vkv, &w.akv)))
+      return rc;
+    w.abk = abk[0];
+  }
+  e->hw.clear();
+  e->weights_ready = true;
+  // SlateRecEnv's second sequence is the constant [0] (slate.py:75 -> 64 x id 0): cache it once.
+  cudaStream_t st = S(stream);
+  if ((rc = reserve(e, e->ws_ids1, (size_t)std::max(e->B, 1) * MAXLEN * 4))) return rc;
+  R4_CUDA(e, cudaMemsetAsync(e->ws_ids1.p, 0, (size_t)MAXLEN * 4, st));
+  if ((rc = build_cache(e, 1, reinterpret_cast<const int32_t*>(e->ws_ids1.p), 1, e->c1const, st))) return rc;
+  return R4_OK;
+}
+
+int r4_load_log(r4_env* e, const int32_t* user_cat, const float* user_dense, const int32_t* user_seq,
+                const int32_t* logged_items, const uint8_t* feedback, int64_t n_rows, int n_slots) {
+  if (!e || !user_cat || !user_dense || !user_seq || !logged_items || !feedback || n_rows < 1 || n_slots < 1)
+    return fail(e, R4_ERR_ARG, "r4_load_log: bad argument");
+  if (n_rows > 0x7fffffffLL) return fail(e, R4_ERR_ARG, "r4_load_log: more than 2^31-1 rows");
+  e->log_cat = user_cat; e->log_dense = user_dense; e->log_seq = user_seq; e->log_items = logged_items;
+  e->log_fb = feedback; e->log_n = n_rows; e->log_slots = n_slots;
+  e->has_reset = false;
+  return R4_OK;
+}
+
+int r4_reset(r4_env* e, const int32_t* row_idx, const r4_out* out, void* stream) {
+  if (!e || !row_idx) return fail(e, R4_ERR_ARG, "r4_reset: null argument");
+  if (!e->weights_ready || !e->items_ready || !e->log_cat)
+    return fail(e, R4_ERR_STATE, "r4_reset: load items, weights (+finalize) and log first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  int rc;
+  const int B = e->B;
+  R4_CUDA(e, cudaMemcpyAsync(e->row_idx, row_idx, (size_t)B * 4, cudaMemcpyDeviceToDevice, st));
+  e->cur_steps = 0;
+  e->c1_is_page = false;
+  k_init_state<<<(B + 3) / 4, 128, 0, st>>>(B, e->T, e->A, e->words, e->prev_actions, e->amask, e->sflag,
+                                             out ? out->action_mask : nullptr, 0);
+  R4_LAUNCH_CHECK(e, "k_init_state");
+  if ((rc = reserve(e, e->ws_ids0, (size_t)B * MAXLEN * 4))) return rc;
+  k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, 0, e->row_idx, e->log_seq, e->prev_actions,
+                                                       (int32_t*)e->ws_ids0.p, nullptr, out ? out->seq : nullptr);
+  R4_LAUNCH_CHECK(e, "k_seq_ids");
+  e->has_reset = true;
+  // user-history GRU-1 + input projections: once per episode (they do not depend on the actions)
+  if ((rc = build_cache(e, 0, (const int32_t*)e->ws_ids0.p, B, e->c0, st))) return rc;
+  if ((rc = obs_pass(e, 0, 0, out, st))) return rc;
+  if (out && out->reward) { k_fill_f64<<<(B + 255) / 256, 256, 0, st>>>(B, 0.0, out->reward); R4_LAUNCH_CHECK(e, "k_fill_f64"); }
+  if (out && out->done) { k_fill_u8<<<(B + 255) / 256, 256, 0, st>>>(B, 0, out->done); R4_LAUNCH_CHECK(e, "k_fill_u8"); }
+  if ((rc = write_masked_actions(e, out, st))) return rc;
+  return R4_OK;
+}
+
+int r4_step(r4_env* e, const void* action, int action_is_f64, const r4_out* out, void* stream) {
+  if (!e || !action) return fail(e, R4_ERR_ARG, "r4_step: null argument");
+  if (!e->has_reset) return fail(e, R4_ERR_STATE, "r4_step: reset first");
+  if (e->cur_steps >= e->T)   // the reference raises IndexError at slate.py:198
+    return fail(e, R4_ERR_STATE, "r4_step: episode is over (cur_steps == max_steps)");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  int rc;
+  const int B = e->B, cur = e->cur_steps;
+  bool conti = (e->cfg.flags & R4_FLAG_CONTI) != 0;
+  // SeqSlate: entering a new page, the second sequence becomes the items of all previous pages
+  // (seqslate.py:109-110) -> rebuild its GRU-1 cache once per page.
+  if (e->seq && cur > 0 && cur % e->P == 0) {
+    if ((rc = reserve(e, e->ws_ids1, (size_t)B * MAXLEN * 4))) return rc;
+    k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, cur, e->row_idx, e->log_seq, e->prev_actions,
+                                                         nullptr, (int32_t*)e->ws_ids1.p, nullptr);
+    R4_LAUNCH_CHECK(e, "k_seq_ids");
+    if ((rc = build_cache(e, 1, (const int32_t*)e->ws_ids1.p, B, e->c1page, st))) return rc;
+    e->c1_is_page = true;
+  }
+  ActParams ap{B, e->T, e->P, e->A, e->words, e->seq, conti ? 1 : 0, e->emb_dim, cur, action_is_f64};
+  k_act<<<(B + 3) / 4, 128, 0, st>>>(ap, action, e->action_emb, e->special, e->prev_actions, e->amask, e->sflag,
+                                      out ? out->chosen : nullptr, out ? out->action_mask : nullptr);
+  R4_LAUNCH_CHECK(e, "k_act");
+  e->cur_steps = cur + 1;
+  if (out && out->seq) {
+    int p0 = e->seq ? cur / e->P * e->P : 0;
+    k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, p0, e->row_idx, e->log_seq, e->prev_actions,
+                                                         nullptr, nullptr, out->seq);
+    R4_LAUNCH_CHECK(e, "k_seq_ids");
+  }
+  if ((rc = obs_pass(e, 1, cur, out, st))) return rc;
+  if (out && out->reward) {
+    bool pay = e->seq ? (e->cur_steps % e->P == 0) : (e->cur_steps >= e->T);
+    if (pay) { if ((rc = reward_pass(e, e->cur_steps, out, st))) return rc; }
+    else { k_fill_f64<<<(B + 255) / 256, 256, 0, st>>>(B, 0.0, out->reward); R4_LAUNCH_CHECK(e, "k_fill_f64"); }
+  }
+  if (out && out->done) {       // base.py:165-168 with the pre-increment step (Q1)
+    k_fill_u8<<<(B + 255) / 256, 256, 0, st>>>(B, cur < e->T - 1 ? 0 : 1, out->done);
+    R4_LAUNCH_CHECK(e, "k_fill_u8");
+  }
+  if ((rc = write_masked_actions(e, out, st))) return rc;
+  return R4_OK;
+}
+
+int r4_offline_action(r4_env* e, int32_t* items, double* emb, void* stream) {
+  if (!e || (!items && !emb)) return fail(e, R4_ERR_ARG, "r4_offline_action: null argument");
+  if (!e->has_reset) return fail(e, R4_ERR_STATE, "r4_offline_action: reset first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  k_offline_action<<<(e->B + 3) / 4, 128, 0, S(stream)>>>(e->B, e->log_slots, e->cur_steps, e->T, e->emb_dim,
+                                                         e->row_idx, e->log_items, e->action_emb, items, emb);
+  R4_LAUNCH_CHECK(e, "k_offline_action");
+  return R4_OK;
+}
+
+int r4_offline_reward(r4_env* e, double* reward, void* stream) {
+  if (!e || !reward) return fail(e, R4_ERR_ARG, "r4_offline_reward: null argument");
+  if (!e->has_reset) return fail(e, R4_ERR_STATE, "r4_offline_reward: reset first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  int c = e->cur_steps, lo = 0, hi = 0;
+  if (e->seq) {                       // seqslate.py:71-86 (hard-coded 9 at :74)
+    if (c % 9 == 0 && c > 0) { lo = c - e->P; hi = c; }
+  } else if (c >= e->T) { lo = 0; hi = e->log_slots; }   // slate.py:164-174: every logged slot
+  if (hi > e->log_slots) hi = e->log_slots;
+  k_offline_reward<<<(e->B + 127) / 128, 128, 0, S(stream)>>>(e->B, e->log_slots, lo, hi, e->row_idx, e->log_items,
+                                                              e->log_fb, e->price, reward);
+  R4_LAUNCH_CHECK(e, "k_offline_reward");
+  return R4_OK;
+}
+
+int r4_violation(r4_env* e, int32_t* out, void* stream) {
+  if (!e || !out) return fail(e, R4_ERR_ARG, "r4_violation: null argument");
+  if (!e->has_reset) return fail(e, R4_ERR_STATE, "r4_violation: reset first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  k_violation<<<(e->B + 127) / 128, 128, 0, S(stream)>>>(e->B, e->T, e->P, e->seq, e->cur_steps, e->prev_actions,
+                                                         e->special, out);
+  R4_LAUNCH_CHECK(e, "k_violation");
+  return R4_OK;
+}
+
+int r4_nearest_neighbor(r4_env* e, const void* action, int action_is_f64, int n, int32_t* out, void* stream) {
+  if (!e || !action || !out || n < 1) return fail(e, R4_ERR_ARG, "r4_nearest_neighbor: bad argument");
+  if (!e->items_ready) return fail(e, R4_ERR_STATE, "r4_nearest_neighbor: load items first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  k_knn_plain<<<(n + 3) / 4, 128, 0, S(stream)>>>(n, e->A, e->emb_dim, action_is_f64, action, e->action_emb, out);
+  R4_LAUNCH_CHECK(e, "k_knn_plain");
+  return R4_OK;
+}
+
+int r4_cur_steps(const r4_env* e) { return e ? e->cur_steps : -1; }
+const int32_t* r4_prev_actions(const r4_env* e) { return e ? e->prev_actions : nullptr; }
+int64_t r4_launch_count(const r4_env* e) { return e ? e->launches : 0; }
+
+int r4_copy_prev_actions(r4_env* e, int32_t* out, void* stream) {
+  if (!e || !out) return fail(e, R4_ERR_ARG, "r4_copy_prev_actions: null argument");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  R4_CUDA(e, cudaMemcpyAsync(out, e->prev_actions, (size_t)e->B * e->T * 4, cudaMemcpyDeviceToDevice, S(stream)));
+  return R4_OK;
+}
+
+int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int32_t* cat, int n_rows,
+                    float* obs, float* probs, void* stream) {
+  if (!e || !seq || !dense || !cat || n_rows < 1) return fail(e, R4_ERR_ARG, "r4_dien_forward: bad argument");
+  if (!e->weights_ready) return fail(e, R4_ERR_STATE, "r4_dien_forward: load + finalize weights first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  int rc;
+  SeqCache t0, t1;
+  DevBuf ids;
+  if ((rc = reserve(e, ids, (size_t)2 * n_rows * MAXLEN * 4))) return rc;
+  int32_t* i0 = (int32_t*)ids.p;
+  int32_t* i1 = i0 + (size_t)n_rows * MAXLEN;
+  R4_CUDA(e, cudaMemcpy2DAsync(i0, MAXLEN * 4, seq, 2 * MAXLEN * 4, MAXLEN * 4, n_rows, cudaMemcpyDeviceToDevice, st));
+  R4_CUDA(e, cudaMemcpy2DAsync(i1, MAXLEN * 4, seq + MAXLEN, 2 * MAXLEN * 4, MAXLEN * 4, n_rows, cudaMemcpyDeviceToDevice, st));
+  rc = build_cache(e, 0, i0, n_rows, t0, st);
+  if (!rc) rc = build_cache(e, 1, i1, n_rows, t1, st);
+  int chunk = std::min(n_rows, e->max_rows);
+  for (int r0 = 0; !rc && r0 < n_rows; r0 += chunk) {
+    int nr = std::min(chunk, n_rows - r0);
+    rc = forward_rows(e, nr, r0, 1, cat + (size_t)r0 * NCAT, dense + (size_t)r0 * NDENSE, t0, 0, t1, 0,
+                      obs ? obs + (size_t)r0 * OBSD : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
+  }
+  cudaStreamSynchronize(st);
+  DevBuf* tmp[] = {&t0.H, &t0.XK, &t1.H, &t1.XK, &ids};
+  for (DevBuf* b : tmp) if (b->p) cudaFree(b->p);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+"""Host mirror of rl4rs/env/base.py: RecState, RecDataBase, RecSimBase, RecEnvBase.
+
+Same class names, constructor arguments, methods, properties, return conventions and error
+behaviour as the reference, so callers written against it (README.md:8-21, simulator_eval.py,
+batchrl_trainer.py:172-197, exact_k_train.py:75-87, rllib_vector_env.py) run unchanged.  What
+differs is where the work happens: the file sampler is a cursor over row indices of an
+HBM-resident log (no per-reset parsing), and ``act`` + ``obs_fn`` + ``forward`` of one step are
+ONE call into the CUDA library (rl4rs_b200/engine.py) whose results the three methods hand out.
+
+``config['output_format']`` (an addition; unknown keys are ignored by the reference):
+  'list'  (default) reference-compatible Python lists / list of dicts;
+  'numpy' batched host arrays (obs dict of arrays), no per-row Python objects;
+  'torch' device tensors, no host synchronisation at all.
+"""
+from abc import ABC, abstractmethod
+
+import numpy as np
+
+from .. import gymshim as gym
+from ..synth import Catalog, LogSoA
+from ..utils.datautil import FeatureUtil
+
+
+def single_elem_support(func):
+    """batch_size == 1 returns scalars instead of 1-element lists (base.py:9-23)."""
+    type_list = (list, tuple, np.ndarray)
+
+    def wrapper(*args, **kwargs):
+        res = func(*args, **kwargs)
+        if type(res) in type_list and len(res) == 1:
+            return res[0]
+        elif type(res) in type_list and len(res) and type(res[0]) in type_list and len(res[0]) == 1:
+            return [x[0] for x in res]
+        return res
+
+    return wrapper
+
+
+class RecState(ABC):
+    """State plug-in protocol (base.py:26-57)."""
+
+    def __init__(self, config, records):
+        self.config = config
+        self.records = records
+
+    @property
+    @abstractmethod
+    def state(self):
+        pass
+
+    @property
+    @abstractmethod
+    def user(self):
+        pass
+
+    @property
+    @abstractmethod
+    def info(self):
+        pass
+
+    @abstractmethod
+    def act(self, actions):
+        pass
+
+    @abstractmethod
+    def to_string(self):
+        pass
+
+
+class RecDataBase(object):
+    """The file-based sampler of base.py:60-108 as a cursor over rows of the resident log.
+
+    Semantics kept: ``cache_size`` windows read sequentially; at EOF the file pointer rewinds,
+    one line is discarded and the next one is served (base.py:85-88); eval mode serves the first
+    ``batch_size`` rows of the window and requires cache_size == batch_size (base.py:93-96);
+    otherwise rows are drawn with replacement through the GLOBAL numpy RNG (base.py:98), which
+    ``seed`` seeds (base.py:78-80)."""
+
+    def __init__(self, config, state_cls, engine=None):
+        self.config = config
+        self.sample_list = []
+        self.state_cls = state_cls
+        self.is_eval = config.get("is_eval", False)
+        self.cache_size = config.get("cache_size", 2048)
+        self.engine = engine
+        self.n_rows = engine.log.n
+        self.pos = 0
+
+    @staticmethod
+    def seed(seed):
+        np.random.seed(seed)
+
+    def sample_cache(self, num):
+        for _ in range(num):
+            if self.pos >= self.n_rows:
+                self.pos = 1 if self.n_rows > 1 else 0
+            self.sample_list.append(self.pos)
+            self.pos += 1
+
+    def sample(self, batch_size):
+        if self.is_eval:
+            assert self.cache_size == batch_size
+            assert len(self.sample_list) == batch_size
+            rows = np.asarray(self.sample_list[:batch_size], dtype=np.int64)
+        else:
+            idx = np.random.randint(0, len(self.sample_list), batch_size)
+            rows = np.asarray(self.sample_list, dtype=np.int64)[idx]
+        return self.state_cls(self.config, rows, self.engine)
+
+    def reset(self, reset_file=False):
+        self.sample_list = []
+        if reset_file:
+            self.pos = 0
+        self.sample_cache(self.cache_size)
+
+
+class RecSimBase(ABC):
+    """Simulator plug-in (base.py:111-175).  ``get_model`` loads the DIEN W-table onto the GPU."""
+
+    seq = False
+
+    def __init__(self, config, state_cls):
+        from ..engine import Engine   # needs CUDA; deferred so the host classes import on CPU
+        self.config = config
+        self.max_steps = config["max_steps"]
+        self.batch_size = config["batch_size"]
+        self.output_format = config.get("output_format", "list")
+        if self.output_format not in ("list", "numpy", "torch"):
+            raise ValueError("output_format must be 'list', 'numpy' or 'torch'")
+        catalog = config.get("catalog")
+        if catalog is None:
+            catalog = Catalog.from_file(config["iteminfo_file"])
+        log = config.get("log")
+        if log is None:
+            log = FeatureUtil.load_log(config["sample_file"], config.get("maxlen", 64))
+        assert isinstance(log, LogSoA)
+        self.model = self.get_model(config)
+        self.engine = Engine(config, self.seq, catalog, self.model, log, device=config.get("device"))
+        self._recData = RecDataBase(config, state_cls, self.engine)
+
+    def reset(self, reset_file=False):
+        self._recData.reset(reset_file)
+
+    @abstractmethod
+    def get_model(self, config):
+        pass
+
+    @abstractmethod
+    def obs_fn(self, state):
+        pass
+
+    @abstractmethod
+    def forward(self, model, samples):
+        pass
+
+    def reload_model(self, model_file):
+        """base.py:148-151: load another checkpoint (.npz W-table) into the running simulator."""
+        w = dict(np.load(model_file))
+        self.engine._load_weights(w)
+        self.model = w
+
+    def seed(self, sd=0):
+        self._recData.seed(sd)
+        np.random.seed(sd)
+
+    def _step(self, samples, action, **kwargs):
+        step = kwargs["step"]
+        samples.act(action)                       # one fused device call: act + obs + reward
+        next_obs = self.obs_fn(samples.state)
+        reward = self.forward(self.model, samples)
+        next_info = samples.info
+        done_val = 0 if step < self.max_steps - 1 else 1          # base.py:165-168 (pre-increment step)
+        if self.output_format == "list":
+            done = [done_val] * self.batch_size
+        elif self.output_format == "numpy":
+            done = np.full(self.batch_size, done_val, dtype=np.int64)
+        else:
+            import torch
+            done = torch.full((self.batch_size,), done_val, dtype=torch.int64, device=self.engine.device)
+        return next_obs, reward, done, next_info
+
+    def sample(self, batch_size):
+        samples = self._recData.sample(batch_size)
+        obs = self.obs_fn(samples.state)
+        return samples, obs
+
+
+class RecEnvBase(gym.Env):
+    """gym env over a RecSimBase (base.py:178-273); registered as SlateRecEnv-v0 / SeqSlateRecEnv-v0."""
+
+    metadata = {"render.modes": ["human"]}
+
+    def __init__(self, recsim):
+        self.config = recsim.config
+        self.batch_size = self.config["batch_size"]
+        self.cur_step = 0
+        self.sim = recsim
+        self.sim.reset()                                              # base.py:186-187 (Q19)
+        self.samples, self.obs = self.sim.sample(self.batch_size)
+        spaces = gym.spaces
+        rllib = self.config.get("support_rllib_mask", False)
+        A = self.config["action_size"]
+        if self.config.get("rawstate_as_obs", False):
+            features = {
+                "category_feature": spaces.Box(-1000000.0, 1000000.0, shape=(self.config.get("category_feature_num", 21),)),
+                "dense_feature": spaces.Box(-1000000.0, 1000000.0, shape=(self.config.get("dense_feature_num", 432),)),
+                "sequence_feature": spaces.Box(-1000000.0, 1000000.0,
+                                               shape=(self.config.get("seq_num", 2), self.config.get("maxlen", 64))),
+            }
+            if rllib:
+                self.observation_space = spaces.Dict({"action_mask": spaces.Box(0, 1, shape=(A,)), **features})
+            else:
+                self.observation_space = spaces.Dict(features)
+        else:
+            obs_dim = self.sim.obs_dim
+            if rllib:
+                self.observation_space = spaces.Dict({
+                    "action_mask": spaces.Box(0, 1, shape=(A,)),
+                    "obs": spaces.Box(-100000.0, 100000.0, shape=(obs_dim,))})
+            else:
+                self.observation_space = spaces.Box(-100000.0, 100000.0, shape=(obs_dim,))
+        if self.config.get("support_conti_env", False):
+            self.action_space = spaces.Box(-1, 1, shape=(self.config["action_emb_size"],))
+        else:
+            self.action_space = spaces.Discrete(A)
+        self.reset()                                                  # base.py:230
+
+    def seed(self, sd=0):
+        self.sim.seed(sd)
+        np.random.seed(sd)
+
+    @property
+    @single_elem_support
+    def state(self):
+        return self.obs
+
+    @property
+    @single_elem_support
+    def user_id(self):
+        return self.samples.user
+
+    @property
+    @single_elem_support
+    def offline_action(self):
+        return self.samples.offline_action
+
+    @property
+    @single_elem_support
+    def offline_reward(self):
+        return self.samples.offline_reward
+
+    @single_elem_support
+    def step(self, action):
+        if not isinstance(action, (list, np.ndarray)) and not hasattr(action, "is_cuda"):
+            action = [action]
+        obs, reward, done, info = self.sim._step(self.samples, action, step=self.cur_step)
+        self.cur_step += 1
+        return obs, reward, done, info
+
+    def reset(self, reset_file=False):
+        self.cur_step = 0
+        self.sim.reset(reset_file)
+        self.samples, self.obs = self.sim.sample(self.batch_size)
+        return self.state
+
+    def render(self, mode="human", close=False):
+        print("Current State:", "\n")
+        print(self.samples.to_string())

@@ -1,0 +1,209 @@
+"""Host mirror of rl4rs/env/slate.py: SlateState (RecState plug-in) and SlateRecEnv (RecSimBase).
+
+The state lives on the GPU (prev_actions, bit-packed action mask, special flag); this class is a
+view that keeps the reference's attribute / method names.  ``act`` is the single device call of a
+step; ``SlateRecEnv.obs_fn`` and ``forward`` format what that call produced.
+"""
+import numpy as np
+
+from .base import RecSimBase, RecState
+from ..synth import Catalog
+
+
+class SlateState(RecState):
+    """slate.py:8-217.  ``records`` are row indices into the resident log."""
+
+    seq = False
+
+    def __init__(self, config, records, engine):
+        super().__init__(config, records)
+        self.engine = engine
+        self.rows = np.asarray(records, dtype=np.int64)
+        self.batch_size = config["batch_size"]
+        self.action_size = config["action_size"]
+        self.action_emb_size = engine.emb_dim
+        self.max_steps = config["max_steps"]
+        self.infos = [{} for _ in range(self.batch_size)] if engine.config.get("output_format", "list") == "list" else {}
+        self.action_emb = engine.action_emb                           # slate.py:21-25
+        self.special_items = engine.catalog.special_items             # slate.py:26
+        self.location_mask = self._location_mask(self.action_size)
+        engine.reset(self.rows)                                       # slate.py:16-19 on the device
+
+    # ---- static helpers of the reference ------------------------------------------------------
+    @staticmethod
+    def _location_mask(action_size):
+        m = np.zeros((4, action_size), dtype=np.int64)                # slate.py:60-64
+        m[0, 1:40] = 1
+        m[1, 40:148] = 1
+        m[2, 148:] = 1
+        m[3, 0] = 1
+        return m
+
+    @staticmethod
+    def get_iteminfo_from_file(iteminfo_file, action_size, action_emb_size=32):
+        """slate.py:28-53 -> (item_info_d, action_emb)."""
+        cat = Catalog.from_file(iteminfo_file)
+        d = {str(i): {"item_vec": cat.item_vec[i].tolist(), "price": float(cat.price[i]),
+                      "location": int(cat.location[i])} for i in range(cat.action_size)}
+        return d, cat.action_emb(action_emb_size)
+
+    @staticmethod
+    def get_mask_from_file(iteminfo_file, action_size):
+        """slate.py:55-65 -> (location_mask, special_items)."""
+        cat = Catalog.from_file(iteminfo_file)
+        return SlateState._location_mask(action_size), [int(x) for x in cat.special_items]
+
+    @staticmethod
+    def get_nearest_neighbor(actions, action_emb, temperature=None):
+        """slate.py:180-184 (host utility used by tutorial.ipynb:251-254; tiny, NumPy)."""
+        return np.argmax(np.einsum("ij,kj->ik", np.asarray(actions, dtype=np.float64), action_emb), axis=1)
+
+    @staticmethod
+    def get_nearest_neighbor_with_mask(actions, action_emb, action_mask, temperature=None):
+        """slate.py:186-191.  The env itself resolves actions on the GPU (k_act); this static
+        mirror exists for callers that use it directly."""
+        score = np.einsum("ij,kj->ik", np.asarray(actions, dtype=np.float64), action_emb)
+        score[np.asarray(action_mask) < 0.5] = -2 ** 31
+        return np.argmax(score, axis=1)
+
+    # ---- device-backed attributes ----------------------------------------------------------------
+    @property
+    def cur_steps(self):
+        return self.engine.cur_steps
+
+    @property
+    def prev_actions(self):
+        return self.engine.prev_actions().cpu().numpy().astype(np.int64)
+
+    @property
+    def action_mask(self):
+        """Combined mask of the current state (action_mask & location_mask & special_mask)."""
+        if self.engine.mask is None:
+            raise AttributeError("action masks are materialised only with support_rllib_mask")
+        return self.engine.mask.cpu().numpy().astype(np.int64)
+
+    @property
+    def state(self):
+        """slate.py:90-106: a handle to the device-resident state (what obs_fn consumes)."""
+        return self
+
+    @property
+    def user(self):
+        return [str(int(x)) for x in self.engine.log.session_id[self.rows]]   # slate.py:109-110
+
+    @property
+    def info(self):
+        return self.infos
+
+    def get_price(self, actions):
+        return self.engine.catalog.price[np.asarray(actions)]          # slate.py:112-115
+
+    def get_violation(self):
+        return self.engine.violation().cpu().numpy().astype(np.int64)  # slate.py:133-147
+
+    @property
+    def offline_action(self):
+        items, emb = self.engine.offline_action()                      # slate.py:149-162
+        fmt = self.engine.config.get("output_format", "list")
+        res = emb if self.engine.conti else items
+        if fmt == "torch":
+            return res
+        res = res.cpu().numpy()
+        if fmt == "numpy":
+            return res
+        return [x for x in res] if self.engine.conti else res.tolist()
+
+    @property
+    def offline_reward(self):
+        r = self.engine.offline_reward()                               # slate.py:164-174
+        fmt = self.engine.config.get("output_format", "list")
+        if fmt == "torch":
+            return r
+        r = r.cpu().numpy()
+        return r if fmt == "numpy" else r.tolist()
+
+    def act(self, actions):
+        """slate.py:193-214 -- plus, fused behind it, obs_fn's simulator pass and forward's reward."""
+        self.engine.step(actions)
+
+    def to_string(self):
+        lines = getattr(self.engine.log, "lines", None)
+        if lines is not None:
+            return "\n".join(lines[i] for i in self.rows)
+        return "\n".join("log row %d (user %s)" % (r, u) for r, u in zip(self.rows, self.user))
+
+
+class SlateRecEnv(RecSimBase):
+    """slate.py:220-308.  ``config['model_file']`` is an .npz of the W-table, or
+    ``config['weights']`` holds the arrays."""
+
+    seq = False
+    obs_dim = 256
+
+    def __init__(self, config, state_cls=SlateState):
+        self.max_steps = config["max_steps"]
+        self.batch_size = config["batch_size"]
+        super().__init__(config, state_cls)
+        if config.get("support_d3rl_mask", False) and not config.get("support_rllib_mask", False) \
+                and not config.get("rawstate_as_obs", False):
+            self.obs_dim = 256 + (self.engine.P if self.seq else self.max_steps) + 1   # slate.py:274-277
+
+    def get_model(self, config):
+        algo = config.get("algo", "dien")                              # slate.py:239-242
+        if algo != "dien":
+            raise NotImplementedError("only the 'dien' simulator is built (SURVEY.md section 8f n4)")
+        w = config.get("weights")
+        if w is None:
+            w = dict(np.load(config["model_file"]))
+        return w
+
+    # slate.py:244-279
+    def obs_fn(self, state):
+        eng = self.engine
+        cfg = self.config
+        fmt = self.output_format
+        rllib = cfg.get("support_rllib_mask", False)
+        d3rl = cfg.get("support_d3rl_mask", False) and not rllib
+        if cfg.get("rawstate_as_obs", False):
+            out = {"category_feature": eng.cat, "dense_feature": eng.dense, "sequence_feature": eng.seqf}
+        else:
+            out = {"obs": eng.obs}
+        if rllib:
+            out["action_mask"] = eng.mask
+        if fmt == "torch":
+            if d3rl and "obs" in out:
+                import torch
+                cs = torch.full((eng.B, 1), eng.cur_steps, dtype=torch.float64, device=eng.device)
+                return torch.cat([out["obs"].double(), eng.masked.double(), cs], dim=-1)
+            return {k: v.clone() for k, v in out.items()} if (rllib or "obs" not in out) else out["obs"].clone()
+        host = {k: v.cpu().numpy() for k, v in out.items()}
+        if "action_mask" in host:
+            host["action_mask"] = host["action_mask"].astype(np.int64)
+        if d3rl and "obs" in host:
+            ma = eng.masked.cpu().numpy()
+            cs = np.full((eng.B, 1), eng.cur_steps)
+            return np.concatenate([host["obs"], ma, cs], axis=-1)
+        if not rllib and "obs" in host:
+            return host["obs"]
+        if fmt == "numpy":
+            return host
+        keys = list(host.keys())
+        if "action_mask" in keys:   # reference puts action_mask first (slate.py:258-261,270-273)
+            keys = ["action_mask"] + [k for k in keys if k != "action_mask"]
+        return [{k: host[k][i] for k in keys} for i in range(eng.B)]
+
+    # slate.py:281-308
+    def forward(self, model, samples):
+        eng = self.engine
+        fmt = self.output_format
+        if eng.info_fetch and eng.paid:
+            cp = eng.click_p.cpu().numpy()
+            if isinstance(samples.infos, list):
+                for i in range(eng.B):
+                    samples.infos[i].update({"click_p": cp[i]})
+            else:
+                samples.infos["click_p"] = cp
+        if fmt == "torch":
+            return eng.reward.clone()
+        r = eng.reward.cpu().numpy()
+        return r.tolist() if fmt == "list" else r

