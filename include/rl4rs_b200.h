@@ -136,7 +136,14 @@ const int32_t* r4_prev_actions(const r4_env* env);   /* device i32[B,max_steps] 
 int r4_copy_prev_actions(r4_env* env, int32_t* out /*dev i32[B,max_steps]*/, void* stream);
 /* kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t r4_launch_count(const r4_env* env);
-/* algorithmic constants of the build */
+/* Per-kernel timing with CUDA events on the launching stream (bench.py's roofline leg).
+ * mode 0 = off, 1 = the dominant kernel only (k_recur<256>, the AUGRU recurrence), 2 = every kernel.
+ * r4_profile resets the counters; r4_profile_read synchronises the recorded events and returns, for
+ * slot = 0,1,2,... the kernel name, summed device milliseconds, launches and algorithmic work
+ * (FLOPs for the GEMM-shaped kernels, rows otherwise); it returns 1 past the last slot. */
+int r4_profile(r4_env* env, int mode);
+int r4_profile_read(r4_env* env, int slot, const char** name, double* ms, int64_t* launches, double* work);
+/* ABI version of the build */
 int r4_abi_version(void);
 
 /* ---- the simulator alone (nets/dien.py:8-45), for parity tests and kernel benchmarks ------- */

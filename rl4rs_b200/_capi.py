@@ -45,6 +45,9 @@ EXPORTS = {
     "r4_prev_actions": (C.c_void_p, [C.c_void_p]),
     "r4_copy_prev_actions": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "r4_launch_count": (C.c_int64, [C.c_void_p]),
+    "r4_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "r4_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "r4_abi_version": (C.c_int, []),
     "r4_dien_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

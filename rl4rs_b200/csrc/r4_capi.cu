@@ -76,6 +76,13 @@ struct r4_env {
   bool c1_is_page = false;
   // workspaces
   DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1;
+  // optional per-kernel CUDA-event timing (r4_profile): 0 off, 1 dominant kernel only, 2 every kernel
+  int prof_mode = 0;
+  struct ProfSlot { double ms = 0; int64_t n = 0; double work = 0; };
+  struct PendingEv { cudaEvent_t a, b; int slot; };
+  ProfSlot slots[16];
+  std::vector<PendingEv> pending;
+  std::vector<cudaEvent_t> evpool;
 };
 
 namespace {
@@ -84,6 +91,28 @@ int fail(r4_env* e, int code, const std::string& msg) {
   if (e) e->err = msg; else g_create_error = msg;
   return code;
 }
+
+enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
+       SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_MISC, SL_COUNT };
+const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm[gru1 input proj + E_s gather]",
+    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores", "k_recur<256>[AUGRU]", "k_cat_attn",
+    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "misc"};
+
+// Brackets one launch with CUDA events on the launching stream when profiling is on.
+struct ProfScope {
+  r4_env* e; int slot; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; bool on; double work;
+  static cudaEvent_t get(r4_env* e) {
+    if (!e->evpool.empty()) { cudaEvent_t x = e->evpool.back(); e->evpool.pop_back(); return x; }
+    cudaEvent_t x; cudaEventCreate(&x); return x;
+  }
+  ProfScope(r4_env* e_, int slot_, cudaStream_t st_, double work_) : e(e_), slot(slot_), st(st_), work(work_) {
+    on = e->prof_mode == 2 || (e->prof_mode == 1 && slot == SL_AUGRU);
+    if (on) { a = get(e); b = get(e); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (on) { cudaEventRecord(b, st); e->pending.push_back({a, b, slot}); e->slots[slot].work += work; }
+  }
+};
 
 #define R4_CUDA(e, call)                                                                   \
   do {                                                                                     \
@@ -122,9 +151,10 @@ int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-int gemm(r4_env* e, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
+int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const float* W, const float* bias, float* C, int ldc, cudaStream_t st) {
   if (M <= 0) return R4_OK;
+  ProfScope ps(e, slot, st, 2.0 * M * N * K);
   if ((N & 3) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   dim3 grid((M + 127) / 128, (N + 127) / 128);
   if (act) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, gather, W, bias, C, ldc);
@@ -154,16 +184,17 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
     float* Hc = reinterpret_cast<float*>(c.H.p) + (size_t)s0 * MAXLEN * EMB;
     float* XKc = reinterpret_cast<float*>(c.XK.p) + (size_t)s0 * MAXLEN * XK_LD;
     // x_t [Wgx | Wcx] + [bg | bc] with the Embedding gather fused into the A operand
-    if ((rc = gemm(e, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx,
+    if ((rc = gemm(e, SL_GEMM_XIN, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx,
                    w.gru_bx, xin, XIN_LD, st))) return rc;
     RecurParams p{};
     p.s[0].X = xin; p.s[0].Wgh = w.gru_wgh; p.s[0].Wch = w.gru_wch; p.s[0].scores = nullptr;
     p.s[0].out = Hc; p.s[0].shared = 0;
     p.R = ns; p.row0 = 0; p.div = 1; p.xld = XIN_LD; p.xoff_g = 0; p.xoff_c = 2 * EMB; p.out_ld = 0;
-    k_recur<128, false, true><<<dim3((ns + 63) / 64, 1), 256, SMEM_RECUR_128, st>>>(p);
+    { ProfScope ps(e, SL_GRU1, st, (double)ns * MAXLEN * 2.0 * (EMB * 2 * EMB + EMB * EMB));
+    k_recur<128, false, true><<<dim3((ns + 63) / 64, 1), 256, SMEM_RECUR_128, st>>>(p); }
     R4_LAUNCH_CHECK(e, "k_recur<128>");
     // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]
-    if ((rc = gemm(e, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx, w.au_bx, XKc, XK_LD, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx, w.au_bx, XKc, XK_LD, st))) return rc;
   }
   return R4_OK;
 }
@@ -197,22 +228,26 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   }
   sp.R = R; sp.row0 = row0; sp.div = div;
   rp.R = R; rp.row0 = row0; rp.div = div; rp.xld = XK_LD; rp.xoff_g = 0; rp.xoff_c = XK_C; rp.out_ld = ALLF;
-  k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq);
+  { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
+    k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq); }
   R4_LAUNCH_CHECK(e, "k_scores");
-  k_recur<256, true, false><<<dim3((R + 31) / 32, 2), 256, SMEM_RECUR_256, st>>>(rp);
+  { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
+    k_recur<256, true, false><<<dim3((R + 31) / 32, 2), 256, SMEM_RECUR_256, st>>>(rp); }
   R4_LAUNCH_CHECK(e, "k_recur<256>");
-  k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, st>>>(R, cat, e->emb_cat, allf);
+  { ProfScope ps(e, SL_CAT, st, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
+    k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, st>>>(R, cat, e->emb_cat, allf); }
   R4_LAUNCH_CHECK(e, "k_cat_attn");
-  if ((rc = gemm(e, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1, e->b1, tmp, HU, st))) return rc;
-  if ((rc = gemm(e, 1, R, HU, HU, tmp, HU, nullptr, e->w2, e->b2, allf + 2 * AUH, ALLF, st))) return rc;
+  if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1, e->b1, tmp, HU, st))) return rc;
+  if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2, e->b2, allf + 2 * AUH, ALLF, st))) return rc;
   float* obs = obs_out;
   if (!obs) {
     if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
     obs = reinterpret_cast<float*>(e->ws_obs.p);
   }
-  if ((rc = gemm(e, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo, e->bo, obs, OBSD, st))) return rc;
+  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo, e->bo, obs, OBSD, st))) return rc;
   if (p1_out || probs_out) {
-    k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out);
+    { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
+    k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
     R4_LAUNCH_CHECK(e, "k_reward_head");
   }
   return R4_OK;
@@ -221,8 +256,9 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
 int assemble(r4_env* e, int mode, int step, int rpe, int row0, int nrows, int32_t* cat, float* dense,
              cudaStream_t st) {
   AsmParams p{mode, e->B, e->T, e->P, e->seq, step, rpe, row0, nrows};
-  k_assemble<<<(nrows + 3) / 4, 128, 0, st>>>(p, e->row_idx, e->log_cat, e->log_dense, e->item_vec,
-                                               e->prev_actions, cat, dense);
+  { ProfScope ps(e, SL_ASSEMBLE, st, (double)nrows);
+    k_assemble<<<(nrows + 3) / 4, 128, 0, st>>>(p, e->row_idx, e->log_cat, e->log_dense, e->item_vec,
+                                               e->prev_actions, cat, dense); }
   R4_LAUNCH_CHECK(e, "k_assemble");
   return R4_OK;
 }
@@ -277,8 +313,9 @@ int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st) {
   int zero = 1;                                                   // slate.py:303 `if 1:`
   if (e->seq) zero = (e->cfg.flags & (R4_FLAG_RLLIB_MASK | R4_FLAG_D3RL_MASK)) ? 1 : 0;   // seqslate.py:154-157
   float* click = (out && out->click_p && (e->cfg.flags & R4_FLAG_INFO_FETCH)) ? out->click_p : nullptr;
-  k_reward<<<(B + 127) / 128, 128, 0, st>>>(B, e->T, e->P, e->seq, cur_after, zero, e->prev_actions, e->special,
-                                             e->price, p1, rpe, out->reward, click);
+  { ProfScope ps(e, SL_REWARD, st, (double)B);
+    k_reward<<<(B + 127) / 128, 128, 0, st>>>(B, e->T, e->P, e->seq, cur_after, zero, e->prev_actions, e->special,
+                                             e->price, p1, rpe, out->reward, click); }
   R4_LAUNCH_CHECK(e, "k_reward");
   return R4_OK;
 }
@@ -360,6 +397,8 @@ void r4_destroy(r4_env* e) {
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
                     &e->ws_xin, &e->ws_ids0, &e->ws_ids1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  for (auto& pe : e->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
+  for (cudaEvent_t ev : e->evpool) cudaEventDestroy(ev);
   delete e;
 }
 
@@ -547,8 +586,9 @@ int r4_step(r4_env* e, const void* action, int action_is_f64, const r4_out* out,
     e->c1_is_page = true;
   }
   ActParams ap{B, e->T, e->P, e->A, e->words, e->seq, conti ? 1 : 0, e->emb_dim, cur, action_is_f64};
+  { ProfScope ps(e, SL_ACT, st, (double)B);
   k_act<<<(B + 3) / 4, 128, 0, st>>>(ap, action, e->action_emb, e->special, e->prev_actions, e->amask, e->sflag,
-                                      out ? out->chosen : nullptr, out ? out->action_mask : nullptr);
+                                      out ? out->chosen : nullptr, out ? out->action_mask : nullptr); }
   R4_LAUNCH_CHECK(e, "k_act");
   e->cur_steps = cur + 1;
   if (out && out->seq) {
@@ -618,6 +658,36 @@ int r4_nearest_neighbor(r4_env* e, const void* action, int action_is_f64, int n,
 int r4_cur_steps(const r4_env* e) { return e ? e->cur_steps : -1; }
 const int32_t* r4_prev_actions(const r4_env* e) { return e ? e->prev_actions : nullptr; }
 int64_t r4_launch_count(const r4_env* e) { return e ? e->launches : 0; }
+
+int r4_profile(r4_env* e, int mode) {
+  if (!e || mode < 0 || mode > 2) return fail(e, R4_ERR_ARG, "r4_profile: mode must be 0, 1 or 2");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  R4_CUDA(e, cudaDeviceSynchronize());
+  for (auto& pe : e->pending) { e->evpool.push_back(pe.a); e->evpool.push_back(pe.b); }
+  e->pending.clear();
+  for (auto& sl : e->slots) sl = r4_env::ProfSlot();
+  e->prof_mode = mode;
+  return R4_OK;
+}
+
+int r4_profile_read(r4_env* e, int slot, const char** name, double* ms, int64_t* launches, double* work) {
+  if (!e || slot < 0) return fail(e, R4_ERR_ARG, "r4_profile_read: bad argument");
+  if (slot >= SL_COUNT) return 1;                               // end of the slot list
+  R4_CUDA(e, cudaSetDevice(e->device));
+  for (auto& pe : e->pending) {
+    R4_CUDA(e, cudaEventSynchronize(pe.b));
+    float t = 0.f;
+    R4_CUDA(e, cudaEventElapsedTime(&t, pe.a, pe.b));
+    e->slots[pe.slot].ms += t; e->slots[pe.slot].n += 1;
+    e->evpool.push_back(pe.a); e->evpool.push_back(pe.b);
+  }
+  e->pending.clear();
+  if (name) *name = SLOT_NAMES[slot];
+  if (ms) *ms = e->slots[slot].ms;
+  if (launches) *launches = e->slots[slot].n;
+  if (work) *work = e->slots[slot].work;
+  return R4_OK;
+}
 
 int r4_copy_prev_actions(r4_env* e, int32_t* out, void* stream) {
   if (!e || !out) return fail(e, R4_ERR_ARG, "r4_copy_prev_actions: null argument");

@@ -239,6 +239,25 @@ class Engine(object):
     def launch_count(self):
         return int(self.lib.r4_launch_count(self.h))
 
+    def profile(self, mode):
+        """0 off / 1 time the AUGRU kernel / 2 time every kernel (CUDA events on the launch stream)."""
+        _capi.check(self.lib, self.h, self.lib.r4_profile(self.h, int(mode)), "r4_profile")
+
+    def profile_read(self):
+        """-> list of dicts {name, ms, launches, work} for every kernel slot that launched."""
+        out = []
+        slot = 0
+        while True:
+            name, ms, n, work = C.c_char_p(), C.c_double(), C.c_int64(), C.c_double()
+            rc = self.lib.r4_profile_read(self.h, slot, C.byref(name), C.byref(ms), C.byref(n), C.byref(work))
+            if rc == 1:
+                break
+            _capi.check(self.lib, self.h, rc, "r4_profile_read")
+            if n.value:
+                out.append({"name": name.value.decode(), "ms": ms.value, "launches": n.value, "work": work.value})
+            slot += 1
+        return out
+
     def close(self):
         if getattr(self, "h", None):
             torch.cuda.synchronize(self.device)
