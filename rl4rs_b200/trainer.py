@@ -1,0 +1,279 @@
+"""Model-free trainers over the GPU-resident env: PPO and A2C (the two algorithms of BASELINE
+configs 2, 3 and 5), mirroring ``script/modelfree_trainer.py:get_rl_model`` + the hyper-parameters of
+``script/modelfree_train.py:179-217`` (PPO), ``:248-304`` (A2C), ``:394-417`` (common).
+
+Differences from the reference, by design (north_star):
+  * rollouts never leave the GPU: obs / mask / action / logp / value / reward live in
+    [T, B, ...] device buffers (no HTTP vector env, no Ray object store);
+  * data parallel over env rows: every rank rolls its own shard and ONE ``all_reduce`` over the flat
+    34 973-parameter gradient (~140 KB) per optimizer step is the only collective
+    (NCCL over NVLink on GPUs; gloo in the CPU tests).
+The policy math (forward, losses, Adam) uses torch ops on the device in this round.
+
+RLlib semantics kept: gamma = 1, GAE(lambda = 1) advantages from complete episodes, SoftQ(T=1)
+exploration = sampling from softmax(masked logits), argmax for evaluation; PPO: standardised
+advantages, clip 0.3, vf clip 500, vf coeff 0.5, adaptive KL (0.2 / target 0.01), minibatch 256,
+one SGD epoch, Adam 1e-4; A2C: summed losses, vf coeff 0.5, entropy 0.01, grad-norm clip 10.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from .policy import MaskedPolicy
+
+PPO_DEFAULTS = {"gamma": 1.0, "lambda": 1.0, "kl_coeff": 0.2, "sgd_minibatch_size": 256, "num_sgd_iter": 1,
+                "lr": 1e-4, "vf_loss_coeff": 0.5, "clip_param": 0.3, "vf_clip_param": 500.0, "kl_target": 0.01,
+                "entropy_coeff": 0.0, "grad_clip": None, "shuffle_sequences": True}
+A2C_DEFAULTS = {"gamma": 1.0, "lambda": 1.0, "grad_clip": 10.0, "lr": 1e-4, "vf_loss_coeff": 0.5,
+                "entropy_coeff": 0.01}
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class RolloutBuffer(object):
+    """[T, B, ...] device-resident sample batch of one vector episode."""
+
+    def __init__(self, T, B, A, device):
+        z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
+        self.obs, self.mask = z(T, B, 256), z(T, B, A, dt=torch.uint8)
+        self.action, self.logp, self.value = z(T, B, dt=torch.int64), z(T, B), z(T, B)
+        self.logits, self.reward = z(T, B, A), z(T, B)
+        self.T, self.B = T, B
+
+    def returns_and_advantages(self, gamma, lam):
+        """GAE (RLlib compute_advantages, complete episodes => bootstrap value 0)."""
+        T = self.T
+        adv = torch.zeros_like(self.reward)
+        last = torch.zeros_like(self.reward[0])
+        for t in reversed(range(T)):
+            nv = self.value[t + 1] if t + 1 < T else torch.zeros_like(self.value[0])
+            delta = self.reward[t] + gamma * nv - self.value[t]
+            last = delta + gamma * lam * last
+            adv[t] = last
+        return adv + self.value, adv
+
+
+class _TrainerBase(object):
+    algo = None
+
+    def __init__(self, config, env, device=None, seed=0):
+        """config: RLlib-style hyper-parameter dict (unknown keys ignored); env: a RecEnvBase built
+        with output_format='torch' and support_rllib_mask=True (or any object with that protocol)."""
+        self.config = dict(self.DEFAULTS, **{k: v for k, v in (config or {}).items() if k in self.DEFAULTS})
+        self.env = env
+        self.T = env.config["max_steps"]
+        self.B = env.config["batch_size"]
+        self.A = env.config["action_size"]
+        self.device = torch.device(device) if device is not None else env.sim.engine.device
+        self.policy = MaskedPolicy(self.A, self.device, seed=seed)     # same init on every rank
+        self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
+        self.buf = RolloutBuffer(self.T, self.B, self.A, self.device)
+        self.iteration = 0
+        self.timesteps_total = 0
+
+    # ---- rollout ------------------------------------------------------------------------------
+    @torch.no_grad()
+    def rollout(self, explore=True):
+        env, buf = self.env, self.buf
+        obs = env.reset()
+        for t in range(self.T):
+            a, logp, value, logits = self.policy.act(obs["obs"], obs["action_mask"], explore=explore)
+            buf.obs[t].copy_(obs["obs"]); buf.mask[t].copy_(obs["action_mask"])
+            buf.action[t].copy_(a); buf.logp[t].copy_(logp); buf.value[t].copy_(value); buf.logits[t].copy_(logits)
+            obs, reward, done, info = env.step(a)
+            buf.reward[t].copy_(reward)
+        return buf
+
+    def _allreduce_grad(self, average):
+        w = _world()
+        if w > 1:
+            dist.all_reduce(self.policy.flat.grad, op=dist.ReduceOp.SUM)     # the ONE collective
+            if average:
+                self.policy.flat.grad.div_(w)
+
+    def _global_mean(self, x):
+        x = x.detach().clone().to(torch.float64)
+        if _world() > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM)
+            x /= _world()
+        return float(x)
+
+    def train(self):
+        buf = self.rollout(explore=True)
+        stats = self.learn(buf)
+        self.iteration += 1
+        self.timesteps_total += self.T * self.B * _world()
+        ep_rew = self._global_mean(buf.reward.sum(0).mean())
+        stats.update({"episode_reward_mean": ep_rew, "training_iteration": self.iteration,
+                      "timesteps_this_iter": self.T * self.B * _world(), "timesteps_total": self.timesteps_total,
+                      "episodes_this_iter": self.B * _world()})
+        return stats
+
+    @torch.no_grad()
+    def evaluate(self, episodes=1):
+        """evaluation_config explore=False (modelfree_train.py:412-414): greedy episodes, mean reward."""
+        tot = 0.0
+        for _ in range(episodes):
+            tot += float(self.rollout(explore=False).reward.sum(0).mean())
+        return self._global_mean(torch.tensor(tot / episodes, device=self.device))
+
+    @torch.no_grad()
+    def compute_actions(self, obs, explore=False):
+        """trainer.compute_actions (modelfree_train.py:454): obs = {'obs': [n,256], 'action_mask': [n,A]}
+        (arrays or tensors) or RLlib's {i: {'obs':..,'action_mask':..}} dict."""
+        import numpy as np
+        if isinstance(obs, dict) and "obs" not in obs:
+            keys = list(obs.keys())
+            o = np.stack([np.asarray(obs[k]["obs"]) for k in keys])
+            m = np.stack([np.asarray(obs[k]["action_mask"]) for k in keys])
+            a = self.compute_actions({"obs": o, "action_mask": m}, explore)
+            return dict(zip(keys, a.tolist()))
+        o = torch.as_tensor(obs["obs"], dtype=torch.float32, device=self.device)
+        m = torch.as_tensor(obs["action_mask"], device=self.device)
+        a, _, _, _ = self.policy.act(o, m, explore=explore)
+        return a.cpu().numpy()
+
+    # ---- checkpoint / resume (trainer.save / restore, modelfree_train.py:421-435) -----------------
+    def save(self, checkpoint_dir):
+        os.makedirs(checkpoint_dir, exist_ok=True)
+        path = os.path.join(checkpoint_dir, "checkpoint_%06d.pt" % self.iteration)
+        torch.save({"algo": self.algo, "flat": self.policy.flat.detach().cpu(), "opt": self.opt.state_dict(),
+                    "iteration": self.iteration, "timesteps_total": self.timesteps_total,
+                    "extra": self._extra_state()}, path)
+        return path
+
+    def restore(self, path):
+        st = torch.load(path, map_location="cpu")
+        assert st["algo"] == self.algo
+        with torch.no_grad():
+            self.policy.flat.copy_(st["flat"].to(self.device))
+        self.opt.load_state_dict(st["opt"])
+        self.iteration, self.timesteps_total = st["iteration"], st["timesteps_total"]
+        self._load_extra_state(st["extra"])
+
+    def _extra_state(self):
+        return {}
+
+    def _load_extra_state(self, s):
+        pass
+
+
+class PPOTrainer(_TrainerBase):
+    algo = "PPO"
+    DEFAULTS = PPO_DEFAULTS
+
+    def __init__(self, config, env, device=None, seed=0):
+        super().__init__(config, env, device, seed)
+        self.kl_coeff = self.config["kl_coeff"]
+        self._gen = torch.Generator(device="cpu").manual_seed(seed)
+
+    def loss(self, obs, mask, action, old_logp, old_logits, old_value, adv, target):
+        """RLlib 1.5 ppo_surrogate_loss."""
+        c = self.config
+        logits, value = self.policy.forward(obs, mask)
+        logp_all = torch.log_softmax(logits, -1)
+        logp = logp_all.gather(1, action.unsqueeze(1)).squeeze(1)
+        old_logp_all = torch.log_softmax(old_logits, -1)
+        p_old = old_logp_all.exp()
+        kl = (p_old * (old_logp_all - logp_all)).sum(-1)
+        entropy = -(logp_all.exp() * logp_all).sum(-1)
+        ratio = torch.exp(logp - old_logp)
+        surr = torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - c["clip_param"], 1 + c["clip_param"]))
+        vf1 = (value - target) ** 2
+        vclip = old_value + torch.clamp(value - old_value, -c["vf_clip_param"], c["vf_clip_param"])
+        vf = torch.max(vf1, (vclip - target) ** 2)
+        total = (-surr + self.kl_coeff * kl + c["vf_loss_coeff"] * vf - c["entropy_coeff"] * entropy).mean()
+        return total, {"policy_loss": (-surr).mean(), "vf_loss": vf.mean(), "kl": kl.mean(), "entropy": entropy.mean()}
+
+    def learn(self, buf):
+        c = self.config
+        target, adv = buf.returns_and_advantages(c["gamma"], c["lambda"])
+        n = buf.T * buf.B
+        flat = lambda x: x.reshape((n,) + x.shape[2:])
+        obs, mask, act = flat(buf.obs), flat(buf.mask), flat(buf.action)
+        logp, logits, val = flat(buf.logp), flat(buf.logits), flat(buf.value)
+        adv, target = flat(adv), flat(target)
+        # StandardizeFields(["advantages"]) over the whole (global) train batch
+        mean, sq = adv.mean(), (adv ** 2).mean()
+        if _world() > 1:
+            ms = torch.stack([mean, sq]); dist.all_reduce(ms); ms /= _world(); mean, sq = ms[0], ms[1]
+        adv = (adv - mean) / torch.clamp((sq - mean ** 2).clamp_min(0).sqrt(), min=1e-4)
+        mb = min(c["sgd_minibatch_size"], n)
+        agg, steps = {}, 0
+        for _ in range(c["num_sgd_iter"]):
+            perm = (torch.randperm(n, generator=self._gen) if c["shuffle_sequences"] else torch.arange(n)).to(obs.device)
+            for s in range(0, n - mb + 1, mb):
+                idx = perm[s:s + mb]
+                self.opt.zero_grad(set_to_none=False)
+                if self.policy.flat.grad is not None:
+                    self.policy.flat.grad.zero_()
+                total, st = self.loss(obs[idx], mask[idx], act[idx], logp[idx], logits[idx], val[idx], adv[idx], target[idx])
+                total.backward()
+                self._allreduce_grad(average=True)
+                if c["grad_clip"]:
+                    torch.nn.utils.clip_grad_norm_([self.policy.flat], c["grad_clip"])
+                self.opt.step()
+                steps += 1
+                for k, v in st.items():
+                    agg[k] = agg.get(k, 0.0) + v.detach()
+                agg["total_loss"] = agg.get("total_loss", 0.0) + total.detach()
+        out = {k: self._global_mean(v / max(steps, 1)) for k, v in agg.items()}
+        # adaptive KL (RLlib KLCoeffMixin.update_kl)
+        if out.get("kl", 0.0) > 2.0 * c["kl_target"]:
+            self.kl_coeff *= 1.5
+        elif out.get("kl", 0.0) < 0.5 * c["kl_target"]:
+            self.kl_coeff *= 0.5
+        out.update({"cur_kl_coeff": self.kl_coeff, "sgd_steps": steps})
+        return out
+
+    def _extra_state(self):
+        return {"kl_coeff": self.kl_coeff}
+
+    def _load_extra_state(self, s):
+        self.kl_coeff = s.get("kl_coeff", self.kl_coeff)
+
+
+class A2CTrainer(_TrainerBase):
+    algo = "A2C"
+    DEFAULTS = A2C_DEFAULTS
+
+    def loss(self, obs, mask, action, adv, target):
+        """RLlib 1.5 A3CLoss: summed terms."""
+        c = self.config
+        logits, value = self.policy.forward(obs, mask)
+        logp_all = torch.log_softmax(logits, -1)
+        logp = logp_all.gather(1, action.unsqueeze(1)).squeeze(1)
+        pi_loss = -(logp * adv).sum()
+        vf_loss = 0.5 * ((value - target) ** 2).sum()
+        entropy = -(logp_all.exp() * logp_all).sum()
+        total = pi_loss + c["vf_loss_coeff"] * vf_loss - c["entropy_coeff"] * entropy
+        return total, {"policy_loss": pi_loss, "vf_loss": vf_loss, "entropy": entropy}
+
+    def learn(self, buf):
+        c = self.config
+        target, adv = buf.returns_and_advantages(c["gamma"], c["lambda"])
+        n = buf.T * buf.B
+        flat = lambda x: x.reshape((n,) + x.shape[2:])
+        if self.policy.flat.grad is not None:
+            self.policy.flat.grad.zero_()
+        total, st = self.loss(flat(buf.obs), flat(buf.mask), flat(buf.action), flat(adv), flat(target))
+        total.backward()
+        self._allreduce_grad(average=False)          # summed loss over the global batch
+        gn = torch.nn.utils.clip_grad_norm_([self.policy.flat], c["grad_clip"]) if c["grad_clip"] else torch.zeros(())
+        self.opt.step()
+        out = {k: self._global_mean(v) * _world() for k, v in st.items()}
+        out.update({"total_loss": self._global_mean(total) * _world(), "grad_gnorm": float(gn), "sgd_steps": 1})
+        return out
+
+
+def get_rl_model(algo, rllib_config, env=None, **kw):
+    """script/modelfree_trainer.py:11-36.  Only the algorithms of the BASELINE configs are built."""
+    if algo == "PPO":
+        return PPOTrainer(rllib_config, env, **kw)
+    if algo == "A2C":
+        return A2CTrainer(rllib_config, env, **kw)
+    assert algo in ("PPO", "DQN", "A2C", "A3C", "PG", "IMPALA", "TD3", "RAINBOW", "SLATEQ", "DDPG")
+    raise NotImplementedError("%s is outside the hot-path scope (SURVEY.md section 2, row 11)" % algo)
