@@ -154,8 +154,8 @@ def run_reference(args):
 
 def workload_config(args, seq):
     T = 27 if seq else 9
-    return {"workload": "%s batch=%d/GPU x max_steps=%d, discrete actions from the PPO mask policy "
-                        "(MyMaskActionsModel, SoftQ T=1), DIEN simulator, synthetic 283-item catalog + "
+    return {"workload": "%s batch=%d/GPU x max_steps=%d, PPO discrete (MyMaskActionsModel, SoftQ T=1 rollout + "
+                        "minibatch-256 SGD pass per episode), DIEN simulator, synthetic 283-item catalog + "
                         "synthetic log (seed 1234) + synthetic weights (seed 4321)"
                         % ("SeqSlateRecEnv-v0" if seq else "SlateRecEnv-v0", args.batch_per_gpu, T),
             "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * args.gpus,
@@ -189,7 +189,7 @@ def main():
     from rl4rs_b200 import synth, gymshim
     from rl4rs_b200.env.slate import SlateRecEnv, SlateState
     from rl4rs_b200.env.seqslate import SeqSlateRecEnv, SeqSlateState
-    from rl4rs_b200.policy import MaskedPolicy
+    from rl4rs_b200.trainer import PPOTrainer
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,14 +218,15 @@ def main():
     env = make("torch")
     env.seed(rank)
     eng = env.sim.engine
-    policy = MaskedPolicy(284, dev, seed=0)
+    trainer = PPOTrainer({}, env, seed=0)      # modelfree_train.py:179-217 hyper-parameters
 
     def episode_device():
-        obs = env.reset()
-        for _ in range(T):
-            a, _, _, _ = policy.act(obs["obs"], obs["action_mask"])
-            obs, reward, done, info = env.step(a)
-        return reward
+        # one PPO iteration: device-resident rollout of a vector episode (masked SoftQ sampling) +
+        # the SGD pass (minibatch 256, 1 epoch) with the flat-gradient all-reduce when N > 1
+        return trainer.train()
+
+    def episode_env_only():
+        return trainer.rollout(explore=True)
 
     def barrier():
         if world > 1:
@@ -258,6 +259,8 @@ def main():
     eng.profile(0)
     gpu_launches = eng.launch_count() - launches0
     value = B * world * T * args.steps / (ms / 1e3)
+    ms_env = timed(episode_env_only, args.steps)
+    env_only = B * world * T * args.steps / (ms_env / 1e3)
 
     # ---- e2e: reference-facing call, host buffers (README.md:14-21 loop) ------------------------
     env_h = make("numpy")
@@ -281,7 +284,7 @@ def main():
     kernels = None
     if rank == 0:
         eng.profile(2)
-        episode_device()
+        episode_env_only()
         torch.cuda.synchronize(dev)
         kernels = eng.profile_read()
         eng.profile(0)
@@ -318,7 +321,9 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_h / args.steps,
                     "loop": "README.md:14-21: action = env.offline_action; env.step(action); numpy in/out"},
-            "gpu_launches": gpu_launches, "roofline": roofline}
+            "gpu_launches": gpu_launches, "roofline": roofline,
+            "env_only": {"value": env_only, "unit": UNIT, "ms_per_step": ms_env / args.steps,
+                         "note": "same rollout without the PPO SGD pass (policy sampling still on the GPU)"}}
     if kernels:
         tot = sum(k["ms"] for k in kernels)
         line["kernels"] = [{"name": k["name"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 4),

@@ -2,6 +2,7 @@
 // kernels of r4_kernels.cuh.  No torch, no Python: plain CUDA runtime.  See DESIGN.md.
 #include "../../include/rl4rs_b200.h"
 #include "r4_kernels.cuh"
+#include "r4_augru_tc.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -24,6 +25,7 @@ struct DevBuf {
 struct SeqCache {   // one cached (sequence, weight-set): GRU-1 outputs + AUGRU/attention input halves
   DevBuf H;         // f32 [n, 64, 128]
   DevBuf XK;        // f32 [n, 64, 832]
+  DevBuf XT;        // f32 [ceil(n/128), 64, 768, 128]: the AUGRU input halves, lane-major tiles (k_augru_tc)
   int n = 0;
 };
 
@@ -31,6 +33,7 @@ struct PerSeq {
   float *gru_wx = nullptr, *gru_bx = nullptr, *gru_wgh = nullptr, *gru_wch = nullptr;
   float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
+  uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   float abk = 0.f;
 };
 
@@ -93,10 +96,10 @@ int fail(r4_env* e, int code, const std::string& msg) {
 }
 
 enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
-       SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_MISC, SL_COUNT };
+       SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_XT, SL_MISC, SL_COUNT };
 const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm[gru1 input proj + E_s gather]",
-    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores", "k_recur<256>[AUGRU]", "k_cat_attn",
-    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "misc"};
+    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
+    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "misc"};
 
 // Brackets one launch with CUDA events on the launching stream when profiling is on.
 struct ProfScope {
@@ -164,7 +167,6 @@ int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int 
 }
 
 constexpr int SMEM_RECUR_128 = (128 * 64 * 2 + 64 * 64) * 4;
-constexpr int SMEM_RECUR_256 = (256 * 32 * 2 + 32 * 64) * 4;
 constexpr int SMEM_SCORES = SC_SMEM_FLOATS * 4;
 constexpr int SMEM_CAT = 4 * (NCAT * CAT_LD + NCAT * 24) * 4;
 
@@ -174,6 +176,7 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
   int rc;
   if ((rc = reserve(e, c.H, (size_t)n * MAXLEN * EMB * 4))) return rc;
   if ((rc = reserve(e, c.XK, (size_t)n * MAXLEN * XK_LD * 4))) return rc;
+  if ((rc = reserve(e, c.XT, (size_t)((n + r4tc::TM - 1) / r4tc::TM) * MAXLEN * r4tc::XT_COLS * r4tc::TM * 4))) return rc;
   c.n = n;
   const PerSeq& w = e->ps[si];
   const int chunk = 8192;
@@ -195,6 +198,10 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
     R4_LAUNCH_CHECK(e, "k_recur<128>");
     // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]
     if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx, w.au_bx, XKc, XK_LD, st))) return rc;
+    { ProfScope ps(e, SL_XT, st, (double)ns * MAXLEN * r4tc::XT_COLS * 8.0);
+      r4tc::k_transpose_x<<<dim3((ns + 31) / 32, r4tc::XT_COLS / 32, MAXLEN), dim3(32, 8), 0, st>>>(
+          s0, ns, XKc, XK_LD, reinterpret_cast<float*>(c.XT.p)); }
+    R4_LAUNCH_CHECK(e, "k_transpose_x");
   }
   return R4_OK;
 }
@@ -204,7 +211,9 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
                  const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
                  float* p1_out, float* probs_out, cudaStream_t st) {
   int rc;
-  if ((rc = reserve(e, e->ws_scores, (size_t)2 * R * MAXLEN * 4))) return rc;
+  const int rtiles = (R + r4tc::TM - 1) / r4tc::TM;
+  const size_t sc_per_seq = (size_t)rtiles * r4tc::TM * MAXLEN;
+  if ((rc = reserve(e, e->ws_scores, 2 * sc_per_seq * 4))) return rc;
   if ((rc = reserve(e, e->ws_allf, (size_t)R * ALLF * 4))) return rc;
   if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
   float* scores = reinterpret_cast<float*>(e->ws_scores.p);
@@ -213,27 +222,27 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   const SeqCache* cs[2] = {&c0, &c1};
   int sh[2] = {shared0, shared1};
   ScoreParams sp{};
-  RecurParams rp{};
+  r4tc::AugruTcParams rp{};
   for (int i = 0; i < 2; ++i) {
     const PerSeq& w = e->ps[i];
     ScoreSeq& s = sp.s[i];
     s.H = reinterpret_cast<const float*>(cs[i]->H.p);
     s.XK = reinterpret_cast<const float*>(cs[i]->XK.p);
     s.Wqd = w.wqd; s.Wp = w.wp; s.b1 = w.ab1; s.W2 = w.aw2; s.b2 = w.ab2; s.kv = w.akv; s.bk = w.abk;
-    s.scores = scores + (size_t)i * R * MAXLEN;
+    s.scores = scores + (size_t)i * sc_per_seq;
     s.shared = sh[i];
-    RecurSeq& q = rp.s[i];
-    q.X = s.XK; q.Wgh = w.au_wgh; q.Wch = w.au_wch; q.scores = s.scores;
+    r4tc::AugruTcSeq& q = rp.s[i];
+    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = w.au_img; q.scoresT = s.scores;
     q.out = allf + i * AUH; q.shared = sh[i];
   }
-  sp.R = R; sp.row0 = row0; sp.div = div;
-  rp.R = R; rp.row0 = row0; rp.div = div; rp.xld = XK_LD; rp.xoff_g = 0; rp.xoff_c = XK_C; rp.out_ld = ALLF;
+  sp.R = R; sp.row0 = row0; sp.div = div; sp.transposed = 1;
+  rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF;
   { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
     k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq); }
   R4_LAUNCH_CHECK(e, "k_scores");
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
-    k_recur<256, true, false><<<dim3((R + 31) / 32, 2), 256, SMEM_RECUR_256, st>>>(rp); }
-  R4_LAUNCH_CHECK(e, "k_recur<256>");
+    r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp); }
+  R4_LAUNCH_CHECK(e, "k_augru_tc");
   { ProfScope ps(e, SL_CAT, st, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
     k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, st>>>(R, cat, e->emb_cat, allf); }
   R4_LAUNCH_CHECK(e, "k_cat_attn");
@@ -378,7 +387,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
             cudaMalloc(&e->sflag, (size_t)e->B) == cudaSuccess;
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(k_recur<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_128);
-  cudaFuncSetAttribute(k_recur<256, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_256);
+  cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
   cudaFuncSetAttribute(k_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SCORES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
   st = cudaGetLastError();
@@ -394,6 +403,7 @@ void r4_destroy(r4_env* e) {
   void* own[] = {e->row_idx, e->prev_actions, e->amask, e->sflag, e->item_vec, e->price, e->special, e->action_emb};
   for (void* p : own) if (p) cudaFree(p);
   DevBuf* bufs[] = {&e->c0.H, &e->c0.XK, &e->c1const.H, &e->c1const.XK, &e->c1page.H, &e->c1page.XK,
+                    &e->c0.XT, &e->c1const.XT, &e->c1page.XT,
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
                     &e->ws_xin, &e->ws_ids0, &e->ws_ids1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
@@ -507,6 +517,9 @@ int r4_finalize_weights(r4_env* e, void* stream) {
       for (int n = 0; n < 2 * AUH; ++n) awgh[(size_t)k * 2 * AUH + n] = uwg[(size_t)(EMB + k) * 2 * AUH + n];
       for (int n = 0; n < AUH; ++n) awch[(size_t)k * AUH + n] = uwc[(size_t)(EMB + k) * AUH + n];
     }
+    std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
+    r4tc::build_weight_image(awgh.data(), awch.data(), img.data());
+    if ((rc = upload(e, img, &w.au_img))) return rc;
     std::vector<float> vb1(ab1, ab1 + AH1), vw2(aw2, aw2 + AH1 * AH2), vb2(ab2, ab2 + AH2), vkv(akv, akv + AH2);
     if ((rc = upload(e, wx, &w.gru_wx)) || (rc = upload(e, bx, &w.gru_bx)) || (rc = upload(e, wgh, &w.gru_wgh)) ||
         (rc = upload(e, wch, &w.gru_wch)) || (rc = upload(e, awx, &w.au_wx)) || (rc = upload(e, abx, &w.au_bx)) ||
@@ -719,7 +732,7 @@ int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int
                       obs ? obs + (size_t)r0 * OBSD : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
   }
   cudaStreamSynchronize(st);
-  DevBuf* tmp[] = {&t0.H, &t0.XK, &t1.H, &t1.XK, &ids};
+  DevBuf* tmp[] = {&t0.H, &t0.XK, &t0.XT, &t1.H, &t1.XK, &t1.XT, &ids};
   for (DevBuf* b : tmp) if (b->p) cudaFree(b->p);
   return rc;
 }

@@ -494,6 +494,7 @@ struct ScoreSeq {
 struct ScoreParams {
   ScoreSeq s[2];
   int R, row0, div;
+  int transposed;   // 1: scores[(r/128)*64 + t][r%128] (lane-major tiles for the tensor-core AUGRU kernel)
 };
 
 constexpr int SC_ALD = 132;   // padded stride of the A tile
@@ -582,7 +583,10 @@ __global__ void __launch_bounds__(256) k_scores(ScoreParams p, const int32_t* __
               sigmoidf_(o[2]) * kv_s[jq * 4 + 2] + sigmoidf_(o[3]) * kv_s[jq * 4 + 3];
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (jq == 0) S.scores[(size_t)r * MAXLEN + t] = s + S.bk;
+    if (jq == 0) {
+      size_t o = p.transposed ? ((size_t)(r >> 7) * MAXLEN + t) * 128 + (r & 127) : (size_t)r * MAXLEN + t;
+      S.scores[o] = s + S.bk;
+    }
   }
 }
 

@@ -1,0 +1,91 @@
+// augru_probe.cu -- standalone check + timing of k_augru_tc against a CPU (f64) recurrence.
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/build/augru_probe tools/augru_probe.cu
+#include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+using namespace r4tc;
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
+
+static float frand(float a) { return a * ((rand() % 20001) - 10000) / 10000.f; }
+static uint16_t bf16_bits(float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x7fff + ((u >> 16) & 1)) >> 16; return (uint16_t)u; }
+static float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
+
+void build_image(const std::vector<float>& Wg, const std::vector<float>& Wc, std::vector<uint8_t>& img) {
+  img.assign(W_IMAGE_BYTES, 0);
+  build_weight_image(Wg.data(), Wc.data(), img.data());
+}
+
+int main(int argc, char** argv) {
+  int R = argc > 1 ? atoi(argv[1]) : 300;
+  int div = argc > 2 ? atoi(argv[2]) : 1;
+  int timing_tiles = argc > 3 ? atoi(argv[3]) : 148;
+  srand(3);
+  int ncache = (R + div - 1) / div;
+  std::vector<float> Wg(256 * 512), Wc(256 * 256);
+  for (auto& w : Wg) w = frand(0.17f);
+  for (auto& w : Wc) w = frand(0.17f);
+  std::vector<float> X((size_t)ncache * 64 * 768), sc((size_t)R * 64);
+  for (size_t i = 0; i < X.size(); ++i) X[i] = frand(1.0f) + ((i % 768) < 512 ? 1.0f : 0.f);
+  for (auto& s : sc) s = 0.5f + frand(0.5f);
+  int ctiles = (ncache + TM - 1) / TM, rtiles = (R + TM - 1) / TM;
+  std::vector<float> XT((size_t)ctiles * 64 * 768 * TM, 0.f), sT((size_t)rtiles * 64 * TM, 0.f);
+  for (int c = 0; c < ncache; ++c) for (int t = 0; t < 64; ++t) for (int col = 0; col < 768; ++col)
+    XT[(((size_t)(c / TM) * 64 + t) * 768 + col) * TM + c % TM] = X[((size_t)c * 64 + t) * 768 + col];
+  for (int r = 0; r < R; ++r) for (int t = 0; t < 64; ++t) sT[((size_t)(r / TM) * 64 + t) * TM + r % TM] = sc[(size_t)r * 64 + t];
+  std::vector<uint8_t> img; build_image(Wg, Wc, img);
+  // CPU reference (f64)
+  std::vector<double> href((size_t)R * 256, 0.0);
+  for (int r = 0; r < R; ++r) {
+    int c = r / div;
+    std::vector<double> h(256, 0.0), g(512), rh(256), cc(256);
+    for (int t = 0; t < 64; ++t) {
+      const float* x = &X[((size_t)c * 64 + t) * 768];
+      for (int n = 0; n < 512; ++n) { double s = x[n]; for (int k = 0; k < 256; ++k) s += h[k] * Wg[(size_t)k * 512 + n]; g[n] = 1.0 / (1.0 + exp(-s)); }
+      for (int k = 0; k < 256; ++k) rh[k] = g[k] * h[k];
+      for (int n = 0; n < 256; ++n) { double s = x[512 + n]; for (int k = 0; k < 256; ++k) s += rh[k] * Wc[(size_t)k * 256 + n]; cc[n] = tanh(s); }
+      double om = 1.0 - sc[(size_t)r * 64 + t];
+      for (int n = 0; n < 256; ++n) { double u = om * g[256 + n]; h[n] = u * h[n] + (1 - u) * cc[n]; }
+    }
+    for (int n = 0; n < 256; ++n) href[(size_t)r * 256 + n] = h[n];
+  }
+  float *dXT, *dsT, *dout; uint8_t* dimg;
+  CK(cudaMalloc(&dXT, XT.size() * 4)); CK(cudaMalloc(&dsT, sT.size() * 4)); CK(cudaMalloc(&dout, (size_t)R * 256 * 4)); CK(cudaMalloc(&dimg, img.size()));
+  CK(cudaMemcpy(dXT, XT.data(), XT.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsT, sT.data(), sT.size() * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dout, 0, (size_t)R * 256 * 4));
+  CK(cudaFuncSetAttribute(k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  AugruTcParams p{};
+  p.s[0] = {dXT, dimg, dsT, dout, 0}; p.s[1] = p.s[0];
+  p.R = R; p.row0 = 0; p.div = div; p.out_ld = 256;
+  k_augru_tc<<<dim3(rtiles, 1), NTHREADS, SMEM_BYTES>>>(p);
+  CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+  std::vector<float> hout((size_t)R * 256);
+  CK(cudaMemcpy(hout.data(), dout, hout.size() * 4, cudaMemcpyDeviceToHost));
+  double rms = 0, worst = 0; for (auto v : href) rms += v * v; rms = sqrt(rms / href.size());
+  int wi = 0;
+  for (size_t i = 0; i < href.size(); ++i) { double e = fabs(hout[i] - href[i]); if (e > worst) { worst = e; wi = (int)i; } }
+  printf("R=%d div=%d: rms(h)=%.4f  max abs err %.3g (%.3g of rms) at row %d col %d: got %f ref %f -> %s\n", R, div, rms, worst,
+         worst / rms, wi / 256, wi % 256, hout[wi], href[wi], worst / rms < 1e-4 ? "PASS" : "FAIL");
+  // timing: `timing_tiles` tiles sharing cache row tile 0 (div large -> all rows read cached sequence 0.. via shared)
+  if (timing_tiles > 0) {
+    int RT = timing_tiles * TM;
+    float *dsT2, *dout2;
+    CK(cudaMalloc(&dsT2, (size_t)timing_tiles * 64 * TM * 4)); CK(cudaMalloc(&dout2, (size_t)RT * 256 * 4));
+    CK(cudaMemset(dsT2, 0, (size_t)timing_tiles * 64 * TM * 4));
+    AugruTcParams q = p; q.s[0].scoresT = dsT2; q.s[0].out = dout2; q.s[0].shared = 1; q.R = RT; q.s[1] = q.s[0];
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int it = 0; it < 3; ++it) {
+      cudaEventRecord(e0);
+      k_augru_tc<<<dim3(timing_tiles, 1), NTHREADS, SMEM_BYTES>>>(q);
+      cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+      float ms; cudaEventElapsedTime(&ms, e0, e1);
+      double flops = (double)RT * 64 * 2.0 * (256 * 512 + 256 * 256);
+      printf("timing: %d tiles (%d rows) %.3f ms -> %.1f TFLOP/s fp32-equivalent, %.0f cycles/step @1.965GHz\n", timing_tiles, RT, ms,
+             flops / ms / 1e9, ms * 1e-3 * 1.965e9 / 64 / ((timing_tiles + 147) / 148));
+    }
+  }
+  return 0;
+}
