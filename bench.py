@@ -298,7 +298,7 @@ def main():
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    au = [p for p in prof if p["name"].startswith("k_recur<256>")]
+    au = [p for p in prof if p["name"].startswith("k_augru_tc")]
     roofline = None
     if au:
         au = au[0]
@@ -308,7 +308,7 @@ def main():
         tp = os.path.join(ROOT, "profiles", "augru_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "k_recur<256,AUGRU> (fp32 SIMT recurrence; tensor-core rewrite pending)",
+        roofline = {"kernel": "k_augru_tc (AUGRU recurrence: tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators)",
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "%s bf16 GEMM, sustained (kernel timed inside a long step)" % peaks["source"],

@@ -69,7 +69,9 @@ class _TrainerBase(object):
         self.A = env.config["action_size"]
         self.device = torch.device(device) if device is not None else env.sim.engine.device
         self.policy = MaskedPolicy(self.A, self.device, seed=seed)     # same init on every rank
-        self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
+        self.use_graph = self.device.type == "cuda"
+        self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"], capturable=self.use_graph)
+        self._graphs = None
         self.buf = RolloutBuffer(self.T, self.B, self.A, self.device)
         self.iteration = 0
         self.timesteps_total = 0
@@ -202,15 +204,31 @@ class PPOTrainer(_TrainerBase):
             ms = torch.stack([mean, sq]); dist.all_reduce(ms); ms /= _world(); mean, sq = ms[0], ms[1]
         adv = (adv - mean) / torch.clamp((sq - mean ** 2).clamp_min(0).sqrt(), min=1e-4)
         mb = min(c["sgd_minibatch_size"], n)
+        data = (obs, mask, act, logp, logits, val, adv, target)
+        agg, steps = (self._sgd_graphed if self.use_graph else self._sgd_eager)(data, n, mb)
+        out = {k: self._global_mean(v / max(steps, 1)) for k, v in agg.items()}
+        # adaptive KL (RLlib KLCoeffMixin.update_kl)
+        if out.get("kl", 0.0) > 2.0 * c["kl_target"]:
+            self.kl_coeff *= 1.5
+        elif out.get("kl", 0.0) < 0.5 * c["kl_target"]:
+            self.kl_coeff *= 0.5
+        out.update({"cur_kl_coeff": self.kl_coeff, "sgd_steps": steps})
+        return out
+
+    def _perm(self, n, device):
+        c = self.config
+        return (torch.randperm(n, generator=self._gen) if c["shuffle_sequences"] else torch.arange(n)).to(device)
+
+    def _sgd_eager(self, data, n, mb):
+        c = self.config
         agg, steps = {}, 0
         for _ in range(c["num_sgd_iter"]):
-            perm = (torch.randperm(n, generator=self._gen) if c["shuffle_sequences"] else torch.arange(n)).to(obs.device)
+            perm = self._perm(n, data[0].device)
             for s in range(0, n - mb + 1, mb):
                 idx = perm[s:s + mb]
-                self.opt.zero_grad(set_to_none=False)
                 if self.policy.flat.grad is not None:
                     self.policy.flat.grad.zero_()
-                total, st = self.loss(obs[idx], mask[idx], act[idx], logp[idx], logits[idx], val[idx], adv[idx], target[idx])
+                total, st = self.loss(*[d[idx] for d in data])
                 total.backward()
                 self._allreduce_grad(average=True)
                 if c["grad_clip"]:
@@ -220,14 +238,77 @@ class PPOTrainer(_TrainerBase):
                 for k, v in st.items():
                     agg[k] = agg.get(k, 0.0) + v.detach()
                 agg["total_loss"] = agg.get("total_loss", 0.0) + total.detach()
-        out = {k: self._global_mean(v / max(steps, 1)) for k, v in agg.items()}
-        # adaptive KL (RLlib KLCoeffMixin.update_kl)
-        if out.get("kl", 0.0) > 2.0 * c["kl_target"]:
-            self.kl_coeff *= 1.5
-        elif out.get("kl", 0.0) < 0.5 * c["kl_target"]:
-            self.kl_coeff *= 0.5
-        out.update({"cur_kl_coeff": self.kl_coeff, "sgd_steps": steps})
-        return out
+        return agg, steps
+
+    def _build_graphs(self, data, mb):
+        """Capture one SGD step as two CUDA graphs (forward+backward | clip+Adam) over static minibatch
+        buffers, so the 144 minibatch steps of an iteration cost a few launches each instead of ~60
+        eager torch kernels; the gradient all-reduce (N > 1) runs between the two graphs."""
+        c = self.config
+        dev = self.device
+        static = [torch.zeros((mb,) + d.shape[1:], dtype=d.dtype, device=dev) for d in data]
+        kl_coeff = torch.tensor(float(self.kl_coeff), device=dev)
+        stats = torch.zeros(5, device=dev, dtype=torch.float32)
+        self.policy.flat.grad = torch.zeros_like(self.policy.flat)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+
+        def fb():
+            self.policy.flat.grad.zero_()
+            kc, self.kl_coeff = self.kl_coeff, kl_coeff          # loss() reads the device scalar
+            total, st = self.loss(*static)
+            self.kl_coeff = kc
+            total.backward()
+            stats.add_(torch.stack([st["policy_loss"], st["vf_loss"], st["kl"], st["entropy"], total]).detach())
+
+        def opt():
+            if c["grad_clip"]:
+                torch.nn.utils.clip_grad_norm_([self.policy.flat], c["grad_clip"])
+            self.opt.step()
+
+        with torch.cuda.stream(side):
+            snap = self.policy.flat.detach().clone()
+            opt_state = None
+            for _ in range(3):                                    # warm-up (allocator, lazy Adam state)
+                fb(); opt()
+            with torch.no_grad():                                 # undo the warm-up updates
+                self.policy.flat.copy_(snap)
+            for st_ in self.opt.state.values():
+                for k_, v_ in st_.items():
+                    if torch.is_tensor(v_):
+                        v_.zero_()
+            stats.zero_()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_fb):
+            fb()
+        with torch.cuda.graph(g_opt):
+            opt()
+        stats.zero_()
+        self._graphs = {"static": static, "kl": kl_coeff, "stats": stats, "fb": g_fb, "opt": g_opt, "mb": mb}
+
+    def _sgd_graphed(self, data, n, mb):
+        c = self.config
+        if self._graphs is None or self._graphs["mb"] != mb:
+            self._build_graphs(data, mb)
+        G = self._graphs
+        G["kl"].fill_(float(self.kl_coeff))
+        G["stats"].zero_()
+        steps = 0
+        for _ in range(c["num_sgd_iter"]):
+            perm = self._perm(n, data[0].device)
+            for s in range(0, n - mb + 1, mb):
+                idx = perm[s:s + mb]
+                for dst, src in zip(G["static"], data):
+                    torch.index_select(src, 0, idx, out=dst)
+                G["fb"].replay()
+                self._allreduce_grad(average=True)
+                G["opt"].replay()
+                steps += 1
+        st = G["stats"]
+        agg = {"policy_loss": st[0], "vf_loss": st[1], "kl": st[2], "entropy": st[3], "total_loss": st[4]}
+        return agg, steps
 
     def _extra_state(self):
         return {"kl_coeff": self.kl_coeff}
