@@ -149,7 +149,7 @@ def run_reference(args):
             "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, seq):
@@ -163,6 +163,16 @@ def workload_config(args, seq):
             "parallelism": "env rows sharded by contiguous blocks, dp%d, no data-path collective" % args.gpus,
             "l2": "per-step working set (AUGRU input-projection cache ~0.21 MB/row, 0.87 GB at batch 4096) "
                   "exceeds the 126 MB L2; no explicit flush"}
+
+
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL's version banner, library
+    chatter) was redirected to stderr at start-up so the driver can parse stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -344,7 +354,7 @@ def main():
         line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "2 offline-replay episodes of %d env rows (%d transitions), %.1f s, "
                                           "NumPy/OpenBLAS threads" % (Bs, 2 * Bs * T, dt)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

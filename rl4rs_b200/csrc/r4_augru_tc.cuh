@@ -24,6 +24,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 
 namespace r4tc {
 
@@ -262,6 +263,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {
       const uint32_t par = t & 1;
       const float* xs = xt + (size_t)t * XT_COLS * TM;
       const float one_minus_s = 1.0f - __ldg(st + (size_t)t * TM);
+      // Pull the NEXT step's input halves (768 columns x 128 lanes x 4 B = 3072 lines) from HBM into L2
+      // now: each thread touches 12 lines; the demand loads one step later then see L2 latency.
+      if (t + 1 < STEPS) {
+        const float* xn = S.XT + (((size_t)(ci / TM) * STEPS + (t + 1)) * XT_COLS) * TM;
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(i * 256 + (tid & 255)) * 32));
+      }
       // Each phase walks its 128 columns in 8 chunks of 16 with a 2-deep software pipeline: the TMEM
       // load and the coalesced X loads of chunk ch+1 are in flight while chunk ch is computed.
 #define R4_LOADX(dst, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg(xs + (size_t)((colbase) + j) * TM)

@@ -3,6 +3,7 @@
 #include "../../include/rl4rs_b200.h"
 #include "r4_kernels.cuh"
 #include "r4_augru_tc.cuh"
+#include "r4_gemm_tc.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -33,6 +34,7 @@ struct PerSeq {
   float *gru_wx = nullptr, *gru_bx = nullptr, *gru_wgh = nullptr, *gru_wch = nullptr;
   float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
+  uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
   uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   float abk = 0.f;
 };
@@ -56,6 +58,7 @@ struct r4_env {
   std::map<std::string, std::vector<float>> hw;
   float *emb_cat = nullptr, *emb_seq = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   float *wo = nullptr, *bo = nullptr, *wr = nullptr, *br = nullptr;
+  uint8_t *w1_img = nullptr, *w2_img = nullptr, *wo_img = nullptr;   // tensor-core images (r4_gemm_tc.cuh)
   PerSeq ps[2];
   bool weights_ready = false;
   std::vector<void*> owned;
@@ -79,6 +82,10 @@ struct r4_env {
   bool c1_is_page = false;
   // workspaces
   DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1;
+  // side stream: category attention + dense tower run concurrently with scores + AUGRU (they only
+  // meet at the head GEMM), which fills the SMs the 128-row AUGRU tiles leave idle at small batch
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   // optional per-kernel CUDA-event timing (r4_profile): 0 off, 1 dominant kernel only, 2 every kernel
   int prof_mode = 0;
   struct ProfSlot { double ms = 0; int64_t n = 0; double work = 0; };
@@ -155,15 +162,21 @@ int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
-         const float* W, const float* bias, float* C, int ldc, cudaStream_t st) {
+         const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st) {
   if (M <= 0) return R4_OK;
+  if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
-  if ((N & 3) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
-  dim3 grid((M + 127) / 128, (N + 127) / 128);
-  if (act) k_gemm<1><<<grid, 256, 0, st>>>(M, N, K, A, lda, gather, W, bias, C, ldc);
-  else k_gemm<0><<<grid, 256, 0, st>>>(M, N, K, A, lda, gather, W, bias, C, ldc);
-  R4_LAUNCH_CHECK(e, "k_gemm");
+  r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act};
+  dim3 grid((M + r4tc::G_BM - 1) / r4tc::G_BM, (N + r4tc::G_BNMAX - 1) / r4tc::G_BNMAX);
+  r4tc::k_gemm_tc<<<grid, r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
+  R4_LAUNCH_CHECK(e, "k_gemm_tc");
   return R4_OK;
+}
+
+int upload_image(r4_env* e, const float* W, int K, int N, uint8_t** out) {
+  std::vector<uint8_t> img(r4tc::gemm_image_bytes(K, N));
+  r4tc::build_gemm_image(W, K, N, img.data());
+  return upload(e, img, out);
 }
 
 constexpr int SMEM_RECUR_128 = (128 * 64 * 2 + 64 * 64) * 4;
@@ -187,7 +200,7 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
     float* Hc = reinterpret_cast<float*>(c.H.p) + (size_t)s0 * MAXLEN * EMB;
     float* XKc = reinterpret_cast<float*>(c.XK.p) + (size_t)s0 * MAXLEN * XK_LD;
     // x_t [Wgx | Wcx] + [bg | bc] with the Embedding gather fused into the A operand
-    if ((rc = gemm(e, SL_GEMM_XIN, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx,
+    if ((rc = gemm(e, SL_GEMM_XIN, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx_img,
                    w.gru_bx, xin, XIN_LD, st))) return rc;
     RecurParams p{};
     p.s[0].X = xin; p.s[0].Wgh = w.gru_wgh; p.s[0].Wch = w.gru_wch; p.s[0].scores = nullptr;
@@ -197,7 +210,7 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
     k_recur<128, false, true><<<dim3((ns + 63) / 64, 1), 256, SMEM_RECUR_128, st>>>(p); }
     R4_LAUNCH_CHECK(e, "k_recur<128>");
     // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]
-    if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx, w.au_bx, XKc, XK_LD, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx_img, w.au_bx, XKc, XK_LD, st))) return rc;
     { ProfScope ps(e, SL_XT, st, (double)ns * MAXLEN * r4tc::XT_COLS * 8.0);
       r4tc::k_transpose_x<<<dim3((ns + 31) / 32, r4tc::XT_COLS / 32, MAXLEN), dim3(32, 8), 0, st>>>(
           s0, ns, XKc, XK_LD, reinterpret_cast<float*>(c.XT.p)); }
@@ -237,23 +250,31 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   }
   sp.R = R; sp.row0 = row0; sp.div = div; sp.transposed = 1;
   rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF;
+  // fork: side stream does the action-independent-of-AUGRU half of the feature vector
+  R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
+  R4_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  {
+    cudaStream_t ss = e->side;
+    { ProfScope ps(e, SL_CAT, ss, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
+      k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, ss>>>(R, cat, e->emb_cat, allf); }
+    R4_LAUNCH_CHECK(e, "k_cat_attn");
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, ss))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF, ss))) return rc;
+    R4_CUDA(e, cudaEventRecord(e->ev_join, ss));
+  }
   { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
     k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq); }
   R4_LAUNCH_CHECK(e, "k_scores");
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
     r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp); }
   R4_LAUNCH_CHECK(e, "k_augru_tc");
-  { ProfScope ps(e, SL_CAT, st, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
-    k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, st>>>(R, cat, e->emb_cat, allf); }
-  R4_LAUNCH_CHECK(e, "k_cat_attn");
-  if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1, e->b1, tmp, HU, st))) return rc;
-  if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2, e->b2, allf + 2 * AUH, ALLF, st))) return rc;
+  R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
   if (!obs) {
     if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
     obs = reinterpret_cast<float*>(e->ws_obs.p);
   }
-  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo, e->bo, obs, OBSD, st))) return rc;
+  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo_img, e->bo, obs, OBSD, st))) return rc;
   if (p1_out || probs_out) {
     { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
     k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
@@ -388,10 +409,16 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(k_recur<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_128);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(k_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SCORES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
   st = cudaGetLastError();
   if (st != cudaSuccess) { r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(st)); }
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, "r4_create: stream/event creation failed");
+  }
   *out = e;
   return R4_OK;
 }
@@ -407,6 +434,9 @@ void r4_destroy(r4_env* e) {
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
                     &e->ws_xin, &e->ws_ids0, &e->ws_ids1};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (auto& pe : e->pending) { cudaEventDestroy(pe.a); cudaEventDestroy(pe.b); }
   for (cudaEvent_t ev : e->evpool) cudaEventDestroy(ev);
   delete e;
@@ -468,6 +498,9 @@ int r4_finalize_weights(r4_env* e, void* stream) {
   UP(e->w2, "dense_w2"); UP(e->b2, "dense_b2"); UP(e->wo, "obs_w"); UP(e->bo, "obs_b");
   UP(e->wr, "rew_w"); UP(e->br, "rew_b");
 #undef UP
+  if ((rc = upload_image(e, e->hw["dense_w1"].data(), NDENSE, HU, &e->w1_img)) ||
+      (rc = upload_image(e, e->hw["dense_w2"].data(), HU, HU, &e->w2_img)) ||
+      (rc = upload_image(e, e->hw["obs_w"].data(), ALLF, OBSD, &e->wo_img))) return rc;
   for (int i = 0; i < 2; ++i) {
     std::string si = std::to_string(i);
     const float* gwg = hw_get(e, "gru" + si + "_wg", (size_t)2 * EMB * 2 * EMB);
@@ -517,6 +550,8 @@ int r4_finalize_weights(r4_env* e, void* stream) {
       for (int n = 0; n < 2 * AUH; ++n) awgh[(size_t)k * 2 * AUH + n] = uwg[(size_t)(EMB + k) * 2 * AUH + n];
       for (int n = 0; n < AUH; ++n) awch[(size_t)k * AUH + n] = uwc[(size_t)(EMB + k) * AUH + n];
     }
+    if ((rc = upload_image(e, wx.data(), EMB, XIN_LD, &w.gru_wx_img)) ||
+        (rc = upload_image(e, awx.data(), EMB, XK_LD, &w.au_wx_img))) return rc;
     std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
     r4tc::build_weight_image(awgh.data(), awch.data(), img.data());
     if ((rc = upload(e, img, &w.au_img))) return rc;
