@@ -146,6 +146,29 @@ int r4_profile_read(r4_env* env, int slot, const char** name, double* ms, int64_
 /* ABI version of the build */
 int r4_abi_version(void);
 
+/* ---- policy + learner (K12): MyMaskActionsModel (rllib_mask_model.py:41-62) and the RLlib PPO / A2C losses ----
+ * Stateless: every pointer is caller-owned DEVICE memory.  Flat parameter layout:
+ * w1[256,64] b1[64] w2[64,A] b2[A] wv[64] bv[1]  (r4_policy_num_params(A) floats). */
+int r4_policy_num_params(int action_size);
+/* forward + SoftQ(T=1) sampling (explore != 0) or argmax (modelfree_train.py:398-402,412-414); obs f32[n,256],
+ * mask u8[n,A] -> action i32[n], logp f32[n], value f32[n], logits f32[n,A] (masked logits; may be NULL). */
+int r4_policy_act(const float* params, const float* obs, const uint8_t* mask, int n, int action_size, int explore,
+                  uint64_t seed, uint64_t counter, int32_t* action, float* logp, float* value, float* logits,
+                  void* stream);
+/* gradient of the RLlib loss over samples idx[0..n) (NULL = 0..n-1) of a rollout:
+ * mode 0 PPO surrogate (mean; modelfree_train.py:179-217), mode 1 A2C (sums; :248-304).
+ * scratch: f32[G * (num_params + 5)], G = min(ceil(n/16), 148) CTAs; flat_grad f32[num_params] receives the
+ * deterministic sum; stats_accum f32[5] += {policy_loss, vf_loss, kl, entropy, total} * stat_scale. */
+int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                   const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                   const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                   float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                   float* flat_grad, float* stats_accum, float stat_scale, void* stream);
+/* Adam (torch.optim.Adam semantics) with optional global-norm clipping (clip <= 0 off; norm_scratch f32[1]).
+ * grad_scale multiplies the gradient first (1/world after a SUM all-reduce). step is 1-based. */
+int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, float clip, float* norm_scratch, void* stream);
+
 /* ---- the simulator alone (nets/dien.py:8-45), for parity tests and kernel benchmarks ------- */
 /* seq i32[R,2,64], dense f32[R,432], cat i32[R,21] (device) -> obs f32[R,256], probs f32[R,2]
  * (either may be NULL).  Runs the uncached path: GRU-1 is recomputed for every row. */

@@ -4,6 +4,7 @@
 #include "r4_kernels.cuh"
 #include "r4_augru_tc.cuh"
 #include "r4_gemm_tc.cuh"
+#include "r4_ppo.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -741,6 +742,74 @@ int r4_copy_prev_actions(r4_env* e, int32_t* out, void* stream) {
   if (!e || !out) return fail(e, R4_ERR_ARG, "r4_copy_prev_actions: null argument");
   R4_CUDA(e, cudaSetDevice(e->device));
   R4_CUDA(e, cudaMemcpyAsync(out, e->prev_actions, (size_t)e->B * e->T * 4, cudaMemcpyDeviceToDevice, S(stream)));
+  return R4_OK;
+}
+
+// ---- K12: policy / learner kernels (stateless) ---------------------------------------------------
+#define R4_PCHECK(name)                                                                     \
+  do {                                                                                      \
+    cudaError_t _st = cudaGetLastError();                                                   \
+    if (_st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string(name) + ": " + cudaGetErrorString(_st)); \
+  } while (0)
+
+int r4_policy_num_params(int action_size) { return r4ppo::make_layout(action_size).n; }
+
+int r4_policy_act(const float* params, const float* obs, const uint8_t* mask, int n, int action_size, int explore,
+                  uint64_t seed, uint64_t counter, int32_t* action, float* logp, float* value, float* logits,
+                  void* stream) {
+  if (!params || !obs || !mask || !action || !logp || !value || n < 1 || action_size < 2 || action_size > 512)
+    return fail(nullptr, R4_ERR_ARG, "r4_policy_act: bad argument");
+  r4ppo::Layout L = r4ppo::make_layout(action_size);
+  size_t smem = (size_t)(r4ppo::TS * r4ppo::OBS + r4ppo::TS * r4ppo::HID + r4ppo::TS * action_size + r4ppo::TS) * 4;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(r4ppo::k_policy_act, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); attr = true; }
+  r4ppo::k_policy_act<<<(n + r4ppo::TS - 1) / r4ppo::TS, r4ppo::NT, smem, S(stream)>>>(
+      L, params, obs, mask, n, explore, seed, counter, action, logp, value, logits);
+  R4_PCHECK("k_policy_act");
+  return R4_OK;
+}
+
+int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                   const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                   const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                   float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                   float* flat_grad, float* stats_accum, float stat_scale, void* stream) {
+  if (!params || !obs || !mask || !action || !old_logits || !adv || !target || !scratch || !flat_grad || n < 1 ||
+      G < 1 || action_size < 2 || action_size > 512 || (mode == 0 && (!old_logp || !old_value)))
+    return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: bad argument");
+  r4ppo::Layout L = r4ppo::make_layout(action_size);
+  r4ppo::LossHyper hp{mode, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv_n};
+  size_t smem = (size_t)(((L.n + 3) & ~3) + r4ppo::TS * r4ppo::OBS + 2 * r4ppo::TS * r4ppo::HID +
+                         r4ppo::TS * action_size + 2 * r4ppo::TS) * 4;
+  if (smem > 226 * 1024) return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: action_size too large for the shared-memory accumulator");
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t st_ = cudaFuncSetAttribute(r4ppo::k_policy_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (st_ != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute(k_policy_grad): ") + cudaGetErrorString(st_));
+    attr = smem;
+  }
+  float* partial = scratch;
+  float* stat_partial = scratch + (size_t)G * L.n;
+  r4ppo::k_policy_grad<<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
+                                                         old_value, adv, target, idx, n, partial, stat_partial);
+  R4_PCHECK("k_policy_grad");
+  r4ppo::k_grad_reduce<<<(L.n + 255) / 256, 256, 0, S(stream)>>>(L.n, G, partial, flat_grad, stat_partial, stats_accum, stat_scale);
+  R4_PCHECK("k_grad_reduce");
+  return R4_OK;
+}
+
+int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, float clip, float* norm_scratch, void* stream) {
+  if (!params || !grad || !m || !v || n < 1 || step < 1 || (clip > 0.f && !norm_scratch))
+    return fail(nullptr, R4_ERR_ARG, "r4_adam_step: bad argument");
+  if (clip > 0.f) {
+    cudaMemsetAsync(norm_scratch, 0, 4, S(stream));
+    r4ppo::k_sumsq<<<32, 256, 0, S(stream)>>>(n, grad, norm_scratch);
+    R4_PCHECK("k_sumsq");
+  }
+  r4ppo::k_adam<<<(n + 255) / 256, 256, 0, S(stream)>>>(n, params, grad, m, v, step, lr, beta1, beta2, eps, grad_scale,
+                                                         clip > 0.f ? norm_scratch : nullptr, clip);
+  R4_PCHECK("k_adam");
   return R4_OK;
 }
 

@@ -8,7 +8,10 @@ Differences from the reference, by design (north_star):
   * data parallel over env rows: every rank rolls its own shard and ONE ``all_reduce`` over the flat
     34 973-parameter gradient (~140 KB) per optimizer step is the only collective
     (NCCL over NVLink on GPUs; gloo in the CPU tests).
-The policy math (forward, losses, Adam) uses torch ops on the device in this round.
+On a CUDA device the policy forward + sampling, the loss gradients (hand-derived backward) and Adam
+are the library's own kernels (csrc/r4_ppo.cuh through the C-ABI: r4_policy_act / r4_policy_grad /
+r4_adam_step), 2 launches per SGD step; the torch implementation below is kept as the CPU path of
+the tests and as the autograd cross-check of the kernels (tests/test_gpu_trainer.py).
 
 RLlib semantics kept: gamma = 1, GAE(lambda = 1) advantages from complete episodes, SoftQ(T=1)
 exploration = sampling from softmax(masked logits), argmax for evaluation; PPO: standardised
@@ -17,10 +20,61 @@ one SGD epoch, Adam 1e-4; A2C: summed losses, vf coeff 0.5, entropy 0.01, grad-n
 """
 import os
 
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
 from .policy import MaskedPolicy
+
+
+def _p(t, byte_offset=0):
+    return C.c_void_p(t.data_ptr() + byte_offset) if t is not None else C.c_void_p(0)
+
+
+class KernelOps(object):
+    """ctypes front of the K12 kernels (include/rl4rs_b200.h: r4_policy_act / r4_policy_grad / r4_adam_step)."""
+
+    def __init__(self, A, device, n_params):
+        from . import _capi
+        self.capi = _capi
+        self.lib = _capi.load_library()
+        self.A, self.device, self.n = A, device, n_params
+        assert self.lib.r4_policy_num_params(A) == n_params
+        z = lambda k: torch.zeros(k, dtype=torch.float32, device=device)
+        self.m, self.v, self.grad, self.stats, self.norm = z(n_params), z(n_params), z(n_params), z(5), z(1)
+        self.scratch = z(148 * (n_params + 5))
+        self.step = 0
+        self.counter = 0
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise self.capi.R4Error("%s failed (%d): %s" % (what, rc, (self.lib.r4_last_error(None) or b"?").decode()))
+
+    def act(self, flat, obs, mask, explore, seed, action_i32, logp, value, logits):
+        n = obs.shape[0]
+        rc = self.lib.r4_policy_act(_p(flat), _p(obs), _p(mask), n, self.A, int(bool(explore)), seed, self.counter,
+                                    _p(action_i32), _p(logp), _p(value), _p(logits), self._stream())
+        self._check(rc, "r4_policy_act")
+        self.counter += n
+
+    def policy_grad(self, mode, flat, data, idx, idx_offset, n, hp, inv_n, stat_scale):
+        obs, mask, act, logp, logits, val, adv, target = data
+        G = max(1, min((n + 15) // 16, 148))
+        rc = self.lib.r4_policy_grad(mode, _p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv),
+                                     _p(target), _p(idx, idx_offset * 8) if idx is not None else C.c_void_p(0), n, self.A,
+                                     hp["clip"], hp["vf_clip"], hp["vf_coeff"], hp["kl_coeff"], hp["ent_coeff"], inv_n,
+                                     _p(self.scratch), G, _p(self.grad), _p(self.stats), stat_scale, self._stream())
+        self._check(rc, "r4_policy_grad")
+
+    def adam(self, flat, lr, grad_scale, clip):
+        self.step += 1
+        rc = self.lib.r4_adam_step(_p(flat), _p(self.grad), _p(self.m), _p(self.v), self.n, self.step, lr, 0.9, 0.999,
+                                   1e-8, grad_scale, float(clip or 0.0), _p(self.norm), self._stream())
+        self._check(rc, "r4_adam_step")
 
 PPO_DEFAULTS = {"gamma": 1.0, "lambda": 1.0, "kl_coeff": 0.2, "sgd_minibatch_size": 256, "num_sgd_iter": 1,
                 "lr": 1e-4, "vf_loss_coeff": 0.5, "clip_param": 0.3, "vf_clip_param": 500.0, "kl_target": 0.01,
@@ -69,9 +123,11 @@ class _TrainerBase(object):
         self.A = env.config["action_size"]
         self.device = torch.device(device) if device is not None else env.sim.engine.device
         self.policy = MaskedPolicy(self.A, self.device, seed=seed)     # same init on every rank
-        self.use_graph = self.device.type == "cuda"
-        self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"], capturable=self.use_graph)
-        self._graphs = None
+        self.use_kernels = self.device.type == "cuda" and (config or {}).get("use_kernels", True)
+        self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
+        self.ops = KernelOps(self.A, self.device, self.policy.n_params) if self.use_kernels else None
+        self._act_i32 = torch.zeros(self.B, dtype=torch.int32, device=self.device)
+        self._seed = seed
         self.buf = RolloutBuffer(self.T, self.B, self.A, self.device)
         self.iteration = 0
         self.timesteps_total = 0
@@ -82,9 +138,15 @@ class _TrainerBase(object):
         env, buf = self.env, self.buf
         obs = env.reset()
         for t in range(self.T):
-            a, logp, value, logits = self.policy.act(obs["obs"], obs["action_mask"], explore=explore)
             buf.obs[t].copy_(obs["obs"]); buf.mask[t].copy_(obs["action_mask"])
-            buf.action[t].copy_(a); buf.logp[t].copy_(logp); buf.value[t].copy_(value); buf.logits[t].copy_(logits)
+            if self.use_kernels:       # forward + sampling in ONE kernel, written straight into the rollout buffers
+                a = self._act_i32
+                self.ops.act(self.policy.flat, buf.obs[t], buf.mask[t], explore, self._seed, a,
+                             buf.logp[t], buf.value[t], buf.logits[t])
+                buf.action[t].copy_(a)
+            else:
+                a, logp, value, logits = self.policy.act(obs["obs"], obs["action_mask"], explore=explore)
+                buf.action[t].copy_(a); buf.logp[t].copy_(logp); buf.value[t].copy_(value); buf.logits[t].copy_(logits)
             obs, reward, done, info = env.step(a)
             buf.reward[t].copy_(reward)
         return buf
@@ -133,8 +195,14 @@ class _TrainerBase(object):
             m = np.stack([np.asarray(obs[k]["action_mask"]) for k in keys])
             a = self.compute_actions({"obs": o, "action_mask": m}, explore)
             return dict(zip(keys, a.tolist()))
-        o = torch.as_tensor(obs["obs"], dtype=torch.float32, device=self.device)
+        o = torch.as_tensor(obs["obs"], dtype=torch.float32, device=self.device).contiguous()
         m = torch.as_tensor(obs["action_mask"], device=self.device)
+        if self.use_kernels:
+            n = o.shape[0]
+            a = torch.empty(n, dtype=torch.int32, device=self.device)
+            lp, v = torch.empty(n, device=self.device), torch.empty(n, device=self.device)
+            self.ops.act(self.policy.flat, o, m.to(torch.uint8).contiguous(), explore, self._seed, a, lp, v, None)
+            return a.cpu().numpy()
         a, _, _, _ = self.policy.act(o, m, explore=explore)
         return a.cpu().numpy()
 
@@ -142,7 +210,10 @@ class _TrainerBase(object):
     def save(self, checkpoint_dir):
         os.makedirs(checkpoint_dir, exist_ok=True)
         path = os.path.join(checkpoint_dir, "checkpoint_%06d.pt" % self.iteration)
-        torch.save({"algo": self.algo, "flat": self.policy.flat.detach().cpu(), "opt": self.opt.state_dict(),
+        kst = None
+        if self.use_kernels:
+            kst = {"m": self.ops.m.cpu(), "v": self.ops.v.cpu(), "step": self.ops.step}
+        torch.save({"algo": self.algo, "flat": self.policy.flat.detach().cpu(), "opt": self.opt.state_dict(), "kernel_adam": kst,
                     "iteration": self.iteration, "timesteps_total": self.timesteps_total,
                     "extra": self._extra_state()}, path)
         return path
@@ -153,6 +224,9 @@ class _TrainerBase(object):
         with torch.no_grad():
             self.policy.flat.copy_(st["flat"].to(self.device))
         self.opt.load_state_dict(st["opt"])
+        if self.use_kernels and st.get("kernel_adam"):
+            k = st["kernel_adam"]
+            self.ops.m.copy_(k["m"]); self.ops.v.copy_(k["v"]); self.ops.step = k["step"]
         self.iteration, self.timesteps_total = st["iteration"], st["timesteps_total"]
         self._load_extra_state(st["extra"])
 
@@ -205,7 +279,7 @@ class PPOTrainer(_TrainerBase):
         adv = (adv - mean) / torch.clamp((sq - mean ** 2).clamp_min(0).sqrt(), min=1e-4)
         mb = min(c["sgd_minibatch_size"], n)
         data = (obs, mask, act, logp, logits, val, adv, target)
-        agg, steps = (self._sgd_graphed if self.use_graph else self._sgd_eager)(data, n, mb)
+        agg, steps = (self._sgd_kernels if self.use_kernels else self._sgd_eager)(data, n, mb)
         out = {k: self._global_mean(v / max(steps, 1)) for k, v in agg.items()}
         # adaptive KL (RLlib KLCoeffMixin.update_kl)
         if out.get("kl", 0.0) > 2.0 * c["kl_target"]:
@@ -240,73 +314,26 @@ class PPOTrainer(_TrainerBase):
                 agg["total_loss"] = agg.get("total_loss", 0.0) + total.detach()
         return agg, steps
 
-    def _build_graphs(self, data, mb):
-        """Capture one SGD step as two CUDA graphs (forward+backward | clip+Adam) over static minibatch
-        buffers, so the 144 minibatch steps of an iteration cost a few launches each instead of ~60
-        eager torch kernels; the gradient all-reduce (N > 1) runs between the two graphs."""
+    def _sgd_kernels(self, data, n, mb):
+        """One launch pair per minibatch: r4_policy_grad (forward, RLlib surrogate loss, hand-derived backward,
+        deterministic reduction) + r4_adam_step; the flat-gradient all-reduce (N > 1) sits between them."""
         c = self.config
-        dev = self.device
-        static = [torch.zeros((mb,) + d.shape[1:], dtype=d.dtype, device=dev) for d in data]
-        kl_coeff = torch.tensor(float(self.kl_coeff), device=dev)
-        stats = torch.zeros(5, device=dev, dtype=torch.float32)
-        self.policy.flat.grad = torch.zeros_like(self.policy.flat)
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-
-        def fb():
-            self.policy.flat.grad.zero_()
-            kc, self.kl_coeff = self.kl_coeff, kl_coeff          # loss() reads the device scalar
-            total, st = self.loss(*static)
-            self.kl_coeff = kc
-            total.backward()
-            stats.add_(torch.stack([st["policy_loss"], st["vf_loss"], st["kl"], st["entropy"], total]).detach())
-
-        def opt():
-            if c["grad_clip"]:
-                torch.nn.utils.clip_grad_norm_([self.policy.flat], c["grad_clip"])
-            self.opt.step()
-
-        with torch.cuda.stream(side):
-            snap = self.policy.flat.detach().clone()
-            opt_state = None
-            for _ in range(3):                                    # warm-up (allocator, lazy Adam state)
-                fb(); opt()
-            with torch.no_grad():                                 # undo the warm-up updates
-                self.policy.flat.copy_(snap)
-            for st_ in self.opt.state.values():
-                for k_, v_ in st_.items():
-                    if torch.is_tensor(v_):
-                        v_.zero_()
-            stats.zero_()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        g_fb, g_opt = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g_fb):
-            fb()
-        with torch.cuda.graph(g_opt):
-            opt()
-        stats.zero_()
-        self._graphs = {"static": static, "kl": kl_coeff, "stats": stats, "fb": g_fb, "opt": g_opt, "mb": mb}
-
-    def _sgd_graphed(self, data, n, mb):
-        c = self.config
-        if self._graphs is None or self._graphs["mb"] != mb:
-            self._build_graphs(data, mb)
-        G = self._graphs
-        G["kl"].fill_(float(self.kl_coeff))
-        G["stats"].zero_()
+        ops = self.ops
+        data = tuple(d.contiguous() for d in data)
+        hp = {"clip": c["clip_param"], "vf_clip": c["vf_clip_param"], "vf_coeff": c["vf_loss_coeff"],
+              "kl_coeff": float(self.kl_coeff), "ent_coeff": c["entropy_coeff"]}
+        ops.stats.zero_()
         steps = 0
+        w = _world()
         for _ in range(c["num_sgd_iter"]):
-            perm = self._perm(n, data[0].device)
+            perm = self._perm(n, data[0].device).contiguous()
             for s in range(0, n - mb + 1, mb):
-                idx = perm[s:s + mb]
-                for dst, src in zip(G["static"], data):
-                    torch.index_select(src, 0, idx, out=dst)
-                G["fb"].replay()
-                self._allreduce_grad(average=True)
-                G["opt"].replay()
+                ops.policy_grad(0, self.policy.flat, data, perm, s, mb, hp, 1.0 / mb, 1.0 / mb)
+                if w > 1:
+                    dist.all_reduce(ops.grad, op=dist.ReduceOp.SUM)           # the ONE collective
+                ops.adam(self.policy.flat, c["lr"], 1.0 / w, c["grad_clip"])
                 steps += 1
-        st = G["stats"]
+        st = ops.stats
         agg = {"policy_loss": st[0], "vf_loss": st[1], "kl": st[2], "entropy": st[3], "total_loss": st[4]}
         return agg, steps
 
@@ -338,6 +365,22 @@ class A2CTrainer(_TrainerBase):
         target, adv = buf.returns_and_advantages(c["gamma"], c["lambda"])
         n = buf.T * buf.B
         flat = lambda x: x.reshape((n,) + x.shape[2:])
+        if self.use_kernels:
+            ops, w = self.ops, _world()
+            data = (flat(buf.obs), flat(buf.mask), flat(buf.action), None, flat(buf.logits), None,
+                    flat(adv).contiguous(), flat(target).contiguous())
+            hp = {"clip": 0.0, "vf_clip": 0.0, "vf_coeff": c["vf_loss_coeff"], "kl_coeff": 0.0, "ent_coeff": c["entropy_coeff"]}
+            ops.stats.zero_()
+            ops.policy_grad(1, self.policy.flat, data, None, 0, n, hp, 1.0, 1.0)
+            if w > 1:
+                dist.all_reduce(ops.grad, op=dist.ReduceOp.SUM)                # summed loss over the global batch
+            gn = ops.grad.norm()
+            ops.adam(self.policy.flat, c["lr"], 1.0, c["grad_clip"])
+            st = ops.stats
+            out = {"policy_loss": self._global_mean(st[0]) * w, "vf_loss": self._global_mean(st[1]) * w,
+                   "entropy": self._global_mean(st[3]) * w, "total_loss": self._global_mean(st[4]) * w,
+                   "grad_gnorm": float(gn), "sgd_steps": 1}
+            return out
         if self.policy.flat.grad is not None:
             self.policy.flat.grad.zero_()
         total, st = self.loss(flat(buf.obs), flat(buf.mask), flat(buf.action), flat(adv), flat(target))

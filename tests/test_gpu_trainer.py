@@ -27,3 +27,103 @@ def test_trainer_runs_on_cuda_env(algo, seq):
     assert bool((m == 1).all())
     assert tr.evaluate(1) >= 0
     assert torch.isfinite(tr.policy.flat).all()
+
+
+def _random_batch(n, A, dev, seed=0):
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    obs = torch.randn(n, 256, generator=g).to(dev)
+    mask = torch.zeros(n, A, dtype=torch.uint8)
+    for i in range(n):
+        lo, hi = [(1, 40), (40, 148), (148, A)][i % 3]
+        mask[i, lo:hi] = 1
+        mask[i, lo + (i % 5)] = 0
+    return obs, mask.to(dev)
+
+
+def test_policy_kernels_match_torch_autograd():
+    """K12: r4_policy_act / r4_policy_grad / r4_adam_step against the torch implementation (autograd, torch Adam)."""
+    import torch
+    from rl4rs_b200.policy import MaskedPolicy
+    from rl4rs_b200.trainer import KernelOps, PPOTrainer, A2CTrainer
+    dev = torch.device("cuda")
+    A, n = 284, 300
+    pol = MaskedPolicy(A, dev, seed=3)
+    with torch.no_grad():
+        pol.flat.add_(0.05 * torch.randn_like(pol.flat))
+    ops = KernelOps(A, dev, pol.n_params)
+    obs, mask = _random_batch(n, A, dev)
+    # ---- act: logits / value / logp, greedy action, sampling respects the mask and the distribution
+    a = torch.empty(n, dtype=torch.int32, device=dev)
+    lp, v, lg = torch.empty(n, device=dev), torch.empty(n, device=dev), torch.empty(n, A, device=dev)
+    ops.act(pol.flat, obs, mask, False, 1, a, lp, v, lg)
+    ta, tlp, tv, tlg = pol.act(obs, mask, explore=False)
+    assert torch.equal(a, ta)
+    assert torch.allclose(v, tv, rtol=1e-4, atol=1e-5) and torch.allclose(lp, tlp, rtol=1e-4, atol=1e-5)
+    ok = mask.bool()
+    assert torch.allclose(lg[ok], tlg[ok], rtol=1e-4, atol=1e-5) and bool((lg[~ok] < -1e30).all())
+    reps = 4000
+    o1, m1 = obs[:1].repeat(reps, 1).contiguous(), mask[:1].repeat(reps, 1).contiguous()
+    a1 = torch.empty(reps, dtype=torch.int32, device=dev)
+    ops.act(pol.flat, o1, m1, True, 7, a1, torch.empty(reps, device=dev), torch.empty(reps, device=dev), None)
+    assert bool(m1[0][a1.long()].all())
+    p = torch.softmax(tlg[0], -1)
+    freq = torch.bincount(a1.long(), minlength=A).float() / reps
+    assert float((freq - p).abs().max()) < 4.5 * float((p.max() * (1 - p.max()) / reps) ** 0.5) + 2e-3
+    # ---- gradients: PPO (mean) and A2C (sum) against autograd
+    g = torch.Generator(device="cpu").manual_seed(5)
+    act = torch.stack([torch.multinomial(mask[i].float().cpu(), 1, generator=g)[0] for i in range(n)]).to(dev)
+    old_logits = (tlg + 0.3 * torch.randn(n, A, generator=g).to(dev) * ok).contiguous()
+    old_logp = torch.log_softmax(old_logits, -1).gather(1, act.unsqueeze(1)).squeeze(1).contiguous()
+    old_v = (tv + torch.randn(n, generator=g).to(dev)).contiguous()
+    adv = torch.randn(n, generator=g).to(dev)
+    tgt = (old_v + 600 * torch.randn(n, generator=g).to(dev)).contiguous()      # exercises the vf clip (500)
+
+    class _E(object):
+        config = {"max_steps": 3, "batch_size": 100, "action_size": A}
+        sim = type("S", (), {"engine": type("X", (), {"device": dev})()})()
+
+    for cls, mode in ((PPOTrainer, 0), (A2CTrainer, 1)):
+        tr = cls({"entropy_coeff": 0.01, "use_kernels": False}, _E(), device=dev)
+        tr.policy = pol
+        if pol.flat.grad is not None:
+            pol.flat.grad.zero_()
+        if mode == 0:
+            tr.kl_coeff = 0.2
+            total, st = tr.loss(obs, mask, act, old_logp, old_logits, old_v, adv, tgt)
+            hp = {"clip": 0.3, "vf_clip": 500.0, "vf_coeff": 0.5, "kl_coeff": 0.2, "ent_coeff": 0.01}
+            inv_n, scale = 1.0 / n, 1.0 / n
+        else:
+            total, st = tr.loss(obs, mask, act, adv, tgt)
+            hp = {"clip": 0.0, "vf_clip": 0.0, "vf_coeff": 0.5, "kl_coeff": 0.0, "ent_coeff": 0.01}
+            inv_n, scale = 1.0, 1.0
+        total.backward()
+        ref = pol.flat.grad.detach().clone()
+        ops.stats.zero_()
+        ops.policy_grad(mode, pol.flat, (obs, mask, act, old_logp, old_logits, old_v, adv, tgt), None, 0, n, hp, inv_n, scale)
+        err = (ops.grad - ref).abs().max() / ref.abs().max()
+        assert float(err) < 2e-5, (cls.__name__, float(err))
+        assert abs(float(ops.stats[4]) - float(total)) <= 1e-4 * abs(float(total)), (float(ops.stats[4]), float(total))
+        # minibatch through an index list == the same rows gathered
+        idx = torch.randperm(n, generator=g)[:128].to(dev)
+        ops.policy_grad(mode, pol.flat, (obs, mask, act, old_logp, old_logits, old_v, adv, tgt), idx, 0, 128, hp,
+                 1.0 / 128 if mode == 0 else 1.0, 1.0)
+        g_idx = ops.grad.clone()
+        sel = tuple(x[idx].contiguous() for x in (obs, mask, act, old_logp, old_logits, old_v, adv, tgt))
+        ops.policy_grad(mode, pol.flat, sel, None, 0, 128, hp, 1.0 / 128 if mode == 0 else 1.0, 1.0)
+        assert torch.equal(g_idx, ops.grad)                                   # deterministic reduction
+    # ---- Adam: three steps against torch.optim.Adam, with and without clipping
+    for clip in (0.0, 0.5):
+        p_t = pol.flat.detach().clone().requires_grad_(True)
+        p_k = pol.flat.detach().clone()
+        opt = torch.optim.Adam([p_t], lr=1e-3)
+        ops2 = KernelOps(A, dev, pol.n_params)
+        for it in range(3):
+            gr = torch.randn(pol.n_params, generator=g).to(dev) * (it + 1)
+            p_t.grad = gr.clone()
+            if clip:
+                torch.nn.utils.clip_grad_norm_([p_t], clip)
+            opt.step()
+            ops2.grad.copy_(gr)
+            ops2.adam(p_k, 1e-3, 1.0, clip)
+        assert torch.allclose(p_k, p_t.detach(), rtol=1e-5, atol=1e-7), float((p_k - p_t.detach()).abs().max())
