@@ -133,6 +133,7 @@ struct AugruTcSeq {
 struct AugruTcParams {
   AugruTcSeq s[2];
   int R, row0, div, out_ld;
+  long long* dbg;         // optional: per-step phase timestamps of CTA 0 (development probe), else null
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {

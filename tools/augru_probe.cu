@@ -1,6 +1,18 @@
 // augru_probe.cu -- standalone check + timing of k_augru_tc against a CPU (f64) recurrence.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/build/augru_probe tools/augru_probe.cu
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
+#ifdef V2
+#include "experiments/r4_augru_tc2.cuh"
+#define KERNEL r4tc2::k_augru_tc2
+#define KSMEM r4tc2::SMEM2_BYTES
+#define KTHREADS r4tc2::NTHREADS2
+#define GRIDX(t) (2 * (t))
+#else
+#define KERNEL k_augru_tc
+#define KSMEM SMEM_BYTES
+#define KTHREADS NTHREADS
+#define GRIDX(t) (t)
+#endif
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -15,7 +27,11 @@ static float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; mem
 
 void build_image(const std::vector<float>& Wg, const std::vector<float>& Wc, std::vector<uint8_t>& img) {
   img.assign(W_IMAGE_BYTES, 0);
+#ifdef V2
+  r4tc2::build_weight_image2(Wg.data(), Wc.data(), img.data());
+#else
   build_weight_image(Wg.data(), Wc.data(), img.data());
+#endif
 }
 
 int main(int argc, char** argv) {
@@ -56,11 +72,11 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dXT, XT.data(), XT.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsT, sT.data(), sT.size() * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0, (size_t)R * 256 * 4));
-  CK(cudaFuncSetAttribute(k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, KSMEM));
   AugruTcParams p{};
   p.s[0] = {dXT, dimg, dsT, dout, 0}; p.s[1] = p.s[0];
   p.R = R; p.row0 = 0; p.div = div; p.out_ld = 256;
-  k_augru_tc<<<dim3(rtiles, 1), NTHREADS, SMEM_BYTES>>>(p);
+  KERNEL<<<dim3(GRIDX(rtiles), 1), KTHREADS, KSMEM>>>(p);
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   std::vector<float> hout((size_t)R * 256);
   CK(cudaMemcpy(hout.data(), dout, hout.size() * 4, cudaMemcpyDeviceToHost));
@@ -76,16 +92,28 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dsT2, (size_t)timing_tiles * 64 * TM * 4)); CK(cudaMalloc(&dout2, (size_t)RT * 256 * 4));
     CK(cudaMemset(dsT2, 0, (size_t)timing_tiles * 64 * TM * 4));
     AugruTcParams q = p; q.s[0].scoresT = dsT2; q.s[0].out = dout2; q.s[0].shared = 1; q.R = RT; q.s[1] = q.s[0];
+    long long* ddbg; CK(cudaMalloc(&ddbg, 64 * 16 * 8)); CK(cudaMemset(ddbg, 0, 64 * 16 * 8));
+    q.dbg = ddbg;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
       cudaEventRecord(e0);
-      k_augru_tc<<<dim3(timing_tiles, 1), NTHREADS, SMEM_BYTES>>>(q);
+      KERNEL<<<dim3(GRIDX(timing_tiles), 1), KTHREADS, KSMEM>>>(q);
       cudaEventRecord(e1); CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       double flops = (double)RT * 64 * 2.0 * (256 * 512 + 256 * 256);
+      if (it == 2) {
+        long long hd[64 * 16]; CK(cudaMemcpy(hd, ddbg, sizeof(hd), cudaMemcpyDeviceToHost));
+        if (hd[16 * 10]) for (int t = 10; t < 13; ++t) {
+          long long* d = hd + t * 16;
+          printf("  step %d: waitU %lld | U %lld | waitR %lld | R %lld | waitC %lld | C %lld | total %lld\n", t, d[1] - d[0], d[2] - d[1],
+                 d[3] - d[2], d[4] - d[3], d[5] - d[4], d[6] - d[5], hd[(t + 1) * 16] - d[0]);
+          printf("      R detail: 2 chunks %lld | publish %lld | 2 chunks %lld | publish %lld\n", d[8] - d[3], d[9] - d[8], d[10] - d[9], d[11] - d[10]);
+        }
+      }
       printf("timing: %d tiles (%d rows) %.3f ms -> %.1f TFLOP/s fp32-equivalent, %.0f cycles/step @1.965GHz\n", timing_tiles, RT, ms,
-             flops / ms / 1e9, ms * 1e-3 * 1.965e9 / 64 / ((timing_tiles + 147) / 148));
+             flops / ms / 1e9, ms * 1e-3 * 1.965e9 / 64 / ((GRIDX(timing_tiles) + 147) / 148));
     }
   }
   return 0;
 }
+
