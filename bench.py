@@ -339,7 +339,7 @@ def main():
         line["kernels"] = [{"name": k["name"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 4),
                             "launches": k["launches"]} for k in sorted(kernels, key=lambda k: -k["ms"])]
         # feature-gather path against the HBM roofline (G = 83 732 B / row-forward)
-        gk = [k for k in kernels if k["name"] in ("k_scores", "k_cat_attn", "k_assemble")]
+        gk = [k for k in kernels if k["name"] in ("k_scores_tc", "k_cat_attn", "k_assemble")]
         if gk:
             rows = (T + 1) * B + B * T           # obs rows + reward rows of one episode
             gms = sum(k["ms"] for k in gk)

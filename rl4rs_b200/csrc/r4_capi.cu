@@ -4,11 +4,13 @@
 #include "r4_kernels.cuh"
 #include "r4_augru_tc.cuh"
 #include "r4_gemm_tc.cuh"
+#include "r4_scores_tc.cuh"
 #include "r4_ppo.cuh"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -35,7 +37,7 @@ struct PerSeq {
   float *gru_wx = nullptr, *gru_bx = nullptr, *gru_wgh = nullptr, *gru_wch = nullptr;
   float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
-  uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
+  uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
   uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   float abk = 0.f;
 };
@@ -82,7 +84,7 @@ struct r4_env {
   SeqCache c0, c1const, c1page;
   bool c1_is_page = false;
   // workspaces
-  DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1;
+  DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1, ws_q;
   // side stream: category attention + dense tower run concurrently with scores + AUGRU (they only
   // meet at the head GEMM), which fills the SMs the 128-row AUGRU tiles leave idle at small batch
   cudaStream_t side = nullptr;
@@ -106,8 +108,8 @@ int fail(r4_env* e, int code, const std::string& msg) {
 enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
        SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_XT, SL_MISC, SL_COUNT };
 const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm[gru1 input proj + E_s gather]",
-    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
-    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "misc"};
+    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores_tc", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
+    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "k_query"};
 
 // Brackets one launch with CUDA events on the launching stream when profiling is on.
 struct ProfScope {
@@ -230,46 +232,57 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   if ((rc = reserve(e, e->ws_scores, 2 * sc_per_seq * 4))) return rc;
   if ((rc = reserve(e, e->ws_allf, (size_t)R * ALLF * 4))) return rc;
   if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
+  if ((rc = reserve(e, e->ws_q, (size_t)R * (r4tc::S_K + 2 * r4tc::S_N) * 4))) return rc;
+  float* qbuf = reinterpret_cast<float*>(e->ws_q.p);
+  float* qa0 = qbuf + (size_t)R * r4tc::S_K;
+  float* qa1 = qa0 + (size_t)R * r4tc::S_N;
   float* scores = reinterpret_cast<float*>(e->ws_scores.p);
   float* allf = reinterpret_cast<float*>(e->ws_allf.p);
   float* tmp = reinterpret_cast<float*>(e->ws_tmp.p);
   const SeqCache* cs[2] = {&c0, &c1};
   int sh[2] = {shared0, shared1};
-  ScoreParams sp{};
+  r4tc::ScoreTcParams sp{};
   r4tc::AugruTcParams rp{};
   for (int i = 0; i < 2; ++i) {
     const PerSeq& w = e->ps[i];
-    ScoreSeq& s = sp.s[i];
+    r4tc::ScoreTcSeq& s = sp.s[i];
     s.H = reinterpret_cast<const float*>(cs[i]->H.p);
     s.XK = reinterpret_cast<const float*>(cs[i]->XK.p);
-    s.Wqd = w.wqd; s.Wp = w.wp; s.b1 = w.ab1; s.W2 = w.aw2; s.b2 = w.ab2; s.kv = w.akv; s.bk = w.abk;
-    s.scores = scores + (size_t)i * sc_per_seq;
+    s.qa = i ? qa1 : qa0; s.WpImg = w.wp_img; s.Wqd = w.wqd; s.b1 = w.ab1; s.W2 = w.aw2; s.b2 = w.ab2; s.kv = w.akv; s.bk = w.abk;
+    s.scoresT = scores + (size_t)i * sc_per_seq;
     s.shared = sh[i];
     r4tc::AugruTcSeq& q = rp.s[i];
-    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = w.au_img; q.scoresT = s.scores;
+    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = w.au_img; q.scoresT = s.scoresT;
     q.out = allf + i * AUH; q.shared = sh[i];
   }
-  sp.R = R; sp.row0 = row0; sp.div = div; sp.transposed = 1;
+  sp.R = R; sp.row0 = row0; sp.div = div; sp.q = qbuf;
   rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF;
   // fork: side stream does the action-independent-of-AUGRU half of the feature vector
-  R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
-  R4_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  static const bool no_side = getenv("R4_NO_SIDE_STREAM") != nullptr;   // diagnostics: serialise for clean per-kernel times
+  if (!no_side) {
+    R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
+    R4_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+  }
   {
-    cudaStream_t ss = e->side;
+    cudaStream_t ss = no_side ? st : e->side;
     { ProfScope ps(e, SL_CAT, ss, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
       k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, ss>>>(R, cat, e->emb_cat, allf); }
     R4_LAUNCH_CHECK(e, "k_cat_attn");
     if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, ss))) return rc;
     if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF, ss))) return rc;
-    R4_CUDA(e, cudaEventRecord(e->ev_join, ss));
+    if (!no_side) R4_CUDA(e, cudaEventRecord(e->ev_join, ss));
   }
+  { ProfScope ps(e, SL_MISC, st, (double)R);
+    r4tc::k_query<<<(R + 7) / 8, 128, 0, st>>>(R, cat, e->emb_seq, e->ps[0].wqd, e->ps[0].ab1, e->ps[1].wqd, e->ps[1].ab1,
+                                                qbuf, qa0, qa1); }
+  R4_LAUNCH_CHECK(e, "k_query");
   { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
-    k_scores<<<dim3(R, 2), 256, SMEM_SCORES, st>>>(sp, cat, e->emb_seq); }
-  R4_LAUNCH_CHECK(e, "k_scores");
+    r4tc::k_scores_tc<<<dim3(std::min((R + 1) / 2, 74), 2), r4tc::S_THREADS, r4tc::S_SMEM_BYTES, st>>>(sp, cat, e->emb_seq); }
+  R4_LAUNCH_CHECK(e, "k_scores_tc");
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
     r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp); }
   R4_LAUNCH_CHECK(e, "k_augru_tc");
-  R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
+  if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
   if (!obs) {
     if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
@@ -411,7 +424,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   cudaFuncSetAttribute(k_recur<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_128);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
-  cudaFuncSetAttribute(k_scores, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_SCORES);
+  cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
   st = cudaGetLastError();
   if (st != cudaSuccess) { r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(st)); }
@@ -433,7 +446,7 @@ void r4_destroy(r4_env* e) {
   DevBuf* bufs[] = {&e->c0.H, &e->c0.XK, &e->c1const.H, &e->c1const.XK, &e->c1page.H, &e->c1page.XK,
                     &e->c0.XT, &e->c1const.XT, &e->c1page.XT,
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
-                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1};
+                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -553,6 +566,11 @@ int r4_finalize_weights(r4_env* e, void* stream) {
     }
     if ((rc = upload_image(e, wx.data(), EMB, XIN_LD, &w.gru_wx_img)) ||
         (rc = upload_image(e, awx.data(), EMB, XK_LD, &w.au_wx_img))) return rc;
+    {
+      std::vector<uint8_t> wpi(r4tc::S_B_BYTES);
+      r4tc::build_scores_image(wp.data(), wpi.data());
+      if ((rc = upload(e, wpi, &w.wp_img))) return rc;
+    }
     std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
     r4tc::build_weight_image(awgh.data(), awch.data(), img.data());
     if ((rc = upload(e, img, &w.au_img))) return rc;

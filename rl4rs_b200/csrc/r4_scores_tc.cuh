@@ -1,0 +1,256 @@
+// r4_scores_tc.cuh -- K8 on tcgen05: DIN local-activation scores (deepctr AttentionSequencePoolingLayer
+// (att_hidden_units=(64,16), return_score=True, weight_normalization=False); nets/utils.py:114-115,121-122).
+//
+//   q      = mean_j E_s[cat[-10:]]                                     (query, per feature row)
+//   z1_t   = sigmoid(q (Wq+Wd) + b1 + k_t (Wk-Wd) + (q * k_t) Wp)       k_t = GRU-1 output t (cached H)
+//   z2_t   = sigmoid(z1_t W2 + b2);   score_t = z2_t . kv + b           (raw, unbounded)
+//
+// The only GEMM-shaped term, (q*k_t) Wp, is a [64 keys x 128] x [128 x 64] product per (row, sequence).  Two
+// feature rows are stacked into one UMMA tile (M = 128 key rows, N = 64, K = 128).  Persistent CTAs loop over
+// tiles; producer warps gather the 10 slate embeddings, build A = q*H as bf16 hi/lo core matrices (double
+// buffered), one lane issues 5 MMAs per K16 (A hi/lo x Wp hi/mid/lo: 2-way x 3-way split), epilogue warps
+// (lane = key) add q(Wq+Wd)+b1 and the cached key half, run the 64->16->1 tail in registers and write the
+// scores in the lane-major tile layout k_augru_tc reads.
+#pragma once
+#include "r4_augru_tc.cuh"
+
+namespace r4tc {
+
+constexpr int S_K = 128, S_N = 64, S_KEYS = 64;
+constexpr int S_A_SPLIT = TM * S_K * 2;            // 32 KB per split
+constexpr int S_A_STAGE = 2 * S_A_SPLIT;           // hi + lo = 64 KB
+constexpr int S_B_SPLIT = S_N * S_K * 2;           // 16 KB per split
+constexpr int S_B_BYTES = 3 * S_B_SPLIT;           // 48 KB, resident
+constexpr int S_SBO = (S_K / 8) * 128;             // 2048: 8-row groups (A and B)
+constexpr int S_SMEM_BYTES = 2 * S_A_STAGE + S_B_BYTES + 1024;
+constexpr int S_THREADS = 320;                     // 4 producer + 4 epilogue + MMA + loader warps
+constexpr int S_XK_LD = 832, S_XK_K = 768;         // cached key half lives in XK[..., 768:832]
+
+// host: Wp [128 k][64 n] fp32 -> 3 splits of [64 n x 128 k] K-major core matrices
+inline void build_scores_image(const float* Wp, uint8_t* img) {
+  for (int sp = 0; sp < 3; ++sp)
+    for (int n = 0; n < S_N; ++n)
+      for (int k = 0; k < S_K; ++k) {
+        float w = Wp[(size_t)k * S_N + n];
+        uint16_t hi = host_bf16_bits(w);
+        float r1 = w - host_bf16_val(hi);
+        uint16_t mid = host_bf16_bits(r1);
+        uint16_t lo = host_bf16_bits(r1 - host_bf16_val(mid));
+        uint16_t v = sp == 0 ? hi : (sp == 1 ? mid : lo);
+        memcpy(img + (size_t)sp * S_B_SPLIT + (n / 8) * S_SBO + (k / 8) * LBO + (n % 8) * 16 + (k % 8) * 2, &v, 2);
+      }
+}
+
+struct ScoreTcSeq {
+  const float* qa;       // [R, 64]  q (Wq+Wd) + b1, from k_query
+  const float* H;        // [n_cached, 64, 128]
+  const float* XK;       // [n_cached, 64, 832]
+  const uint8_t* WpImg;  // S_B_BYTES
+  const float* Wqd;      // [128, 64]
+  const float* b1;       // [64]
+  const float* W2;       // [64, 16]
+  const float* b2;       // [16]
+  const float* kv;       // [16]
+  float bk;
+  float* scoresT;        // [ceil(R/128), 64, 128]
+  int shared;
+};
+struct ScoreTcParams {
+  ScoreTcSeq s[2];
+  const float* q;        // [R, 128]  mean of the 10 slate embeddings, from k_query
+  int R, row0, div;
+};
+
+// q = reduce_mean(E_s[cat[-10:]]) and qa_i = q (Wq_i + Wd_i) + b1_i for both sequences (nets/utils.py:114-115 and
+// the query half of :121-122).  8 rows per CTA, 128 threads.  Keeping this out of k_scores_tc takes two dependent
+// HBM round trips (category ids -> embedding rows) and a 128-long serial FMA chain off its per-tile critical path.
+__global__ void __launch_bounds__(128) k_query(int R, const int32_t* __restrict__ cat, const float* __restrict__ emb_seq,
+                                               const float* __restrict__ Wqd0, const float* __restrict__ b10,
+                                               const float* __restrict__ Wqd1, const float* __restrict__ b11,
+                                               float* __restrict__ q_out, float* __restrict__ qa0, float* __restrict__ qa1) {
+  __shared__ float q_s[8][S_K];
+  const int tid = threadIdx.x, r0 = blockIdx.x * 8;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    int r = min(r0 + i, R - 1);
+    const int32_t* crow = cat + (size_t)r * 21;
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) acc += __ldg(emb_seq + (size_t)crow[11 + j] * S_K + tid);
+    acc = acc / 10.0f;
+    q_s[i][tid] = acc;
+    if (r0 + i < R) q_out[(size_t)(r0 + i) * S_K + tid] = acc;
+  }
+  __syncthreads();
+  const int sq = tid >> 6, j = tid & 63;
+  const float* W = sq ? Wqd1 : Wqd0;
+  float acc[8];
+  const float b = __ldg((sq ? b11 : b10) + j);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = b;
+#pragma unroll 4
+  for (int k = 0; k < S_K; ++k) {
+    float w = __ldg(W + k * S_N + j);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(q_s[i][k], w, acc[i]);
+  }
+  float* o = sq ? qa1 : qa0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) if (r0 + i < R) o[(size_t)(r0 + i) * S_N + j] = acc[i];
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, const int32_t* __restrict__ cat,
+                                                            const float* __restrict__ emb_seq) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sA = smem;                           // 2 stages x (hi, lo)
+  uint8_t* sB = smem + 2 * S_A_STAGE;           // Wp hi/mid/lo
+  __shared__ uint64_t bar_afull[2], bar_aempty[2], bar_tfull[2], bar_tempty[2], bar_w;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float W2_s[S_N * 16];
+  __shared__ float b2_s[16], kv_s[16];
+  const ScoreTcSeq& S = p.s[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ntiles = (p.R + 1) / 2;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar_afull[i], 128); mbar_init(&bar_aempty[i], 1);
+      mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 128);
+    }
+    mbar_init(&bar_w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int i = tid; i < S_N * 16; i += S_THREADS) W2_s[i] = __ldg(S.W2 + i);
+  if (tid < 16) { b2_s[tid] = __ldg(S.b2 + tid); kv_s[tid] = __ldg(S.kv + tid); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 9) {
+    if (lane == 0) {                                   // Wp image: once per CTA
+      mbar_expect_tx(&bar_w, S_B_BYTES);
+      bulk_g2s(sB, S.WpImg, S_B_BYTES, &bar_w);
+    }
+  } else if (warp == 8) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TM, S_N);
+      mbar_wait(&bar_w, 0);
+      const uint32_t b0 = smem_u32(sB);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it & 1;
+        const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(&bar_afull[s], ph);
+        mbar_wait(&bar_tempty[s], ph ^ 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + s * S_A_STAGE);
+        const uint32_t d = tbase + s * S_N;
+#pragma unroll
+        for (int j = 0; j < S_K / 16; ++j) {
+          const uint32_t ko = j * 2 * LBO;
+          uint64_t ah = make_desc(a0 + ko, LBO, S_SBO), al = make_desc(a0 + S_A_SPLIT + ko, LBO, S_SBO);
+          uint64_t bh = make_desc(b0 + ko, LBO, S_SBO), bm = make_desc(b0 + S_B_SPLIT + ko, LBO, S_SBO);
+          uint64_t bl = make_desc(b0 + 2 * S_B_SPLIT + ko, LBO, S_SBO);
+          mma_bf16(d, al, bm, idesc, j ? 1u : 0u);
+          mma_bf16(d, ah, bl, idesc, 1u);
+          mma_bf16(d, al, bh, idesc, 1u);
+          mma_bf16(d, ah, bm, idesc, 1u);
+          mma_bf16(d, ah, bh, idesc, 1u);
+        }
+        umma_commit(&bar_aempty[s]);
+        umma_commit(&bar_tfull[s]);
+      }
+    }
+  } else if (warp < 4) {
+    // ===== producers: q (10 gathered embeddings) and A = q * H as bf16 hi/lo =====
+    const int kc = tid & 3;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&bar_aempty[s], ph ^ 1);          // MMA finished reading this A stage
+      uint8_t* a = sA + s * S_A_STAGE;
+#pragma unroll 2
+      for (int kb = 0; kb < S_K / 32; ++kb) {
+#pragma unroll
+        for (int i4 = 0; i4 < 4; ++i4) {
+          const int m = i4 * 32 + (tid >> 2);          // tile row: feature row m/64, key m%64
+          const int rr = m >> 6, key = m & 63;
+          int r = min(tile * 2 + rr, p.R - 1);
+          const size_t ci = S.shared ? 0 : (size_t)((p.row0 + r) / p.div);
+          const int k = kb * 32 + kc * 8;
+          const float* hp = S.H + (ci * S_KEYS + key) * S_K + k;
+          float4 h0 = __ldg(reinterpret_cast<const float4*>(hp)), h1 = __ldg(reinterpret_cast<const float4*>(hp + 4));
+          const float* qp = p.q + (size_t)r * S_K + k;
+          float4 q0 = __ldg(reinterpret_cast<const float4*>(qp)), q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+          float v[8] = {h0.x * q0.x, h0.y * q0.y, h0.z * q0.z, h0.w * q0.w,
+                        h1.x * q1.x, h1.y * q1.y, h1.z * q1.z, h1.w * q1.w};
+          uint4 hi, lo;
+          split8(v, hi, lo);
+          const uint32_t off = (uint32_t)(m / 8) * S_SBO + (uint32_t)(k / 8) * LBO + (uint32_t)(m % 8) * 16;
+          *reinterpret_cast<uint4*>(a + off) = hi;
+          *reinterpret_cast<uint4*>(a + S_A_SPLIT + off) = lo;
+        }
+      }
+      proxy_fence();
+      mbar_arrive(&bar_afull[s]);
+    }
+  } else if (warp < 8) {
+    // ===== epilogue: lane = key row of the tile =====
+    const int e = tid - 128;                     // 0..127
+    const int ew = e >> 5;                       // TMEM lane quarter (warp 4..7 -> 0..3)
+    const int rr = e >> 6, key = e & 63;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int r = tile * 2 + rr;
+      const int rc = min(r, p.R - 1);
+      const size_t ci = S.shared ? 0 : (size_t)((p.row0 + rc) / p.div);
+      mbar_wait(&bar_tfull[s], ph);
+      tc_fence_after();
+      float z[S_N];
+      const uint32_t ta = tbase + ((uint32_t)(ew * 32) << 16) + s * S_N;
+#pragma unroll
+      for (int c = 0; c < S_N; c += 16) tmem_ld16(ta + c, z + c);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&bar_tempty[s]);               // accumulators are free again
+      const float* kp = S.XK + (ci * S_KEYS + key) * S_XK_LD + S_XK_K;
+      const float* qap = S.qa + (size_t)rc * S_N;
+      float o[16];
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) o[jj] = b2_s[jj];
+#pragma unroll
+      for (int j = 0; j < S_N; j += 4) {
+        float4 kk = __ldg(reinterpret_cast<const float4*>(kp + j));
+        float4 qq = __ldg(reinterpret_cast<const float4*>(qap + j));
+        float zz[4] = {z[j] + qq.x + kk.x, z[j + 1] + qq.y + kk.y, z[j + 2] + qq.z + kk.z, z[j + 3] + qq.w + kk.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float a1 = fast_sigmoid(zz[u]);        // ex2.approx + rcp.approx (2^-22 / 1 ulp), as in the AUGRU gates
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) o[jj] = fmaf(a1, W2_s[(j + u) * 16 + jj], o[jj]);
+        }
+      }
+      float sc = S.bk;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) sc = fmaf(fast_sigmoid(o[jj]), kv_s[jj], sc);
+      if (r < p.R) S.scoresT[((size_t)(r >> 7) * S_KEYS + key) * 128 + (r & 127)] = sc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(128));
+}
+
+}  // namespace r4tc
