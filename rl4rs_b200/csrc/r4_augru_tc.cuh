@@ -370,27 +370,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512));
 }
 
-// XK [n, 64, xk_ld] (row-major cache rows) -> XT [ceil(n/128), 64, 768, 128] (lane-major) for the TC kernel.
-// Handles cache rows [cr_base, cr_base + n_here); XK points at row cr_base.
-__global__ void k_transpose_x(int cr_base, int n_here, const float* __restrict__ XK, int xk_ld, float* __restrict__ XT) {
-  __shared__ float tile[32][33];
-  int t = blockIdx.z;
-  int l0 = blockIdx.x * 32, col0 = blockIdx.y * 32;
-  int tx = threadIdx.x, ty = threadIdx.y;     // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    int l = l0 + i;
-    tile[i][tx] = (l < n_here) ? XK[((size_t)l * STEPS + t) * xk_ld + col0 + tx] : 0.f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    int col = col0 + i, l = l0 + tx;
-    if (l < n_here) {
-      int cr = cr_base + l;
-      XT[(((size_t)(cr / TM) * STEPS + t) * XT_COLS + col) * TM + (cr % TM)] = tile[tx][i];
-    }
-  }
-}
-
 // host: fp32 recurrent weights -> the pre-tiled bf16 hi/lo stream image (order u, r, c; 8 K blocks; hi, lo).
 // Wg: [256][512] rows = h index, columns [r | u];  Wc: [256][256].
 inline uint16_t host_bf16_bits(float x) {

@@ -5,6 +5,7 @@
 #include "r4_augru_tc.cuh"
 #include "r4_gemm_tc.cuh"
 #include "r4_scores_tc.cuh"
+#include "r4_gru_tc.cuh"
 #include "r4_ppo.cuh"
 
 #include <algorithm>
@@ -27,9 +28,9 @@ struct DevBuf {
 };
 
 struct SeqCache {   // one cached (sequence, weight-set): GRU-1 outputs + AUGRU/attention input halves
-  DevBuf H;         // f32 [n, 64, 128]
-  DevBuf XK;        // f32 [n, 64, 832]
-  DevBuf XT;        // f32 [ceil(n/128), 64, 768, 128]: the AUGRU input halves, lane-major tiles (k_augru_tc)
+  DevBuf H;         // f32 [n, 64, 128]            GRU-1 outputs
+  DevBuf Kp;        // f32 [n, 64, 64]             attention key half k_t (Wk - Wd)
+  DevBuf XT;        // f32 [ceil(n/128), 64, 768, 128]: AUGRU input halves [r|u|c] (+bias), lane-major tiles
   int n = 0;
 };
 
@@ -37,7 +38,7 @@ struct PerSeq {
   float *gru_wx = nullptr, *gru_bx = nullptr, *gru_wgh = nullptr, *gru_wch = nullptr;
   float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
-  uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
+  uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr, *gru_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
   uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   float abk = 0.f;
 };
@@ -107,9 +108,9 @@ int fail(r4_env* e, int code, const std::string& msg) {
 
 enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
        SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_XT, SL_MISC, SL_COUNT };
-const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm[gru1 input proj + E_s gather]",
-    "k_recur<128>[GRU-1]", "k_gemm[augru/att input proj]", "k_scores_tc", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
-    "k_gemm[dense tower]", "k_gemm[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "k_query"};
+const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm_tc[gru1 input proj + E_s gather]",
+    "k_gru_tc[GRU-1 tcgen05]", "k_gemm_tc[augru/att input proj]", "k_scores_tc", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
+    "k_gemm_tc[dense tower]", "k_gemm_tc[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "k_query"};
 
 // Brackets one launch with CUDA events on the launching stream when profiling is on.
 struct ProfScope {
@@ -165,11 +166,12 @@ int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
-         const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st) {
+         const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
+         int ldT = 0, float* outT = nullptr, float* outK = nullptr) {
   if (M <= 0) return R4_OK;
   if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
-  r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act};
+  r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act, tm_ns, cr_base, ldT, outT, outK};
   dim3 grid((M + r4tc::G_BM - 1) / r4tc::G_BM, (N + r4tc::G_BNMAX - 1) / r4tc::G_BNMAX);
   r4tc::k_gemm_tc<<<grid, r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
   R4_LAUNCH_CHECK(e, "k_gemm_tc");
@@ -182,42 +184,35 @@ int upload_image(r4_env* e, const float* W, int K, int N, uint8_t** out) {
   return upload(e, img, out);
 }
 
-constexpr int SMEM_RECUR_128 = (128 * 64 * 2 + 64 * 64) * 4;
-constexpr int SMEM_SCORES = SC_SMEM_FLOATS * 4;
 constexpr int SMEM_CAT = 4 * (NCAT * CAT_LD + NCAT * 24) * 4;
 
-// GRU-1 + input projections of one sequence set (nets/utils.py:113,120 and the x-halves of
-// :121-124).  ids: i32 [n,64] device.  Chunked so the input-projection scratch stays bounded.
+// GRU-1 + input projections of one sequence set (nets/utils.py:113,120 and the x-halves of :121-124).
+// ids: i32 [n,64] device.  Chunked (multiples of 128 sequences) so the input-projection scratch stays bounded.
 int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaStream_t st) {
   int rc;
+  const int TM = r4tc::TM;
   if ((rc = reserve(e, c.H, (size_t)n * MAXLEN * EMB * 4))) return rc;
-  if ((rc = reserve(e, c.XK, (size_t)n * MAXLEN * XK_LD * 4))) return rc;
-  if ((rc = reserve(e, c.XT, (size_t)((n + r4tc::TM - 1) / r4tc::TM) * MAXLEN * r4tc::XT_COLS * r4tc::TM * 4))) return rc;
+  if ((rc = reserve(e, c.Kp, (size_t)n * MAXLEN * AH1 * 4))) return rc;
+  if ((rc = reserve(e, c.XT, (size_t)((n + TM - 1) / TM) * MAXLEN * r4tc::XT_COLS * TM * 4))) return rc;
   c.n = n;
   const PerSeq& w = e->ps[si];
   const int chunk = 8192;
-  if ((rc = reserve(e, e->ws_xin, (size_t)std::min(n, chunk) * MAXLEN * XIN_LD * 4))) return rc;
-  float* xin = reinterpret_cast<float*>(e->ws_xin.p);
+  const int nsmax = std::min(n, chunk);
+  if ((rc = reserve(e, e->ws_xin, (size_t)((nsmax + TM - 1) / TM) * MAXLEN * r4tc::G1_XT_COLS * TM * 4))) return rc;
+  float* xinT = reinterpret_cast<float*>(e->ws_xin.p);
   for (int s0 = 0; s0 < n; s0 += chunk) {
     int ns = std::min(chunk, n - s0);
     float* Hc = reinterpret_cast<float*>(c.H.p) + (size_t)s0 * MAXLEN * EMB;
-    float* XKc = reinterpret_cast<float*>(c.XK.p) + (size_t)s0 * MAXLEN * XK_LD;
-    // x_t [Wgx | Wcx] + [bg | bc] with the Embedding gather fused into the A operand
+    // x_t [Wgx | Wcx] + [bg | bc]: Embedding gather fused into the A operand, output in lane-major tiles
     if ((rc = gemm(e, SL_GEMM_XIN, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx_img,
-                   w.gru_bx, xin, XIN_LD, st))) return rc;
-    RecurParams p{};
-    p.s[0].X = xin; p.s[0].Wgh = w.gru_wgh; p.s[0].Wch = w.gru_wch; p.s[0].scores = nullptr;
-    p.s[0].out = Hc; p.s[0].shared = 0;
-    p.R = ns; p.row0 = 0; p.div = 1; p.xld = XIN_LD; p.xoff_g = 0; p.xoff_c = 2 * EMB; p.out_ld = 0;
+                   w.gru_bx, nullptr, XIN_LD, st, ns, 0, XIN_LD, xinT, nullptr))) return rc;
     { ProfScope ps(e, SL_GRU1, st, (double)ns * MAXLEN * 2.0 * (EMB * 2 * EMB + EMB * EMB));
-    k_recur<128, false, true><<<dim3((ns + 63) / 64, 1), 256, SMEM_RECUR_128, st>>>(p); }
-    R4_LAUNCH_CHECK(e, "k_recur<128>");
-    // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]
-    if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx_img, w.au_bx, XKc, XK_LD, st))) return rc;
-    { ProfScope ps(e, SL_XT, st, (double)ns * MAXLEN * r4tc::XT_COLS * 8.0);
-      r4tc::k_transpose_x<<<dim3((ns + 31) / 32, r4tc::XT_COLS / 32, MAXLEN), dim3(32, 8), 0, st>>>(
-          s0, ns, XKc, XK_LD, reinterpret_cast<float*>(c.XT.p)); }
-    R4_LAUNCH_CHECK(e, "k_transpose_x");
+      r4tc::GruTcParams gp{xinT, w.gru_img, Hc, ns};
+      r4tc::k_gru_tc<<<(ns + TM - 1) / TM, r4tc::NTHREADS, r4tc::G1_SMEM_BYTES, st>>>(gp); }
+    R4_LAUNCH_CHECK(e, "k_gru_tc");
+    // H_t [Wgx | Wcx | Wk-Wd] + [bg | bc | 0]: AUGRU halves -> XT tiles, key half -> Kp
+    if ((rc = gemm(e, SL_GEMM_XK, 0, ns * MAXLEN, XK_LD, EMB, Hc, EMB, nullptr, w.au_wx_img, w.au_bx, nullptr, XK_LD, st,
+                   ns, s0, r4tc::XT_COLS, reinterpret_cast<float*>(c.XT.p), reinterpret_cast<float*>(c.Kp.p)))) return rc;
   }
   return R4_OK;
 }
@@ -247,7 +242,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     const PerSeq& w = e->ps[i];
     r4tc::ScoreTcSeq& s = sp.s[i];
     s.H = reinterpret_cast<const float*>(cs[i]->H.p);
-    s.XK = reinterpret_cast<const float*>(cs[i]->XK.p);
+    s.Kp = reinterpret_cast<const float*>(cs[i]->Kp.p);
     s.qa = i ? qa1 : qa0; s.WpImg = w.wp_img; s.Wqd = w.wqd; s.b1 = w.ab1; s.W2 = w.aw2; s.b2 = w.ab2; s.kv = w.akv; s.bk = w.abk;
     s.scoresT = scores + (size_t)i * sc_per_seq;
     s.shared = sh[i];
@@ -421,7 +416,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
             cudaMalloc(&e->amask, (size_t)e->B * e->words * 4) == cudaSuccess &&
             cudaMalloc(&e->sflag, (size_t)e->B) == cudaSuccess;
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
-  cudaFuncSetAttribute(k_recur<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_RECUR_128);
+  cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
@@ -443,7 +438,7 @@ void r4_destroy(r4_env* e) {
   for (void* p : e->owned) cudaFree(p);
   void* own[] = {e->row_idx, e->prev_actions, e->amask, e->sflag, e->item_vec, e->price, e->special, e->action_emb};
   for (void* p : own) if (p) cudaFree(p);
-  DevBuf* bufs[] = {&e->c0.H, &e->c0.XK, &e->c1const.H, &e->c1const.XK, &e->c1page.H, &e->c1page.XK,
+  DevBuf* bufs[] = {&e->c0.H, &e->c0.Kp, &e->c1const.H, &e->c1const.Kp, &e->c1page.H, &e->c1page.Kp,
                     &e->c0.XT, &e->c1const.XT, &e->c1page.XT,
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
                     &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q};
@@ -563,6 +558,11 @@ int r4_finalize_weights(r4_env* e, void* stream) {
     for (int k = 0; k < AUH; ++k) {
       for (int n = 0; n < 2 * AUH; ++n) awgh[(size_t)k * 2 * AUH + n] = uwg[(size_t)(EMB + k) * 2 * AUH + n];
       for (int n = 0; n < AUH; ++n) awch[(size_t)k * AUH + n] = uwc[(size_t)(EMB + k) * AUH + n];
+    }
+    {
+      std::vector<uint8_t> gi(r4tc::G1_IMAGE_BYTES);
+      r4tc::build_gru_image(wgh.data(), wch.data(), gi.data());
+      if ((rc = upload(e, gi, &w.gru_img))) return rc;
     }
     if ((rc = upload_image(e, wx.data(), EMB, XIN_LD, &w.gru_wx_img)) ||
         (rc = upload_image(e, awx.data(), EMB, XK_LD, &w.au_wx_img))) return rc;
@@ -854,7 +854,7 @@ int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int
                       obs ? obs + (size_t)r0 * OBSD : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
   }
   cudaStreamSynchronize(st);
-  DevBuf* tmp[] = {&t0.H, &t0.XK, &t0.XT, &t1.H, &t1.XK, &t1.XT, &ids};
+  DevBuf* tmp[] = {&t0.H, &t0.Kp, &t0.XT, &t1.H, &t1.Kp, &t1.XT, &ids};
   for (DevBuf* b : tmp) if (b->p) cudaFree(b->p);
   return rc;
 }

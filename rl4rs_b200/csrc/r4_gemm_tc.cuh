@@ -66,6 +66,12 @@ struct GemmTcParams {
   const float* A; int lda; const int32_t* gather;
   const uint8_t* Wimg; const float* bias; float* C; int ldc;
   int M, N, K, act;     // act: 0 none, 1 ELU
+  // "sequence" mode (tm_ns > 0): the M = tm_ns * 64 rows are (sequence n, step t) pairs enumerated t-major
+  // (m = t * tm_ns + n; source row n * 64 + t), and the result is written in the lane-major tile layout the
+  // recurrent kernels read: columns < ldT -> outT[((nabs/128) * 64 + t) * ldT + col) * 128 + nabs % 128],
+  // columns >= ldT -> outK[(nabs * 64 + t) * (N - ldT) + col - ldT], nabs = cr_base + n.  Consecutive threads are
+  // consecutive sequences of one step, so both reads and transposed writes stay coalesced.
+  int tm_ns, cr_base, ldT; float* outT; float* outK;
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     for (int it = 0; it < 4; ++it) {
       int m = m0 + it * 32 + (tid >> 2);
       if (m >= p.M) m = p.M - 1;
+      if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
       size_t src = p.gather ? (size_t)p.gather[m] : (size_t)m;
       arow[it] = p.A + src * p.lda + kc * 8;
     }
@@ -218,7 +225,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
       float a[16];
       tmem_ld16(tlane + c, a);
       tmem_wait_ld();
-      if (m < p.M) {
+      if (m < p.M && p.tm_ns > 0) {
+        const int t = m / p.tm_ns, nabs = p.cr_base + m % p.tm_ns;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int col = n0 + c + j;
+          float r = a[j] + (p.bias ? __ldg(p.bias + col) : 0.f);
+          if (p.act == 1) r = r > 0.f ? r : expm1f(r);
+          if (col < p.ldT) p.outT[(((size_t)(nabs / TM) * STEPS + t) * p.ldT + col) * TM + (nabs % TM)] = r;
+          else p.outK[((size_t)nabs * STEPS + t) * (p.N - p.ldT) + (col - p.ldT)] = r;
+        }
+      } else if (m < p.M) {
         float* o = p.C + (size_t)m * p.ldc + n0 + c;
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {

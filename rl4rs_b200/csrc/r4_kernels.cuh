@@ -1,4 +1,6 @@
-// r4_kernels.cuh -- sm_100a kernels of the RL4RS hot path.
+// r4_kernels.cuh -- sm_100a kernels of the RL4RS hot path: the integer / gather half
+// (K1-K5, K10 tail, K11).  The GEMM-shaped half lives in r4_gemm_tc.cuh, r4_gru_tc.cuh, r4_scores_tc.cuh,
+// r4_augru_tc.cuh (tcgen05) and the policy/learner in r4_ppo.cuh.
 //
 // Every kernel cites the reference operation it replaces.  Arithmetic is fp32 with precise
 // expf/tanhf/expm1f (parity: 1e-4 relative against the f32 CPU oracle); reward and kNN scores are
@@ -239,355 +241,6 @@ __global__ void k_seq_ids(int B, int T, int p0, const int32_t* __restrict__ row_
   if (seq0) seq0[i] = v0;
   if (seq1) seq1[i] = v1;
   if (seq_out) { seq_out[(size_t)b * 2 * MAXLEN + t] = v0; seq_out[(size_t)b * 2 * MAXLEN + MAXLEN + t] = v1; }
-}
-
-// ------------------------------------------------------------------------------------------
-// Generic fp32 GEMM  C[M,N] = act(A[M,K] @ W[K,N] + bias)   (Keras Dense: nets/utils.py:50-53,
-// dien.py:35) with optional row gather on A (Embedding lookup fused into the input projection,
-// nets/utils.py:113).  128x128x8 tiles, 8x8 register micro-tiles.  N % 4 == 0, K % 8 == 0.
-// ------------------------------------------------------------------------------------------
-template <int ACT>   // 0 none, 1 ELU
-__global__ void __launch_bounds__(256) k_gemm(int M, int N, int K, const float* __restrict__ A, int lda,
-                                              const int32_t* __restrict__ gather, const float* __restrict__ W,
-                                              const float* __restrict__ bias, float* __restrict__ C, int ldc) {
-  __shared__ __align__(16) float As[8][128];
-  __shared__ __align__(16) float Bs[8][128];
-  int tid = threadIdx.x;
-  int m0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
-  int tx = tid & 15, ty = tid >> 4;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  int arow = tid >> 1, akq = (tid & 1) * 4;
-  int gm = m0 + arow;
-  const float* aptr = nullptr;
-  if (gm < M) {
-    int64_t src = gather ? (int64_t)gather[gm] : (int64_t)gm;
-    aptr = A + src * lda + akq;
-  }
-  int bk = tid >> 5, bn = (tid & 31) * 4;
-  bool bok = (n0 + bn) < N;
-  for (int k0 = 0; k0 < K; k0 += 8) {
-    float4 av = aptr ? ldg4(aptr + k0) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 bv = bok ? ldg4(W + (size_t)(k0 + bk) * N + n0 + bn) : make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
-    As[akq + 0][arow] = av.x; As[akq + 1][arow] = av.y; As[akq + 2][arow] = av.z; As[akq + 3][arow] = av.w;
-    *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      float4 a1 = *reinterpret_cast<const float4*>(&As[k][64 + ty * 4]);
-      float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      float4 b1 = *reinterpret_cast<const float4*>(&Bs[k][64 + tx * 4]);
-      float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (m >= M) continue;
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      int n = n0 + (h ? 64 : 0) + tx * 4;
-      if (n >= N) continue;
-      float4 bb = bias ? ldg4(bias + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 v;
-      v.x = acc[i][h * 4 + 0] + bb.x; v.y = acc[i][h * 4 + 1] + bb.y;
-      v.z = acc[i][h * 4 + 2] + bb.z; v.w = acc[i][h * 4 + 3] + bb.w;
-      if (ACT == 1) { v.x = eluf_(v.x); v.y = eluf_(v.y); v.z = eluf_(v.z); v.w = eluf_(v.w); }
-      *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = v;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K7 / K9 recurrence.  TF1 GRUCell (HID=128, nets/utils.py:120) and deepctr VecAttGRUCell
-// (HID=256, AUGRU, nets/utils.py:123-124), h0 = 0, all 64 steps:
-//   [r,u] = sigmoid(x_t Wgx + h Wgh + bg);  c = tanh(x_t Wcx + (r*h) Wch + bc)
-//   AUGRU: u <- (1 - score_t) * u;          h <- u*h + (1-u)*c
-// The input halves x_t Wgx + bg and x_t Wcx + bc are precomputed (X, row stride xld, per cached
-// sequence); this kernel does the h-dependent halves.  One CTA = M rows x 64 steps; h lives in
-// shared memory transposed (hT[k][row]) so a warp's operand reads are broadcasts; each thread owns
-// an 8-row x 4-column tile of r, u and c, so the gate algebra never leaves registers.
-// grid.y selects the sequence (two independent weight sets).
-// ------------------------------------------------------------------------------------------
-struct RecurSeq {
-  const float* X;        // [n_cached, 64, xld]
-  const float* Wgh;      // [HID, 2*HID]
-  const float* Wch;      // [HID, HID]
-  const float* scores;   // [R, 64] (AUGRU) or null
-  float* out;            // STORE_ALL: [R, 64, HID]; else final state rows with stride out_ld
-  int shared;            // 1: every row uses cached sequence 0
-};
-struct RecurParams {
-  RecurSeq s[2];
-  int R, row0, div, xld, xoff_g, xoff_c, out_ld;
-};
-
-template <int HID, bool AUGRU_, bool STORE_ALL>
-__global__ void __launch_bounds__(256, 2) k_recur(RecurParams p) {
-  constexpr int NCG = HID / 4;          // column groups of 4
-  constexpr int NRG = 256 / NCG;        // row groups of 8
-  constexpr int M = 8 * NRG;            // rows per CTA: 32 (HID=256) / 64 (HID=128)
-  extern __shared__ __align__(16) float smem[];
-  float* hT = smem;                     // [HID][M]
-  float* rhT = smem + HID * M;          // [HID][M]
-  float* sc = rhT + HID * M;            // [M][64] scores (AUGRU)
-  __shared__ int cidx_s[M];             // cached-sequence index of each row
-  const RecurSeq& S = p.s[blockIdx.y];
-  int tid = threadIdx.x;
-  int tx = tid % NCG, ty = tid / NCG;
-  int m0 = blockIdx.x * M;
-  int rows_here = p.R - m0 < M ? p.R - m0 : M;
-  if (tid < M) {
-    int r = m0 + tid;
-    if (r >= p.R) r = p.R - 1;
-    cidx_s[tid] = S.shared ? 0 : (p.row0 + r) / p.div;
-  }
-  const size_t seq_stride = (size_t)MAXLEN * p.xld;
-  for (int i = tid; i < HID * M; i += 256) hT[i] = 0.f;
-  if (AUGRU_) {
-    for (int i = tid; i < M * MAXLEN; i += 256) {
-      int rr = i / MAXLEN;
-      int r = m0 + rr; if (r >= p.R) r = p.R - 1;
-      sc[i] = S.scores[(size_t)r * MAXLEN + (i % MAXLEN)];
-    }
-  }
-  float hreg[8][4];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) hreg[i][c] = 0.f;
-  __syncthreads();
-
-  for (int t = 0; t < MAXLEN; ++t) {
-    float ar[8][4], au[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float* xp = S.X + cidx_s[ty * 8 + i] * seq_stride + (size_t)t * p.xld + p.xoff_g + tx * 4;
-      float4 vr = ldg4(xp), vu = ldg4(xp + HID);
-      ar[i][0] = vr.x; ar[i][1] = vr.y; ar[i][2] = vr.z; ar[i][3] = vr.w;
-      au[i][0] = vu.x; au[i][1] = vu.y; au[i][2] = vu.z; au[i][3] = vu.w;
-    }
-    const float* wg = S.Wgh + tx * 4;
-#pragma unroll 4
-    for (int k = 0; k < HID; ++k) {
-      float4 wr = ldg4(wg + (size_t)k * 2 * HID);
-      float4 wu = ldg4(wg + (size_t)k * 2 * HID + HID);
-      float4 h0 = *reinterpret_cast<const float4*>(&hT[k * M + ty * 8]);
-      float4 h1 = *reinterpret_cast<const float4*>(&hT[k * M + ty * 8 + 4]);
-      float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ar[i][0] = fmaf(hv[i], wr.x, ar[i][0]); ar[i][1] = fmaf(hv[i], wr.y, ar[i][1]);
-        ar[i][2] = fmaf(hv[i], wr.z, ar[i][2]); ar[i][3] = fmaf(hv[i], wr.w, ar[i][3]);
-        au[i][0] = fmaf(hv[i], wu.x, au[i][0]); au[i][1] = fmaf(hv[i], wu.y, au[i][1]);
-        au[i][2] = fmaf(hv[i], wu.z, au[i][2]); au[i][3] = fmaf(hv[i], wu.w, au[i][3]);
-      }
-    }
-    // r * h -> rhT ; keep u
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float4 lo, hi;
-      lo.x = sigmoidf_(ar[0][c]) * hreg[0][c]; lo.y = sigmoidf_(ar[1][c]) * hreg[1][c];
-      lo.z = sigmoidf_(ar[2][c]) * hreg[2][c]; lo.w = sigmoidf_(ar[3][c]) * hreg[3][c];
-      hi.x = sigmoidf_(ar[4][c]) * hreg[4][c]; hi.y = sigmoidf_(ar[5][c]) * hreg[5][c];
-      hi.z = sigmoidf_(ar[6][c]) * hreg[6][c]; hi.w = sigmoidf_(ar[7][c]) * hreg[7][c];
-      *reinterpret_cast<float4*>(&rhT[(tx * 4 + c) * M + ty * 8]) = lo;
-      *reinterpret_cast<float4*>(&rhT[(tx * 4 + c) * M + ty * 8 + 4]) = hi;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) au[i][c] = sigmoidf_(au[i][c]);
-    __syncthreads();
-    // candidate
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 vc = ldg4(S.X + cidx_s[ty * 8 + i] * seq_stride + (size_t)t * p.xld + p.xoff_c + tx * 4);
-      ar[i][0] = vc.x; ar[i][1] = vc.y; ar[i][2] = vc.z; ar[i][3] = vc.w;
-    }
-    const float* wc = S.Wch + tx * 4;
-#pragma unroll 4
-    for (int k = 0; k < HID; ++k) {
-      float4 w = ldg4(wc + (size_t)k * HID);
-      float4 h0 = *reinterpret_cast<const float4*>(&rhT[k * M + ty * 8]);
-      float4 h1 = *reinterpret_cast<const float4*>(&rhT[k * M + ty * 8 + 4]);
-      float hv[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        ar[i][0] = fmaf(hv[i], w.x, ar[i][0]); ar[i][1] = fmaf(hv[i], w.y, ar[i][1]);
-        ar[i][2] = fmaf(hv[i], w.z, ar[i][2]); ar[i][3] = fmaf(hv[i], w.w, ar[i][3]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float scale = 1.f;
-      if (AUGRU_) scale = 1.0f - sc[(ty * 8 + i) * MAXLEN + t];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float u = au[i][c];
-        if (AUGRU_) u = scale * u;
-        float cand = tanhf(ar[i][c]);
-        hreg[i][c] = u * hreg[i][c] + (1.0f - u) * cand;
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      *reinterpret_cast<float4*>(&hT[(tx * 4 + c) * M + ty * 8]) =
-          make_float4(hreg[0][c], hreg[1][c], hreg[2][c], hreg[3][c]);
-      *reinterpret_cast<float4*>(&hT[(tx * 4 + c) * M + ty * 8 + 4]) =
-          make_float4(hreg[4][c], hreg[5][c], hreg[6][c], hreg[7][c]);
-    }
-    if (STORE_ALL) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        int rr = ty * 8 + i;
-        if (rr < rows_here)
-          *reinterpret_cast<float4*>(S.out + ((size_t)(m0 + rr) * MAXLEN + t) * HID + tx * 4) =
-              make_float4(hreg[i][0], hreg[i][1], hreg[i][2], hreg[i][3]);
-      }
-    }
-    __syncthreads();
-  }
-  if (!STORE_ALL) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int rr = ty * 8 + i;
-      if (rr < rows_here)
-        *reinterpret_cast<float4*>(S.out + (size_t)(m0 + rr) * p.out_ld + tx * 4) =
-            make_float4(hreg[i][0], hreg[i][1], hreg[i][2], hreg[i][3]);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// K8 DIN local-activation scores (deepctr AttentionSequencePoolingLayer(att_hidden_units=(64,16),
-// return_score=True), weight_normalization=False; nets/utils.py:114-115,121-122):
-//   q = mean_j E_s[cat[-10:]]                                  (reduce_mean, keepdims)
-//   z1_t = sigmoid([q, k_t, q-k_t, q*k_t] W1 + b1) = sigmoid(q(Wq+Wd) + b1 + k_t(Wk-Wd) + (q*k_t)Wp)
-//   z2_t = sigmoid(z1_t W2 + b2);  score_t = z2_t . kv + b        (raw, unbounded)
-// The key-only term k_t(Wk-Wd) is cached with the sequence (XK[..., 768:832]).
-// One CTA per (row, sequence): a 64x64x128 tile product with A = q*H staged in shared memory.
-// ------------------------------------------------------------------------------------------
-struct ScoreSeq {
-  const float* H;     // [n_cached, 64, 128]  GRU-1 outputs
-  const float* XK;    // [n_cached, 64, 832]
-  const float* Wqd;   // [128, 64]  Wq + Wd
-  const float* Wp;    // [128, 64]
-  const float* b1;    // [64]
-  const float* W2;    // [64, 16]
-  const float* b2;    // [16]
-  const float* kv;    // [16]
-  float bk;
-  float* scores;      // [R, 64]
-  int shared;
-};
-struct ScoreParams {
-  ScoreSeq s[2];
-  int R, row0, div;
-  int transposed;   // 1: scores[(r/128)*64 + t][r%128] (lane-major tiles for the tensor-core AUGRU kernel)
-};
-
-constexpr int SC_ALD = 132;   // padded stride of the A tile
-constexpr int SC_SMEM_FLOATS = 128 * 64 + 64 * SC_ALD + 128 + 64 * 4 + 64 + 64 * 16 + 16 + 16;
-
-__global__ void __launch_bounds__(256) k_scores(ScoreParams p, const int32_t* __restrict__ cat,
-                                                const float* __restrict__ emb_seq) {
-  extern __shared__ __align__(16) float smem[];
-  float* Wp_s = smem;                         // [128][64]
-  float* A_s = Wp_s + 128 * 64;               // [64][132]  (later z1)
-  float* q_s = A_s + 64 * SC_ALD;             // [128]
-  float* qa_part = q_s + 128;                 // [4][64]
-  float* qa_s = qa_part + 256;                // [64]
-  float* W2_s = qa_s + 64;                    // [64][16]
-  float* b2_s = W2_s + 64 * 16;               // [16]
-  float* kv_s = b2_s + 16;                    // [16]
-  const ScoreSeq& S = p.s[blockIdx.y];
-  int r = blockIdx.x, tid = threadIdx.x;
-  size_t ci = S.shared ? 0 : (size_t)((p.row0 + r) / p.div);
-  const int32_t* crow = cat + (size_t)r * NCAT;
-  if (tid < 128) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 10; ++j) s += __ldg(emb_seq + (size_t)crow[NCAT - 10 + j] * EMB + tid);
-    q_s[tid] = s / 10.0f;
-  }
-  for (int i = tid; i < 128 * 64 / 4; i += 256)
-    reinterpret_cast<float4*>(Wp_s)[i] = __ldg(reinterpret_cast<const float4*>(S.Wp) + i);
-  for (int i = tid; i < 64 * 16; i += 256) W2_s[i] = __ldg(S.W2 + i);
-  if (tid < 16) { b2_s[tid] = __ldg(S.b2 + tid); kv_s[tid] = __ldg(S.kv + tid); }
-  __syncthreads();
-  {  // qa = q (Wq + Wd) + b1, split over 4 k-ranges
-    int j = tid & 63, part = tid >> 6;
-    float s = 0.f;
-#pragma unroll 8
-    for (int k = part * 32; k < part * 32 + 32; ++k) s = fmaf(q_s[k], __ldg(S.Wqd + k * 64 + j), s);
-    qa_part[part * 64 + j] = s;
-  }
-  const float* Hrow = S.H + ci * MAXLEN * EMB;
-  for (int i = tid; i < 64 * 32; i += 256) {
-    int t = i >> 5, k4 = (i & 31) * 4;
-    float4 h = ldg4(Hrow + (size_t)t * EMB + k4);
-    float4 q = *reinterpret_cast<const float4*>(&q_s[k4]);
-    *reinterpret_cast<float4*>(&A_s[t * SC_ALD + k4]) = make_float4(h.x * q.x, h.y * q.y, h.z * q.z, h.w * q.w);
-  }
-  __syncthreads();
-  if (tid < 64) qa_s[tid] = qa_part[tid] + qa_part[64 + tid] + qa_part[128 + tid] + qa_part[192 + tid] + __ldg(S.b1 + tid);
-  __syncthreads();
-  int tx = tid & 15, ty = tid >> 4;
-  float z[4][4];
-  {
-    const float* kp = S.XK + ci * MAXLEN * XK_LD + XK_K + tx * 4;
-    float4 qa = *reinterpret_cast<const float4*>(&qa_s[tx * 4]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float4 kk = ldg4(kp + (size_t)(ty * 4 + i) * XK_LD);
-      z[i][0] = qa.x + kk.x; z[i][1] = qa.y + kk.y; z[i][2] = qa.z + kk.z; z[i][3] = qa.w + kk.w;
-    }
-  }
-#pragma unroll 4
-  for (int k = 0; k < 128; ++k) {
-    float4 b = *reinterpret_cast<const float4*>(&Wp_s[k * 64 + tx * 4]);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a = A_s[(ty * 4 + i) * SC_ALD + k];
-      z[i][0] = fmaf(a, b.x, z[i][0]); z[i][1] = fmaf(a, b.y, z[i][1]);
-      z[i][2] = fmaf(a, b.z, z[i][2]); z[i][3] = fmaf(a, b.w, z[i][3]);
-    }
-  }
-  __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    *reinterpret_cast<float4*>(&A_s[(ty * 4 + i) * SC_ALD + tx * 4]) =
-        make_float4(sigmoidf_(z[i][0]), sigmoidf_(z[i][1]), sigmoidf_(z[i][2]), sigmoidf_(z[i][3]));
-  __syncthreads();
-  {
-    int t = tid >> 2, jq = tid & 3;
-    float o[4] = {b2_s[jq * 4], b2_s[jq * 4 + 1], b2_s[jq * 4 + 2], b2_s[jq * 4 + 3]};
-#pragma unroll 8
-    for (int j = 0; j < 64; ++j) {
-      float a = A_s[t * SC_ALD + j];
-      float4 w = *reinterpret_cast<const float4*>(&W2_s[j * 16 + jq * 4]);
-      o[0] = fmaf(a, w.x, o[0]); o[1] = fmaf(a, w.y, o[1]); o[2] = fmaf(a, w.z, o[2]); o[3] = fmaf(a, w.w, o[3]);
-    }
-    float s = sigmoidf_(o[0]) * kv_s[jq * 4] + sigmoidf_(o[1]) * kv_s[jq * 4 + 1] +
-              sigmoidf_(o[2]) * kv_s[jq * 4 + 2] + sigmoidf_(o[3]) * kv_s[jq * 4 + 3];
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    if (jq == 0) {
-      size_t o = p.transposed ? ((size_t)(r >> 7) * MAXLEN + t) * 128 + (r & 127) : (size_t)r * MAXLEN + t;
-      S.scores[o] = s + S.bk;
-    }
-  }
 }
 
 // ------------------------------------------------------------------------------------------

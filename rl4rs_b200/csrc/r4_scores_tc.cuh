@@ -24,7 +24,7 @@ constexpr int S_B_BYTES = 3 * S_B_SPLIT;           // 48 KB, resident
 constexpr int S_SBO = (S_K / 8) * 128;             // 2048: 8-row groups (A and B)
 constexpr int S_SMEM_BYTES = 2 * S_A_STAGE + S_B_BYTES + 1024;
 constexpr int S_THREADS = 320;                     // 4 producer + 4 epilogue + MMA + loader warps
-constexpr int S_XK_LD = 832, S_XK_K = 768;         // cached key half lives in XK[..., 768:832]
+constexpr int S_KP_LD = 64;                        // cached key half k_t (Wk - Wd): Kp [n_cached, 64 keys, 64]
 
 // host: Wp [128 k][64 n] fp32 -> 3 splits of [64 n x 128 k] K-major core matrices
 inline void build_scores_image(const float* Wp, uint8_t* img) {
@@ -44,7 +44,7 @@ inline void build_scores_image(const float* Wp, uint8_t* img) {
 struct ScoreTcSeq {
   const float* qa;       // [R, 64]  q (Wq+Wd) + b1, from k_query
   const float* H;        // [n_cached, 64, 128]
-  const float* XK;       // [n_cached, 64, 832]
+  const float* Kp;       // [n_cached, 64, 64]   k_t (Wk - Wd)
   const uint8_t* WpImg;  // S_B_BYTES
   const float* Wqd;      // [128, 64]
   const float* b1;       // [64]
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&bar_tempty[s]);               // accumulators are free again
-      const float* kp = S.XK + (ci * S_KEYS + key) * S_XK_LD + S_XK_K;
+      const float* kp = S.Kp + (ci * S_KEYS + key) * S_KP_LD;
       const float* qap = S.qa + (size_t)rc * S_N;
       float o[16];
 #pragma unroll
