@@ -7,15 +7,17 @@
 A "step" is ONE EPISODE of the batched env: reset (row sampling, user-history GRU-1 + input
 projections) followed by max_steps x env.step (act, feature assembly, DIEN forward, reward/done),
 over `batch_per_gpu` env rows per GPU = batch x max_steps transitions.  N = 1 runs BASELINE
-configs[1]: SlateRecEnv-v0, batch 4096, discrete actions sampled by the PPO mask policy, synthetic
+configs[1]: SlateRecEnv-v0, batch 4096, PPO discrete (mask policy rollout + SGD pass), synthetic
 283-item catalog, synthetic log/weights of the dataset's shape (no dataset/checkpoint offline).
 
 JSON keys beyond the base contract:
-  value     device-resident loop (policy + env on the GPU, nothing crosses PCIe in the timed region
-            except 16 KB of row indices per reset).
+  value     one PPO iteration, device-resident: masked SoftQ rollout of a vector episode (policy + env on the GPU)
+            followed by the minibatch-256 SGD pass, all hand-written kernels; nothing crosses PCIe in the timed
+            region except 16 KB of row indices per reset and the 144 KB minibatch permutation.
+  env_only  the same rollout without the SGD pass.
   e2e       the reference-facing call with HOST buffers: README.md:14-21 loop, numpy actions in,
             numpy obs/mask/reward out, every copy inside the timed region.
-  roofline  the dominant kernel (k_recur<256>, AUGRU recurrence) timed live with CUDA events on the
+  roofline  the dominant kernel (k_augru_tc, the tcgen05 AUGRU recurrence) timed live with CUDA events on the
             launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
             2*(256*512 + 256*256) against the measured bf16 GEMM peak.
   cpu_baseline  the oracle port (oracle/env_np.py + dien_np.py) on this box's host cores, bounded sample.

@@ -9,7 +9,7 @@ ONE call into the CUDA library (rl4rs_b200/engine.py) whose results the three me
 
 ``config['output_format']`` (an addition; unknown keys are ignored by the reference):
   'list'  (default) reference-compatible Python lists / list of dicts;
-  'numpy' batched host arrays (obs dict of arrays), no per-row Python objects;
+  'numpy' batched host arrays (obs dict of arrays; action_mask stays uint8), no per-row Python objects;
   'torch' device tensors, no host synchronisation at all.
 """
 from abc import ABC, abstractmethod

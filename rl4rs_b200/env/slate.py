@@ -108,7 +108,7 @@ class SlateState(RecState):
         res = emb if self.engine.conti else items
         if fmt == "torch":
             return res
-        res = res.cpu().numpy()
+        res = self.engine.to_host(offline_action=res)["offline_action"]
         if fmt == "numpy":
             return res
         return [x for x in res] if self.engine.conti else res.tolist()
@@ -119,7 +119,7 @@ class SlateState(RecState):
         fmt = self.engine.config.get("output_format", "list")
         if fmt == "torch":
             return r
-        r = r.cpu().numpy()
+        r = self.engine.to_host(offline_reward=r)["offline_reward"]
         return r if fmt == "numpy" else r.tolist()
 
     def act(self, actions):
@@ -176,11 +176,13 @@ class SlateRecEnv(RecSimBase):
                 cs = torch.full((eng.B, 1), eng.cur_steps, dtype=torch.float64, device=eng.device)
                 return torch.cat([out["obs"].double(), eng.masked.double(), cs], dim=-1)
             return {k: v.clone() for k, v in out.items()} if (rllib or "obs" not in out) else out["obs"].clone()
-        host = {k: v.cpu().numpy() for k, v in out.items()}
-        if "action_mask" in host:
-            host["action_mask"] = host["action_mask"].astype(np.int64)
+        if d3rl and "obs" in out:
+            out["_masked"] = eng.masked
+        host = eng.to_host(**out)
+        if "action_mask" in host and fmt == "list":
+            host["action_mask"] = host["action_mask"].astype(np.int64)   # reference dtype (np.int, slate.py:17)
         if d3rl and "obs" in host:
-            ma = eng.masked.cpu().numpy()
+            ma = host.pop("_masked")
             cs = np.full((eng.B, 1), eng.cur_steps)
             return np.concatenate([host["obs"], ma, cs], axis=-1)
         if not rllib and "obs" in host:
@@ -197,7 +199,7 @@ class SlateRecEnv(RecSimBase):
         eng = self.engine
         fmt = self.output_format
         if eng.info_fetch and eng.paid:
-            cp = eng.click_p.cpu().numpy()
+            cp = eng.to_host(click_p=eng.click_p)["click_p"]
             if isinstance(samples.infos, list):
                 for i in range(eng.B):
                     samples.infos[i].update({"click_p": cp[i]})
@@ -205,5 +207,5 @@ class SlateRecEnv(RecSimBase):
                 samples.infos["click_p"] = cp
         if fmt == "torch":
             return eng.reward.clone()
-        r = eng.reward.cpu().numpy()
+        r = eng.to_host(reward=eng.reward)["reward"]
         return r.tolist() if fmt == "list" else r
