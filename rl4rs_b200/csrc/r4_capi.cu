@@ -797,19 +797,26 @@ int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_
     return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: bad argument");
   r4ppo::Layout L = r4ppo::make_layout(action_size);
   r4ppo::LossHyper hp{mode, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv_n};
-  size_t smem = (size_t)(((L.n + 3) & ~3) + r4ppo::TS * r4ppo::OBS + 2 * r4ppo::TS * r4ppo::HID +
-                         r4ppo::TS * action_size + 2 * r4ppo::TS) * 4;
-  if (smem > 226 * 1024) return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: action_size too large for the shared-memory accumulator");
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t st_ = cudaFuncSetAttribute(r4ppo::k_policy_grad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool single = ((n + r4ppo::TS - 1) / r4ppo::TS) == G;      // one tile per CTA (PPO minibatch)
+  const size_t head = single ? (size_t)(r4ppo::OBS * r4ppo::HID + ((r4ppo::HID * action_size + 3) & ~3)) : (size_t)((L.n + 3) & ~3);
+  size_t smem = (head + r4ppo::TS * r4ppo::OBS + 2 * r4ppo::TS * r4ppo::HID + r4ppo::TS * action_size + 2 * r4ppo::TS) * 4;
+  if (smem > 226 * 1024) return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: action_size too large for the shared-memory layout");
+  static size_t attr[2] = {0, 0};
+  if (smem > attr[single]) {
+    cudaError_t st_ = single
+        ? cudaFuncSetAttribute(r4ppo::k_policy_grad<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+        : cudaFuncSetAttribute(r4ppo::k_policy_grad<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (st_ != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute(k_policy_grad): ") + cudaGetErrorString(st_));
-    attr = smem;
+    attr[single] = smem;
   }
   float* partial = scratch;
   float* stat_partial = scratch + (size_t)G * L.n;
-  r4ppo::k_policy_grad<<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
-                                                         old_value, adv, target, idx, n, partial, stat_partial);
+  if (single)
+    r4ppo::k_policy_grad<true><<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
+                                                                 old_value, adv, target, idx, n, partial, stat_partial);
+  else
+    r4ppo::k_policy_grad<false><<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
+                                                                  old_value, adv, target, idx, n, partial, stat_partial);
   R4_PCHECK("k_policy_grad");
   r4ppo::k_grad_reduce<<<(L.n + 255) / 256, 256, 0, S(stream)>>>(L.n, G, partial, flat_grad, stat_partial, stats_accum, stat_scale);
   R4_PCHECK("k_grad_reduce");

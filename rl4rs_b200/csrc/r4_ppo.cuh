@@ -45,9 +45,13 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 
 // Forward of one tile of TS samples (rows given by src index): fills h_s[TS][HID], lg_s[TS][A]
 // (masked logits), val_s[TS].  obs_s[TS][OBS] is loaded here.  All 256 threads participate.
-__device__ inline void forward_tile(const Layout& L, const float* __restrict__ prm, const float* __restrict__ obs,
-                                    const uint8_t* __restrict__ mask, const int64_t* src, int nvalid,
-                                    float* obs_s, float* h_s, float* lg_s, float* val_s) {
+template <bool WS>   // WS: w1p / w2p point to shared-memory copies of the two weight matrices
+__device__ __forceinline__ float ldw(const float* p) { return WS ? *p : __ldg(p); }
+
+template <bool WS>
+__device__ inline void forward_tile(const Layout& L, const float* __restrict__ prm, const float* w1p, const float* w2p,
+                                    const float* __restrict__ obs, const uint8_t* __restrict__ mask, const int64_t* src,
+                                    int nvalid, float* obs_s, float* h_s, float* lg_s, float* val_s) {
   const int tid = threadIdx.x;
   for (int i = tid; i < TS * OBS / 4; i += NT) {
     int s = i / (OBS / 4), k4 = i % (OBS / 4);
@@ -59,10 +63,10 @@ __device__ inline void forward_tile(const Layout& L, const float* __restrict__ p
   {  // h = tanh(obs W1 + b1): thread (j = tid%64, g = tid/64) -> samples 4g..4g+3
     const int j = tid & 63, g = tid >> 6;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* w = prm + L.o_w1 + j;
+    const float* w = w1p + j;
 #pragma unroll 8
     for (int k = 0; k < OBS; ++k) {
-      float wk = __ldg(w + k * HID);
+      float wk = ldw<WS>(w + k * HID);
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[i] = fmaf(obs_s[(4 * g + i) * OBS + k], wk, acc[i]);
     }
@@ -75,9 +79,10 @@ __device__ inline void forward_tile(const Layout& L, const float* __restrict__ p
     float acc[TS];
 #pragma unroll
     for (int s = 0; s < TS; ++s) acc[s] = 0.f;
-    const float* w = prm + L.o_w2 + col;
+    const float* w = w2p + col;
+#pragma unroll 4
     for (int k = 0; k < HID; ++k) {
-      float wk = __ldg(w + (size_t)k * L.A);
+      float wk = ldw<WS>(w + (size_t)k * L.A);
 #pragma unroll
       for (int s = 0; s < TS; ++s) acc[s] = fmaf(h_s[s * HID + k], wk, acc[s]);
     }
@@ -111,7 +116,7 @@ __global__ void __launch_bounds__(NT) k_policy_act(Layout L, const float* __rest
   const int nvalid = min(TS, B - s0);
   if (tid < TS) src[tid] = min(s0 + tid, B - 1);
   __syncthreads();
-  forward_tile(L, prm, obs, mask, src, nvalid, obs_s, h_s, lg_s, val_s);
+  forward_tile<false>(L, prm, prm + L.o_w1, prm + L.o_w2, obs, mask, src, nvalid, obs_s, h_s, lg_s, val_s);
   for (int s = warp; s < nvalid; s += NT / 32) {
     const float* lg = lg_s + s * L.A;
     float m = -INFINITY;
@@ -172,6 +177,10 @@ struct LossHyper {
   float clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv_n;
 };
 
+// SINGLE = true: the grid has exactly one tile per CTA (a PPO minibatch): no shared-memory gradient accumulator;
+// instead both weight matrices are staged in shared memory once (136 KB) so every inner loop reads shared memory, and
+// each gradient element is stored straight to this CTA's partial row by its owner thread.
+template <bool SINGLE>
 __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, const float* __restrict__ prm,
                                                     const float* __restrict__ obs, const uint8_t* __restrict__ mask,
                                                     const int64_t* __restrict__ action, const float* __restrict__ old_logp,
@@ -180,8 +189,9 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
                                                     const int64_t* __restrict__ idx, int n, float* __restrict__ partial,
                                                     float* __restrict__ stat_partial /*[grid,5]*/) {
   extern __shared__ __align__(16) float sm[];
-  float* g_s = sm;                              // [L.n] gradient accumulator of this CTA
-  float* obs_s = g_s + ((L.n + 3) & ~3);
+  float* g_s = sm;                              // !SINGLE: [L.n] gradient accumulator; SINGLE: w1 | w2 copies
+  const int head = SINGLE ? (OBS * HID + ((HID * L.A + 3) & ~3)) : ((L.n + 3) & ~3);
+  float* obs_s = g_s + head;
   float* h_s = obs_s + TS * OBS;
   float* lg_s = h_s + TS * HID;                 // logits -> logp_all -> dlogits
   float* val_s = lg_s + TS * L.A;
@@ -190,7 +200,17 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
   __shared__ int64_t src[TS];
   __shared__ float stat_s[5];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < L.n; i += NT) g_s[i] = 0.f;
+  float* gout = partial + (size_t)blockIdx.x * L.n;
+  const float* w1p = prm + L.o_w1;
+  const float* w2p = prm + L.o_w2;
+  if (SINGLE) {
+    for (int i = tid; i < OBS * HID / 4; i += NT) reinterpret_cast<float4*>(g_s)[i] = __ldg(reinterpret_cast<const float4*>(prm + L.o_w1) + i);
+    float* w2s = g_s + OBS * HID;
+    for (int i = tid; i < HID * L.A; i += NT) w2s[i] = __ldg(prm + L.o_w2 + i);
+    w1p = g_s; w2p = w2s;
+  } else {
+    for (int i = tid; i < L.n; i += NT) g_s[i] = 0.f;
+  }
   if (tid < 5) stat_s[tid] = 0.f;
   const int ntiles = (n + TS - 1) / TS;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -199,7 +219,7 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
     __syncthreads();
     if (tid < TS) { int i = min(s0 + tid, n - 1); src[tid] = idx ? idx[i] : (int64_t)i; }
     __syncthreads();
-    forward_tile(L, prm, obs, mask, src, nvalid, obs_s, h_s, lg_s, val_s);
+    forward_tile<SINGLE>(L, prm, w1p, w2p, obs, mask, src, nvalid, obs_s, h_s, lg_s, val_s);
     // ---- per-sample loss derivatives: one warp per sample ----
     for (int s = warp; s < TS; s += NT / 32) {
       float* lg = lg_s + s * L.A;
@@ -272,12 +292,12 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
       float sb = 0.f;
 #pragma unroll
       for (int s = 0; s < TS; ++s) { d[s] = lg_s[s * L.A + col]; sb += d[s]; }
-      g_s[L.o_b2 + col] += sb;
+      if (SINGLE) gout[L.o_b2 + col] = sb; else g_s[L.o_b2 + col] += sb;
       for (int k = 0; k < HID; ++k) {
         float acc = 0.f;
 #pragma unroll
         for (int s = 0; s < TS; ++s) acc = fmaf(h_s[s * HID + k], d[s], acc);
-        g_s[L.o_w2 + k * L.A + col] += acc;
+        if (SINGLE) gout[L.o_w2 + k * L.A + col] = acc; else g_s[L.o_w2 + k * L.A + col] += acc;
       }
     }
     // dh[s][k] = sum_col dlog[s][col] W2[k][col] + dv[s] wv[k];  dpre = dh (1 - h^2): warp per (s, k-range)
@@ -289,7 +309,7 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
       for (int c = lane; c < L.A; c += 32) {
         float dz = lg_s[s * L.A + c];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(dz, __ldg(prm + L.o_w2 + (size_t)(k0 + i) * L.A + c), acc[i]);
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(dz, ldw<SINGLE>(w2p + (size_t)(k0 + i) * L.A + c), acc[i]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
@@ -312,25 +332,24 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
         float acc = 0.f;
 #pragma unroll
         for (int s = 0; s < TS; ++s) acc = fmaf(obs_s[s * OBS + i], dp[s], acc);
-        g_s[L.o_w1 + i * HID + k] += acc;
+        if (SINGLE) gout[L.o_w1 + i * HID + k] = acc; else g_s[L.o_w1 + i * HID + k] += acc;
       }
       if (ig == 0) {
         float sb = 0.f, sw = 0.f;
 #pragma unroll
         for (int s = 0; s < TS; ++s) { sb += dp[s]; sw = fmaf(h_s[s * HID + k], dv_s[s], sw); }
-        g_s[L.o_b1 + k] += sb;
-        g_s[L.o_wv + k] += sw;
+        if (SINGLE) { gout[L.o_b1 + k] = sb; gout[L.o_wv + k] = sw; } else { g_s[L.o_b1 + k] += sb; g_s[L.o_wv + k] += sw; }
       }
       if (tid == 0) {
         float sv = 0.f;
 #pragma unroll
         for (int s = 0; s < TS; ++s) sv += dv_s[s];
-        g_s[L.o_bv] += sv;
+        if (SINGLE) gout[L.o_bv] = sv; else g_s[L.o_bv] += sv;
       }
     }
   }
   __syncthreads();
-  for (int i = tid; i < L.n; i += NT) partial[(size_t)blockIdx.x * L.n + i] = g_s[i];
+  if (!SINGLE) for (int i = tid; i < L.n; i += NT) gout[i] = g_s[i];
   if (tid < 5) stat_partial[blockIdx.x * 5 + tid] = stat_s[tid];
 }
 

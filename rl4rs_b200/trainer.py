@@ -61,9 +61,9 @@ class KernelOps(object):
         self._check(rc, "r4_policy_act")
         self.counter += n
 
-    def policy_grad(self, mode, flat, data, idx, idx_offset, n, hp, inv_n, stat_scale):
+    def policy_grad(self, mode, flat, data, idx, idx_offset, n, hp, inv_n, stat_scale, G=None):
         obs, mask, act, logp, logits, val, adv, target = data
-        G = max(1, min((n + 15) // 16, 148))
+        G = G or max(1, min((n + 15) // 16, 148))
         rc = self.lib.r4_policy_grad(mode, _p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv),
                                      _p(target), _p(idx, idx_offset * 8) if idx is not None else C.c_void_p(0), n, self.A,
                                      hp["clip"], hp["vf_clip"], hp["vf_coeff"], hp["kl_coeff"], hp["ent_coeff"], inv_n,

@@ -255,3 +255,21 @@ def test_full_batch_properties():
         o, srew, _, _ = small.step(small.offline_action)
         np.testing.assert_array_equal(o["obs"], runs[0][0][t + 1][:64])
     np.testing.assert_array_equal(np.asarray(srew), rew[:64])
+
+
+def test_row_chunking_is_invisible():
+    """max_rows_per_pass bounds the simulator rows per launch group (obs and reward passes are chunked);
+    results must not depend on it.  B=48 with 40-row chunks: ragged obs chunks (40 + 8) and 4-env reward chunks."""
+    B = 48
+    cfg, cat, log, w = _synthetic(B, False, support_rllib_mask=True, simulator_info_fetch=True)
+    runs = []
+    for mr in (0, 40):
+        env = make_env(dict(cfg, max_rows_per_pass=mr), False, cat, log, w, output_format="numpy")
+        o = env.reset(reset_file=True)
+        tr = [o["obs"].copy()]
+        for t in range(9):
+            o, rew, _, info = env.step(env.offline_action)
+            tr.append(o["obs"].copy())
+        runs.append((np.stack(tr), np.asarray(rew), info["click_p"].copy()))
+    for a, b in zip(runs[0], runs[1]):
+        np.testing.assert_array_equal(a, b)

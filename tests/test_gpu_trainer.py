@@ -112,6 +112,11 @@ def test_policy_kernels_match_torch_autograd():
         sel = tuple(x[idx].contiguous() for x in (obs, mask, act, old_logp, old_logits, old_v, adv, tgt))
         ops.policy_grad(mode, pol.flat, sel, None, 0, 128, hp, 1.0 / 128 if mode == 0 else 1.0, 1.0)
         assert torch.equal(g_idx, ops.grad)                                   # deterministic reduction
+        # multi-tile path (several tiles per CTA, shared-memory accumulator) against the one-tile-per-CTA path
+        ops.policy_grad(mode, pol.flat, (obs, mask, act, old_logp, old_logits, old_v, adv, tgt), None, 0, n, hp, inv_n, scale)
+        g_single = ops.grad.clone()
+        ops.policy_grad(mode, pol.flat, (obs, mask, act, old_logp, old_logits, old_v, adv, tgt), None, 0, n, hp, inv_n, scale, G=5)
+        assert float((ops.grad - g_single).abs().max() / g_single.abs().max()) < 1e-5
     # ---- Adam: three steps against torch.optim.Adam, with and without clipping
     for clip in (0.0, 0.5):
         p_t = pol.flat.detach().clone().requires_grad_(True)
