@@ -129,7 +129,6 @@ class Engine(object):
         self.act_f64 = z((B, self.emb_dim), torch.float64) if self.conti else None
         self.pin_act_i32 = torch.zeros((B,), dtype=torch.int32).pin_memory()
         self.pin_rows = torch.zeros((B,), dtype=torch.int32).pin_memory()
-        self._pins = {}
         self.paid = False       # did the last step compute a reward (click_p valid)?
 
     # ---- episode -----------------------------------------------------------------------------
@@ -238,18 +237,16 @@ class Engine(object):
         return obs, probs
 
     def to_host(self, **tensors):
-        """Device tensors -> fresh NumPy arrays through pinned staging buffers: all copies are enqueued
-        asynchronously on the current stream, ONE synchronisation, then a host memcpy out of the staging area."""
+        """Device tensors -> NumPy arrays.  Each result lives in a FRESH pinned host block (torch's caching host
+        allocator makes that cheap), so the D2H copy lands directly in the array handed to the caller: all copies are
+        enqueued asynchronously on the current stream, then ONE synchronisation, no second host memcpy."""
         outs = {}
         for name, t in tensors.items():
-            pin = self._pins.get(name)
-            if pin is None or pin.shape != t.shape or pin.dtype != t.dtype:
-                pin = torch.empty(t.shape, dtype=t.dtype).pin_memory()
-                self._pins[name] = pin
+            pin = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             pin.copy_(t, non_blocking=True)
             outs[name] = pin
         torch.cuda.current_stream(self.device).synchronize()
-        return {k: v.numpy().copy() for k, v in outs.items()}
+        return {k: v.numpy() for k, v in outs.items()}
 
     def launch_count(self):
         return int(self.lib.r4_launch_count(self.h))
