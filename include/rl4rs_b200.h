@@ -157,7 +157,7 @@ int r4_policy_act(const float* params, const float* obs, const uint8_t* mask, in
                   void* stream);
 /* gradient of the RLlib loss over samples idx[0..n) (NULL = 0..n-1) of a rollout:
  * mode 0 PPO surrogate (mean; modelfree_train.py:179-217), mode 1 A2C (sums; :248-304).
- * scratch: f32[G * (num_params + 5)], G = min(ceil(n/16), 148) CTAs; flat_grad f32[num_params] receives the
+ * scratch: f32[G * (num_params + 5)], G = min(ceil(n/4), 148) CTAs; flat_grad f32[num_params] receives the
  * deterministic sum; stats_accum f32[5] += {policy_loss, vf_loss, kl, entropy, total} * stat_scale. */
 int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
                    const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
@@ -168,6 +168,17 @@ int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_
  * grad_scale multiplies the gradient first (1/world after a SUM all-reduce). step is 1-based. */
 int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
                  float beta2, float eps, float grad_scale, float clip, float* norm_scratch, void* stream);
+
+/* One PPO SGD epoch on a single GPU (num_sgd_iter = 1 of modelfree_train.py:179-217): for every full minibatch
+ * perm[s .. s+mb) of the rollout, r4_policy_grad (mode 0, mean over mb) followed by r4_adam_step, with no host round
+ * trip between the steps.  step0 = Adam steps already taken; returns the number of steps done (>= 0) or a negative
+ * r4_status.  Multi-GPU learners call r4_policy_grad / all-reduce / r4_adam_step per step instead. */
+int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int64_t* action, const float* old_logp,
+                 const float* old_logits, const float* old_value, const float* adv, const float* target,
+                 const int64_t* perm, int n, int mb, int action_size, float clip, float vf_clip, float vf_coeff,
+                 float kl_coeff, float ent_coeff, float* scratch, float* flat_grad, float* stats_accum, float* m,
+                 float* v, int step0, float lr, float beta1, float beta2, float eps, float grad_clip,
+                 float* norm_scratch, void* stream);
 
 /* ---- the simulator alone (nets/dien.py:8-45), for parity tests and kernel benchmarks ------- */
 /* seq i32[R,2,64], dense f32[R,432], cat i32[R,21] (device) -> obs f32[R,256], probs f32[R,2]

@@ -838,6 +838,27 @@ int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, in
   return R4_OK;
 }
 
+int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int64_t* action, const float* old_logp,
+                 const float* old_logits, const float* old_value, const float* adv, const float* target,
+                 const int64_t* perm, int n, int mb, int action_size, float clip, float vf_clip, float vf_coeff,
+                 float kl_coeff, float ent_coeff, float* scratch, float* flat_grad, float* stats_accum, float* m,
+                 float* v, int step0, float lr, float beta1, float beta2, float eps, float grad_clip,
+                 float* norm_scratch, void* stream) {
+  if (!perm || n < 1 || mb < 1 || mb > n || step0 < 0) return fail(nullptr, R4_ERR_ARG, "r4_ppo_epoch: bad argument");
+  const int G = std::max(1, std::min((mb + r4ppo::TS - 1) / r4ppo::TS, 148));
+  const int np = r4ppo::make_layout(action_size).n;
+  int steps = 0;
+  for (int s = 0; s + mb <= n; s += mb, ++steps) {
+    int rc = r4_policy_grad(0, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, perm + s, mb,
+                            action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, 1.0f / mb, scratch, G, flat_grad,
+                            stats_accum, 1.0f / mb, stream);
+    if (rc) return rc;
+    rc = r4_adam_step(params, flat_grad, m, v, np, step0 + steps + 1, lr, beta1, beta2, eps, 1.0f, grad_clip, norm_scratch, stream);
+    if (rc) return rc;
+  }
+  return steps;
+}
+
 int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int32_t* cat, int n_rows,
                     float* obs, float* probs, void* stream) {
   if (!e || !seq || !dense || !cat || n_rows < 1) return fail(e, R4_ERR_ARG, "r4_dien_forward: bad argument");

@@ -16,7 +16,9 @@
 
 namespace r4ppo {
 
-constexpr int OBS = 256, HID = 64, TS = 16;      // TS = samples per CTA tile
+constexpr int OBS = 256, HID = 64, TS = 4;       // TS = samples per CTA tile (small: the kernels are latency-bound,
+                                                 // so a 256-sample minibatch should spread over 64 SMs, not 16)
+constexpr int SPG = TS / 4;                      // samples per thread group in the first layer
 constexpr int NT = 256;
 constexpr float FLOAT_MIN = -3.402823466e+38f;
 
@@ -60,19 +62,21 @@ __device__ inline void forward_tile(const Layout& L, const float* __restrict__ p
     reinterpret_cast<float4*>(obs_s)[i] = v;
   }
   __syncthreads();
-  {  // h = tanh(obs W1 + b1): thread (j = tid%64, g = tid/64) -> samples 4g..4g+3
+  {  // h = tanh(obs W1 + b1): thread (j = tid%64, g = tid/64) -> samples SPG*g .. SPG*g+SPG-1
     const int j = tid & 63, g = tid >> 6;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[SPG];
+#pragma unroll
+    for (int i = 0; i < SPG; ++i) acc[i] = 0.f;
     const float* w = w1p + j;
 #pragma unroll 8
     for (int k = 0; k < OBS; ++k) {
       float wk = ldw<WS>(w + k * HID);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) acc[i] = fmaf(obs_s[(4 * g + i) * OBS + k], wk, acc[i]);
+      for (int i = 0; i < SPG; ++i) acc[i] = fmaf(obs_s[(SPG * g + i) * OBS + k], wk, acc[i]);
     }
     float b = __ldg(prm + L.o_b1 + j);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h_s[(4 * g + i) * HID + j] = tanhf(acc[i] + b);
+    for (int i = 0; i < SPG; ++i) h_s[(SPG * g + i) * HID + j] = tanhf(acc[i] + b);
   }
   __syncthreads();
   for (int col = tid; col < L.A; col += NT) {  // logits = h W2 + b2 + clamp(log(mask))

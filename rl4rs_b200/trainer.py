@@ -63,12 +63,24 @@ class KernelOps(object):
 
     def policy_grad(self, mode, flat, data, idx, idx_offset, n, hp, inv_n, stat_scale, G=None):
         obs, mask, act, logp, logits, val, adv, target = data
-        G = G or max(1, min((n + 15) // 16, 148))
+        G = G or max(1, min((n + 3) // 4, 148))          # 4 samples per CTA tile (r4_ppo.cuh: TS)
         rc = self.lib.r4_policy_grad(mode, _p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv),
                                      _p(target), _p(idx, idx_offset * 8) if idx is not None else C.c_void_p(0), n, self.A,
                                      hp["clip"], hp["vf_clip"], hp["vf_coeff"], hp["kl_coeff"], hp["ent_coeff"], inv_n,
                                      _p(self.scratch), G, _p(self.grad), _p(self.stats), stat_scale, self._stream())
         self._check(rc, "r4_policy_grad")
+
+    def ppo_epoch(self, flat, data, perm, n, mb, hp, lr, clip):
+        """All minibatch steps of one SGD epoch in ONE library call (single-GPU learner)."""
+        obs, mask, act, logp, logits, val, adv, target = data
+        rc = self.lib.r4_ppo_epoch(_p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv), _p(target),
+                                   _p(perm), n, mb, self.A, hp["clip"], hp["vf_clip"], hp["vf_coeff"], hp["kl_coeff"],
+                                   hp["ent_coeff"], _p(self.scratch), _p(self.grad), _p(self.stats), _p(self.m), _p(self.v),
+                                   self.step, lr, 0.9, 0.999, 1e-8, float(clip or 0.0), _p(self.norm), self._stream())
+        if rc < 0:
+            self._check(rc, "r4_ppo_epoch")
+        self.step += rc
+        return rc
 
     def adam(self, flat, lr, grad_scale, clip):
         self.step += 1
@@ -327,6 +339,9 @@ class PPOTrainer(_TrainerBase):
         w = _world()
         for _ in range(c["num_sgd_iter"]):
             perm = self._perm(n, data[0].device).contiguous()
+            if w == 1:
+                steps += ops.ppo_epoch(self.policy.flat, data, perm, n, mb, hp, c["lr"], c["grad_clip"])
+                continue
             for s in range(0, n - mb + 1, mb):
                 ops.policy_grad(0, self.policy.flat, data, perm, s, mb, hp, 1.0 / mb, 1.0 / mb)
                 if w > 1:

@@ -117,6 +117,17 @@ def test_policy_kernels_match_torch_autograd():
         g_single = ops.grad.clone()
         ops.policy_grad(mode, pol.flat, (obs, mask, act, old_logp, old_logits, old_v, adv, tgt), None, 0, n, hp, inv_n, scale, G=5)
         assert float((ops.grad - g_single).abs().max() / g_single.abs().max()) < 1e-5
+    # ---- r4_ppo_epoch (all minibatch steps in one call) == the per-step loop, bit for bit
+    hp = {"clip": 0.3, "vf_clip": 500.0, "vf_coeff": 0.5, "kl_coeff": 0.2, "ent_coeff": 0.0}
+    data = (obs, mask, act, old_logp, old_logits, old_v, adv, tgt)
+    perm = torch.randperm(n, generator=g).to(dev)
+    pa, pb = pol.flat.detach().clone(), pol.flat.detach().clone()
+    oa, ob = KernelOps(A, dev, pol.n_params), KernelOps(A, dev, pol.n_params)
+    assert oa.ppo_epoch(pa, data, perm, n, 64, hp, 1e-3, None) == n // 64 and oa.step == n // 64
+    for s in range(0, n - 64 + 1, 64):
+        ob.policy_grad(0, pb, data, perm, s, 64, hp, 1.0 / 64, 1.0 / 64)
+        ob.adam(pb, 1e-3, 1.0, None)
+    assert torch.equal(pa, pb) and torch.equal(oa.stats, ob.stats) and float((pa - pol.flat).abs().max()) > 1e-4
     # ---- Adam: three steps against torch.optim.Adam, with and without clipping
     for clip in (0.0, 0.5):
         p_t = pol.flat.detach().clone().requires_grad_(True)
