@@ -129,6 +129,7 @@ class Engine(object):
         self.act_f64 = z((B, self.emb_dim), torch.float64) if self.conti else None
         self.pin_act_i32 = torch.zeros((B,), dtype=torch.int32).pin_memory()
         self.pin_rows = torch.zeros((B,), dtype=torch.int32).pin_memory()
+        self._ev_rows, self._ev_act = torch.cuda.Event(), torch.cuda.Event()   # guard reuse of the staging buffers
         self.paid = False       # did the last step compute a reward (click_p valid)?
 
     # ---- episode -----------------------------------------------------------------------------
@@ -142,8 +143,12 @@ class Engine(object):
                 raise ValueError("reset needs %d row indices" % self.B)
             if rows.min() < 0 or rows.max() >= self.log.n:
                 raise IndexError("log row out of range")
+            # the previous episode's copy may still be queued behind its kernels (torch mode never syncs):
+            # wait for it before the staging buffer is overwritten
+            self._ev_rows.synchronize()
             self.pin_rows.numpy()[:] = rows
             self.rows.copy_(self.pin_rows, non_blocking=True)
+            self._ev_rows.record()
         rc = self.lib.r4_reset(self.h, _ptr(self.rows), C.byref(self.out), self._sp())
         _capi.check(self.lib, self.h, rc, "r4_reset")
         self.paid = False
@@ -176,8 +181,10 @@ class Engine(object):
                     raise ValueError("discrete action must have %d entries" % self.B)
                 if arr.size and (arr.min() < 0 or arr.max() >= self.A):
                     raise IndexError("action id out of range [0, %d)" % self.A)   # slate.py:199 IndexError
+                self._ev_act.synchronize()
                 self.pin_act_i32.numpy()[:] = arr
                 self.act_i32.copy_(self.pin_act_i32, non_blocking=True)
+                self._ev_act.record()
                 a = self.act_i32
         self._keep = a
         cur = self.cur_steps
