@@ -3,6 +3,7 @@
 #include "../../include/rl4rs_b200.h"
 #include "r4_kernels.cuh"
 #include "r4_augru_tc.cuh"
+#include "r4_augru_pair.cuh"
 #include "r4_gemm_tc.cuh"
 #include "r4_scores_tc.cuh"
 #include "r4_gru_tc.cuh"
@@ -39,6 +40,7 @@ struct PerSeq {
   float *au_wx = nullptr, *au_bx = nullptr, *au_wgh = nullptr, *au_wch = nullptr;
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
   uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr, *gru_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
+  uint8_t* au_pair_img = nullptr;   // the same weights tiled per CTA rank for the 2-CTA kernel (r4_augru_pair.cuh)
   uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   float abk = 0.f;
 };
@@ -217,6 +219,19 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
   return R4_OK;
 }
 
+// Which AUGRU kernel runs `ctas` = 2 x row tiles of work.  The 2-CTA pair kernel finishes a 128-row tile in ~0.66 of
+// the time of the one-CTA kernel but occupies two SMs for it, so it wins exactly when the one-CTA kernel would leave
+// SMs idle (a 4096-row observation pass: 64 tiles on 148 SMs) and loses on multi-wave launches (the reward pass,
+// batch x 9 rows).  Measured per wave: pair 0.75 ms, single 1.13 ms (tools/augru_probe.cu) -> compare 2*waves vs 3*waves.
+// R4_AUGRU_SINGLE=1 / R4_AUGRU_PAIR=1 force one kernel (A/B runs).
+static bool augru_use_single(int ctas) {
+  static const int force = getenv("R4_AUGRU_SINGLE") ? 1 : (getenv("R4_AUGRU_PAIR") ? 2 : 0);
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  if (force) return force == 1;
+  const int w_single = (ctas + sms - 1) / sms, w_pair = (ctas + sms / 2 - 1) / (sms / 2);
+  return 3 * w_single <= 2 * w_pair;
+}
+
 // One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
 int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const float* dense,
                  const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
@@ -247,25 +262,31 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     s.scoresT = scores + (size_t)i * sc_per_seq;
     s.shared = sh[i];
     r4tc::AugruTcSeq& q = rp.s[i];
-    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = w.au_img; q.scoresT = s.scoresT;
+    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = augru_use_single(2 * rtiles) ? w.au_img : w.au_pair_img; q.scoresT = s.scoresT;
     q.out = allf + i * AUH; q.shared = sh[i];
   }
   sp.R = R; sp.row0 = row0; sp.div = div; sp.q = qbuf;
   rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF;
-  // fork: side stream does the action-independent-of-AUGRU half of the feature vector
+  // The side stream (lowest priority) does the AUGRU-independent half of the feature vector: category attention +
+  // dense tower.  It forks AFTER k_scores_tc and is fed after the AUGRU launch, so the AUGRU pairs (1 CTA per SM,
+  // 128 SMs at 4096 rows) are resident first and the side kernels fill the remaining SMs instead of delaying them.
   static const bool no_side = getenv("R4_NO_SIDE_STREAM") != nullptr;   // diagnostics: serialise for clean per-kernel times
-  if (!no_side) {
-    R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
-    R4_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-  }
-  {
+  static const bool side_early = getenv("R4_SIDE_EARLY") != nullptr;    // diagnostics: fork before k_query (old schedule)
+  auto side_work = [&]() -> int {
     cudaStream_t ss = no_side ? st : e->side;
+    if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
     { ProfScope ps(e, SL_CAT, ss, (double)R * 2.0 * (NCAT * NCAT * EMB * 2));
       k_cat_attn<<<(R + 3) / 4, 128, SMEM_CAT, ss>>>(R, cat, e->emb_cat, allf); }
     R4_LAUNCH_CHECK(e, "k_cat_attn");
-    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, ss))) return rc;
-    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF, ss))) return rc;
+    int rc2;
+    if ((rc2 = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, ss))) return rc2;
+    if ((rc2 = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF, ss))) return rc2;
     if (!no_side) R4_CUDA(e, cudaEventRecord(e->ev_join, ss));
+    return R4_OK;
+  };
+  if (no_side || side_early) {
+    if (!no_side) R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
+    if ((rc = side_work())) return rc;
   }
   { ProfScope ps(e, SL_MISC, st, (double)R);
     r4tc::k_query<<<(R + 7) / 8, 128, 0, st>>>(R, cat, e->emb_seq, e->ps[0].wqd, e->ps[0].ab1, e->ps[1].wqd, e->ps[1].ab1,
@@ -274,9 +295,12 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
     r4tc::k_scores_tc<<<dim3(std::min((R + 1) / 2, 74), 2), r4tc::S_THREADS, r4tc::S_SMEM_BYTES, st>>>(sp, cat, e->emb_seq); }
   R4_LAUNCH_CHECK(e, "k_scores_tc");
+  if (!no_side && !side_early) R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
-    r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp); }
+    if (augru_use_single(2 * rtiles)) r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp);
+    else r4tc::k_augru_pair<<<dim3(rtiles * 2, 2), r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(rp); }
   R4_LAUNCH_CHECK(e, "k_augru_tc");
+  if (!no_side && !side_early && (rc = side_work())) return rc;
   if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
   if (!obs) {
@@ -418,12 +442,15 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
   st = cudaGetLastError();
   if (st != cudaSuccess) { r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(st)); }
-  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) {
     r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, "r4_create: stream/event creation failed");
@@ -574,6 +601,8 @@ int r4_finalize_weights(r4_env* e, void* stream) {
     std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
     r4tc::build_weight_image(awgh.data(), awch.data(), img.data());
     if ((rc = upload(e, img, &w.au_img))) return rc;
+    r4tc::build_pair_image(awgh.data(), awch.data(), img.data());
+    if ((rc = upload(e, img, &w.au_pair_img))) return rc;
     std::vector<float> vb1(ab1, ab1 + AH1), vw2(aw2, aw2 + AH1 * AH2), vb2(ab2, ab2 + AH2), vkv(akv, akv + AH2);
     if ((rc = upload(e, wx, &w.gru_wx)) || (rc = upload(e, bx, &w.gru_bx)) || (rc = upload(e, wgh, &w.gru_wgh)) ||
         (rc = upload(e, wch, &w.gru_wch)) || (rc = upload(e, awx, &w.au_wx)) || (rc = upload(e, abx, &w.au_bx)) ||

@@ -221,7 +221,10 @@ def test_full_batch_properties():
     """BASELINE config 2 size (B=4096): size-independent properties instead of an oracle run.
     * determinism / idempotence: replaying the same rows and actions reproduces obs and rewards bit-exact;
     * row independence (the sharding premise): a row's outputs do not depend on its batch neighbours
-      -- compare against a B=64 env fed a slice of the same rows/actions;
+      -- compare against a B=64 env fed a slice of the same rows/actions.  Integer outputs must be identical; float
+      outputs are compared at the parity tolerance, because the launch geometry picks the AUGRU kernel (2-CTA pair
+      kernel for launches that would leave SMs idle, one-CTA kernel for multi-wave launches such as the B=4096
+      reward pass) and the two round differently in the last bits;
     * mask algebra: chosen items are cleared, popcounts follow the layer sizes;
     * rewards are 0 before the last step and bounded by sum(price) after it."""
     B = 4096
@@ -250,11 +253,13 @@ def test_full_batch_properties():
     small = make_env(small_cfg, False, cat, log, w, output_format="numpy")
     small.sim._recData.pos = 0
     o = small.reset(reset_file=True)
-    np.testing.assert_array_equal(o["obs"], runs[0][0][0][:64])
+    assert_close_rel(o["obs"], runs[0][0][0][:64], what="row independence: reset obs")
     for t in range(9):
-        o, srew, _, _ = small.step(small.offline_action)
-        np.testing.assert_array_equal(o["obs"], runs[0][0][t + 1][:64])
-    np.testing.assert_array_equal(np.asarray(srew), rew[:64])
+        a = small.offline_action
+        o, srew, _, _ = small.step(a)
+        assert_close_rel(o["obs"], runs[0][0][t + 1][:64], what="row independence: obs %d" % t)
+    np.testing.assert_array_equal(small.samples.prev_actions, pa[:64])
+    assert_close_rel(np.asarray(srew), rew[:64], what="row independence: reward")
 
 
 def test_row_chunking_is_invisible():

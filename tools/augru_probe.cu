@@ -1,7 +1,13 @@
 // augru_probe.cu -- standalone check + timing of k_augru_tc against a CPU (f64) recurrence.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/build/augru_probe tools/augru_probe.cu
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
-#ifdef V2
+#ifdef PAIR
+#include "../rl4rs_b200/csrc/r4_augru_pair.cuh"
+#define KERNEL k_augru_pair
+#define KSMEM P_SMEM_BYTES
+#define KTHREADS NTHREADS
+#define GRIDX(t) (2 * (t))
+#elif defined(V2)
 #include "experiments/r4_augru_tc2.cuh"
 #define KERNEL r4tc2::k_augru_tc2
 #define KSMEM r4tc2::SMEM2_BYTES
@@ -27,7 +33,9 @@ static float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; mem
 
 void build_image(const std::vector<float>& Wg, const std::vector<float>& Wc, std::vector<uint8_t>& img) {
   img.assign(W_IMAGE_BYTES, 0);
-#ifdef V2
+#ifdef PAIR
+  build_pair_image(Wg.data(), Wc.data(), img.data());
+#elif defined(V2)
   r4tc2::build_weight_image2(Wg.data(), Wc.data(), img.data());
 #else
   build_weight_image(Wg.data(), Wc.data(), img.data());
@@ -91,7 +99,14 @@ int main(int argc, char** argv) {
     float *dsT2, *dout2;
     CK(cudaMalloc(&dsT2, (size_t)timing_tiles * 64 * TM * 4)); CK(cudaMalloc(&dout2, (size_t)RT * 256 * 4));
     CK(cudaMemset(dsT2, 0, (size_t)timing_tiles * 64 * TM * 4));
-    AugruTcParams q = p; q.s[0].scoresT = dsT2; q.s[0].out = dout2; q.s[0].shared = 1; q.R = RT; q.s[1] = q.s[0];
+    AugruTcParams q = p; q.s[0].scoresT = dsT2; q.s[0].out = dout2; q.s[0].shared = 1; q.R = RT;
+    if (argc > 4 && atoi(argv[4])) {          // every tile streams its own inputs from HBM (as in the product)
+      float* dXTbig; size_t nb = (size_t)timing_tiles * 64 * 768 * TM * 4;
+      CK(cudaMalloc(&dXTbig, nb)); CK(cudaMemset(dXTbig, 0, nb));
+      q.s[0].XT = dXTbig; q.s[0].shared = 0; q.div = 1; q.row0 = 0;
+      printf("unshared inputs: %.2f GB per launch\n", nb / 1e9);
+    }
+    q.s[1] = q.s[0];
     long long* ddbg; CK(cudaMalloc(&ddbg, 64 * 16 * 8)); CK(cudaMemset(ddbg, 0, 64 * 16 * 8));
     q.dbg = ddbg;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -103,12 +118,22 @@ int main(int argc, char** argv) {
       double flops = (double)RT * 64 * 2.0 * (256 * 512 + 256 * 256);
       if (it == 2) {
         long long hd[64 * 16]; CK(cudaMemcpy(hd, ddbg, sizeof(hd), cudaMemcpyDeviceToHost));
+#ifdef PAIR
+        for (int t = 10; t < 13; ++t) {
+          long long* d = hd + t * 16;
+          printf("  step %d MMA thread: wait h %lld | issue r %lld | issue u %lld | wait rh %lld | issue c %lld | total %lld (ring waits: own %lld peer %lld)\n", t, d[1] - d[0],
+                 d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], hd[(t + 1) * 16] - d[0], d[6], d[7]);
+          printf("      epilogue thread 0: wait r %lld | R %lld | wait u %lld | U %lld | wait c %lld | C %lld\n", d[9] - d[8], d[10] - d[9],
+                 d[11] - d[10], d[12] - d[11], d[13] - d[12], d[14] - d[13]);
+        }
+#else
         if (hd[16 * 10]) for (int t = 10; t < 13; ++t) {
           long long* d = hd + t * 16;
           printf("  step %d: waitU %lld | U %lld | waitR %lld | R %lld | waitC %lld | C %lld | total %lld\n", t, d[1] - d[0], d[2] - d[1],
                  d[3] - d[2], d[4] - d[3], d[5] - d[4], d[6] - d[5], hd[(t + 1) * 16] - d[0]);
           printf("      R detail: 2 chunks %lld | publish %lld | 2 chunks %lld | publish %lld\n", d[8] - d[3], d[9] - d[8], d[10] - d[9], d[11] - d[10]);
         }
+#endif
       }
       printf("timing: %d tiles (%d rows) %.3f ms -> %.1f TFLOP/s fp32-equivalent, %.0f cycles/step @1.965GHz\n", timing_tiles, RT, ms,
              flops / ms / 1e9, ms * 1e-3 * 1.965e9 / 64 / ((GRIDX(timing_tiles) + 147) / 148));
