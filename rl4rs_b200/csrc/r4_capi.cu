@@ -167,22 +167,27 @@ int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// n-tile width of the observation-head GEMM (K = 3456, N = 256): 128 doubles its CTA count (64 at batch 4096).
+constexpr int HEAD_BNT = 128;
+
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
-         int ldT = 0, float* outT = nullptr, float* outK = nullptr) {
+         int ldT = 0, float* outT = nullptr, float* outK = nullptr, int bnt = r4tc::G_BNMAX) {
   if (M <= 0) return R4_OK;
   if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
   r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act, tm_ns, cr_base, ldT, outT, outK};
-  dim3 grid((M + r4tc::G_BM - 1) / r4tc::G_BM, (N + r4tc::G_BNMAX - 1) / r4tc::G_BNMAX);
-  r4tc::k_gemm_tc<<<grid, r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
+  p.bnt = bnt;
+  static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  const int tiles = ((M + r4tc::G_BM - 1) / r4tc::G_BM) * ((N + bnt - 1) / bnt);
+  r4tc::k_gemm_tc<<<std::min(tiles, sms), r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
   R4_LAUNCH_CHECK(e, "k_gemm_tc");
   return R4_OK;
 }
 
-int upload_image(r4_env* e, const float* W, int K, int N, uint8_t** out) {
-  std::vector<uint8_t> img(r4tc::gemm_image_bytes(K, N));
-  r4tc::build_gemm_image(W, K, N, img.data());
+int upload_image(r4_env* e, const float* W, int K, int N, uint8_t** out, int bnt = r4tc::G_BNMAX) {
+  std::vector<uint8_t> img(r4tc::gemm_image_bytes(K, N, bnt));
+  r4tc::build_gemm_image(W, K, N, img.data(), bnt);
   return upload(e, img, out);
 }
 
@@ -307,7 +312,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
     obs = reinterpret_cast<float*>(e->ws_obs.p);
   }
-  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo_img, e->bo, obs, OBSD, st))) return rc;
+  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr, nullptr, HEAD_BNT))) return rc;
   if (p1_out || probs_out) {
     { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
     k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
@@ -536,7 +541,7 @@ int r4_finalize_weights(r4_env* e, void* stream) {
 #undef UP
   if ((rc = upload_image(e, e->hw["dense_w1"].data(), NDENSE, HU, &e->w1_img)) ||
       (rc = upload_image(e, e->hw["dense_w2"].data(), HU, HU, &e->w2_img)) ||
-      (rc = upload_image(e, e->hw["obs_w"].data(), ALLF, OBSD, &e->wo_img))) return rc;
+      (rc = upload_image(e, e->hw["obs_w"].data(), ALLF, OBSD, &e->wo_img, HEAD_BNT))) return rc;
   for (int i = 0; i < 2; ++i) {
     std::string si = std::to_string(i);
     const float* gwg = hw_get(e, "gru" + si + "_wg", (size_t)2 * EMB * 2 * EMB);

@@ -7,21 +7,24 @@
 // 24 significand bits together), and the six products whose magnitude exceeds 2^-24 of the result are
 // issued (hh, hm, mh, hl, lh, mm), fp32 accumulation in TMEM.  These layers are a few % of the step, so
 // the 2x tensor work over the 2-way split of the recurrence buys parity margin for free.
-// One CTA = a 128-row x (<=256)-column tile.
-// Warp roles: 0-3 A producers (fp32 -> bf16 hi/lo core matrices, coalesced 32-byte reads per thread)
-// and, at the end, the epilogue (TMEM -> bias/act -> global); 4 MMA issuer; 5 TMA producer for W.
-// Ring: 3 stages x (A hi/mid/lo 24 KB + W hi/mid/lo <=48 KB), K block = 32.
+// Persistent CTAs (one per SM) walk the 128-row x (<=256)-column tiles.
+// Warp roles: 0-7 A producers (cp.async fp32 rows -> bf16 hi/mid/lo core matrices), 8 MMA issuer, 9 TMA producer
+// for W, 12-15 epilogue (TMEM -> bias/act -> global) on the second of two TMEM accumulators, 10-11 idle.
+// Operand ring: 2 stages x (A hi/mid/lo 24 KB + W hi/mid/lo <=48 KB), K block = 32; raw A ring: 4 x 16 KB.
 #pragma once
 #include "r4_augru_tc.cuh"
 
 namespace r4tc {
 
-constexpr int G_BM = 128, G_BK = 32, G_NST = 3, G_BNMAX = 256, G_SPLIT = 3;
+constexpr int G_BM = 128, G_BK = 32, G_NST = 2, G_BNMAX = 256, G_SPLIT = 3, G_RAW = 3, G_OUTB = 3;
 constexpr int G_A_STAGE = G_BM * G_BK * 2;                 // 8 KB per split
 constexpr int G_B_STAGE = G_BNMAX * G_BK * 2;              // 16 KB per split (max)
 constexpr int G_STAGE_BYTES = G_SPLIT * G_A_STAGE + G_SPLIT * G_B_STAGE;   // 72 KB
-constexpr int G_SMEM_BYTES = G_NST * G_STAGE_BYTES + 1024;
-constexpr int G_THREADS = 192;
+constexpr int G_RAW_BYTES = G_BM * G_BK * 4;                // 16 KB: one K block of fp32 A rows as they arrive (cp.async)
+constexpr int G_OUT_BYTES = 16 * G_BM * 4;                  // 8 KB: 16 output columns x 128 rows, staged for one bulk store
+constexpr int G_SMEM_BYTES = G_NST * G_STAGE_BYTES + G_RAW * G_RAW_BYTES + G_OUTB * G_OUT_BYTES + 1024;
+constexpr int G_THREADS = 512;
+constexpr int G_W_MMA = 8, G_W_TMA = 9, G_W_EPI = 12, G_EPI_T0 = G_W_EPI * 32;   // warps 0-7 produce A, 10-11 idle
 constexpr int G_A_SBO = (G_BK / 8) * 128;                  // 512
 constexpr int G_B_SBO = (G_BK / 8) * 128;                  // 512
 
@@ -32,17 +35,19 @@ struct GemmImage {
 };
 
 // image layout: n-tile nt (256 columns, last one narrower), K block kb, split {hi, lo}: [bn x 32] core matrices
-inline size_t gemm_image_bytes(int K, int N) {
+// bnt = n-tile width the image is cut for (<= 256, multiple of 16): 256 by default; 128 for a GEMM whose m-tiles alone
+// would leave most SMs idle (the observation head: 32 m-tiles at batch 4096).
+inline size_t gemm_image_bytes(int K, int N, int bnt = G_BNMAX) {
   int kb = (K + G_BK - 1) / G_BK;
   size_t tot = 0;
-  for (int n0 = 0; n0 < N; n0 += G_BNMAX) tot += (size_t)kb * G_SPLIT * std::min(G_BNMAX, N - n0) * G_BK * 2;
+  for (int n0 = 0; n0 < N; n0 += bnt) tot += (size_t)kb * G_SPLIT * std::min(bnt, N - n0) * G_BK * 2;
   return tot;
 }
-inline void build_gemm_image(const float* W /*[K][N]*/, int K, int N, uint8_t* img) {
+inline void build_gemm_image(const float* W /*[K][N]*/, int K, int N, uint8_t* img, int bnt = G_BNMAX) {
   int kbn = (K + G_BK - 1) / G_BK;
   size_t off = 0;
-  for (int n0 = 0; n0 < N; n0 += G_BNMAX) {
-    int bn = std::min(G_BNMAX, N - n0);
+  for (int n0 = 0; n0 < N; n0 += bnt) {
+    int bn = std::min(bnt, N - n0);
     for (int kb = 0; kb < kbn; ++kb)
       for (int sp = 0; sp < G_SPLIT; ++sp) {
         uint8_t* st = img + off;
@@ -72,28 +77,38 @@ struct GemmTcParams {
   // columns >= ldT -> outK[(nabs * 64 + t) * (N - ldT) + col - ldT], nabs = cr_base + n.  Consecutive threads are
   // consecutive sequences of one step, so both reads and transposed writes stay coalesced.
   int tm_ns, cr_base, ldT; float* outT; float* outK;
+  int bnt = G_BNMAX;          // n-tile width of the weight image (build_gemm_image)
+  long long* dbg = nullptr;   // development probe (tools/gemm_probe.cu): per-role wait/busy cycles of CTA 0
 };
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+// Persistent: gridDim.x CTAs walk the (m-tile, n-tile) list (n inner, so the CTAs working on one m-tile at the same
+// time share its A rows in L2).  The four pipelines -- A staging (cp.async, G_RAW K blocks in flight per thread),
+// W stream (TMA), MMA, epilogue -- run across tile boundaries; two 256-column TMEM accumulators let the epilogue of
+// tile i overlap the main loop of tile i+1.
 __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_a[G_NST], bar_b[G_NST], bar_empty[G_NST], bar_done;
+  uint8_t* raw = smem + G_NST * G_STAGE_BYTES;
+  uint8_t* outb = raw + G_RAW * G_RAW_BYTES;
+  __shared__ uint64_t bar_a[G_NST], bar_b[G_NST], bar_empty[G_NST], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float bias_s[2][G_BNMAX];          // bias of the tile in each accumulator's epilogue
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * G_BM;
-  const int n0 = blockIdx.y * G_BNMAX;
-  const int bn = min(G_BNMAX, p.N - n0);
   const int kbn = (p.K + G_BK - 1) / G_BK;
-  // start of this n-tile in the image: full tiles before it are 256 wide
-  const uint8_t* wtile = p.Wimg + (size_t)blockIdx.y * kbn * G_SPLIT * G_BNMAX * G_BK * 2;
-  const uint32_t b_split_bytes = (uint32_t)bn * G_BK * 2;
+  const int ntn = (p.N + p.bnt - 1) / p.bnt, mtn = (p.M + G_BM - 1) / G_BM, ntiles = mtn * ntn;
 
   if (tid == 0) {
-    for (int i = 0; i < G_NST; ++i) { mbar_init(&bar_a[i], 128); mbar_init(&bar_b[i], 1); mbar_init(&bar_empty[i], 1); }
-    mbar_init(&bar_done, 1);
+    for (int i = 0; i < G_NST; ++i) { mbar_init(&bar_a[i], 256); mbar_init(&bar_b[i], 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256));
+  if (warp == G_W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
@@ -101,158 +116,247 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
 
-  if (warp == 5) {
+  if (warp == G_W_TMA) {
+    // ===== W stream =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < kbn; ++kb) {
-        mbar_wait(&bar_empty[stage], phase ^ 1);
-        uint8_t* dst = smem + stage * G_STAGE_BYTES + G_SPLIT * G_A_STAGE;
-        mbar_expect_tx(&bar_b[stage], G_SPLIT * b_split_bytes);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int nt = tile % ntn;
+        const uint32_t bsb = (uint32_t)min(p.bnt, p.N - nt * p.bnt) * G_BK * 2;
+        // start of this n-tile in the image: the tiles before it are full width
+        const uint8_t* wtile = p.Wimg + (size_t)nt * kbn * G_SPLIT * p.bnt * G_BK * 2;
+        for (int kb = 0; kb < kbn; ++kb) {
+          mbar_wait(&bar_empty[stage], phase ^ 1);
+          uint8_t* dst = smem + stage * G_STAGE_BYTES + G_SPLIT * G_A_STAGE;
+          mbar_expect_tx(&bar_b[stage], G_SPLIT * bsb);
 #pragma unroll
-        for (int sp = 0; sp < G_SPLIT; ++sp)
-          bulk_g2s(dst + sp * G_B_STAGE, wtile + ((size_t)kb * G_SPLIT + sp) * b_split_bytes, b_split_bytes, &bar_b[stage]);
-        if (++stage == G_NST) { stage = 0; phase ^= 1; }
+          for (int sp = 0; sp < G_SPLIT; ++sp)
+            bulk_g2s(dst + sp * G_B_STAGE, wtile + ((size_t)kb * G_SPLIT + sp) * bsb, bsb, &bar_b[stage]);
+          if (++stage == G_NST) { stage = 0; phase ^= 1; }
+        }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == G_W_MMA) {
+    // ===== MMA issuer =====
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(G_BM, bn);
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < kbn; ++kb) {
-        mbar_wait(&bar_a[stage], phase);
-        mbar_wait(&bar_b[stage], phase);
+      int li = 0;
+      long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();
+      const bool probe = p.dbg && blockIdx.x == 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+        const int nt = tile % ntn;
+        const uint32_t idesc = make_idesc(G_BM, min(p.bnt, p.N - nt * p.bnt));
+        const uint32_t acc = tbase + (uint32_t)(li & 1) * G_BNMAX;
+        long long c0 = probe ? clock64() : 0;
+        mbar_wait(&acc_empty[li & 1], (uint32_t)((li >> 1) & 1) ^ 1u);   // the epilogue has drained this accumulator
+        if (probe) w_acc += clock64() - c0;
         tc_fence_after();
-        uint32_t sa = smem_u32(smem + stage * G_STAGE_BYTES);
-        uint32_t sb = sa + G_SPLIT * G_A_STAGE;
+        for (int kb = 0; kb < kbn; ++kb) {
+          if (probe) {
+            long long c1 = clock64(); mbar_wait(&bar_a[stage], phase);
+            long long c2 = clock64(); mbar_wait(&bar_b[stage], phase);
+            w_a += c2 - c1; w_b += clock64() - c2;
+          } else { mbar_wait(&bar_a[stage], phase); mbar_wait(&bar_b[stage], phase); }
+          tc_fence_after();
+          uint32_t sa = smem_u32(smem + stage * G_STAGE_BYTES);
+          uint32_t sb = sa + G_SPLIT * G_A_STAGE;
 #pragma unroll
-        for (int j = 0; j < G_BK / 16; ++j) {
-          uint64_t a[3], b[3];
+          for (int j = 0; j < G_BK / 16; ++j) {
+            uint64_t a[3], b[3];
 #pragma unroll
-          for (int sp = 0; sp < 3; ++sp) {
-            a[sp] = make_desc(sa + sp * G_A_STAGE + j * 2 * LBO, LBO, G_A_SBO);
-            b[sp] = make_desc(sb + sp * G_B_STAGE + j * 2 * LBO, LBO, G_B_SBO);
+            for (int sp = 0; sp < 3; ++sp) {
+              a[sp] = make_desc(sa + sp * G_A_STAGE + j * 2 * LBO, LBO, G_A_SBO);
+              b[sp] = make_desc(sb + sp * G_B_STAGE + j * 2 * LBO, LBO, G_B_SBO);
+            }
+            // smallest products first so they are not absorbed by a large partial sum
+            mma_bf16(acc, a[1], b[1], idesc, (kb | j) ? 1u : 0u);   // mid*mid
+            mma_bf16(acc, a[0], b[2], idesc, 1u);                   // hi*lo
+            mma_bf16(acc, a[2], b[0], idesc, 1u);                   // lo*hi
+            mma_bf16(acc, a[0], b[1], idesc, 1u);                   // hi*mid
+            mma_bf16(acc, a[1], b[0], idesc, 1u);                   // mid*hi
+            mma_bf16(acc, a[0], b[0], idesc, 1u);                   // hi*hi
           }
-          // smallest products first so they are not absorbed by a large partial sum
-          mma_bf16(tbase, a[1], b[1], idesc, (kb | j) ? 1u : 0u);   // mid*mid
-          mma_bf16(tbase, a[0], b[2], idesc, 1u);                   // hi*lo
-          mma_bf16(tbase, a[2], b[0], idesc, 1u);                   // lo*hi
-          mma_bf16(tbase, a[0], b[1], idesc, 1u);                   // hi*mid
-          mma_bf16(tbase, a[1], b[0], idesc, 1u);                   // mid*hi
-          mma_bf16(tbase, a[0], b[0], idesc, 1u);                   // hi*hi
+          umma_commit(&bar_empty[stage]);
+          if (++stage == G_NST) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&bar_empty[stage]);
-        if (++stage == G_NST) { stage = 0; phase ^= 1; }
+        umma_commit(&acc_full[li & 1]);
       }
-      umma_commit(&bar_done);
+      if (probe) { p.dbg[0] = clock64() - t_begin; p.dbg[1] = w_acc; p.dbg[2] = w_a; p.dbg[3] = w_b; p.dbg[4] = li; }
     }
-  } else {
-    // ---- A producers: thread (r8 = tid/4, kc = tid%4) converts 8 consecutive K values of 4 rows per K block ----
-    const int kc = tid & 3;
-    const float* arow[4];
+  } else if (warp < 8) {
+    // ===== A producers: thread (r8 = tid/4, kc = tid%4) stages and converts 8 consecutive K values of 4 rows per
+    // K block.  The fp32 rows come in through cp.async into a private 32-byte slot per (row, kc); G_RAW - 1 K blocks
+    // are in flight while one is converted (a register-staged single prefetch left the GEMMs latency-bound).
+    const int kc = tid & 3, r8 = tid >> 2;      // 64 row slots x 2 passes
+    const float* arow[2] = {p.A, p.A};
+    int is_tile = blockIdx.x, is_kb = 0;
+    auto issue = [&](int slot) {
+      if (is_tile < ntiles) {
+        if (is_kb == 0) {
+          const int m0 = (is_tile / ntn) * G_BM;
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
-      int m = m0 + it * 32 + (tid >> 2);
-      if (m >= p.M) m = p.M - 1;
-      if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
-      size_t src = p.gather ? (size_t)p.gather[m] : (size_t)m;
-      arow[it] = p.A + src * p.lda + kc * 8;
-    }
-    int stage = 0; uint32_t phase = 0;
-    float v[4][8], nx[4][8];
-    auto load_block = [&](int kb, float (*dst)[8]) {
-      const int k = kb * G_BK + kc * 8;
-      const bool kok = kb < kbn && k + 8 <= p.K;        // K % 8 == 0 is required
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        if (kok) {
-          float4 x0 = __ldg(reinterpret_cast<const float4*>(arow[it] + kb * G_BK));
-          float4 x1 = __ldg(reinterpret_cast<const float4*>(arow[it] + kb * G_BK + 4));
-          dst[it][0] = x0.x; dst[it][1] = x0.y; dst[it][2] = x0.z; dst[it][3] = x0.w;
-          dst[it][4] = x1.x; dst[it][5] = x1.y; dst[it][6] = x1.z; dst[it][7] = x1.w;
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[it][j] = 0.f;
+          for (int it = 0; it < 2; ++it) {
+            int m = m0 + it * 64 + r8;
+            if (m >= p.M) m = p.M - 1;
+            if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
+            size_t src = p.gather ? (size_t)__ldg(p.gather + m) : (size_t)m;
+            arow[it] = p.A + src * p.lda + kc * 8;
+          }
         }
+        const bool kok = is_kb * G_BK + kc * 8 + 8 <= p.K;   // K % 8 == 0 is required; beyond K: zero fill
+        const uint32_t nb = kok ? 16u : 0u;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          uint8_t* dst = raw + slot * G_RAW_BYTES + (it * 64 + r8) * (G_BK * 4) + kc * 32;
+          const float* src = kok ? arow[it] + is_kb * G_BK : arow[it];
+          cp_async16(dst, src, nb);
+          cp_async16(dst + 16, src + 4, nb);
+        }
+        if (++is_kb == kbn) { is_kb = 0; is_tile += gridDim.x; }
       }
+      cp_async_commit();
     };
-    load_block(0, v);
-    for (int kb = 0; kb < kbn; ++kb) {
-      load_block(kb + 1, nx);                           // next block's global loads fly during this one
-      mbar_wait(&bar_empty[stage], phase ^ 1);
-      uint8_t* sa = smem + stage * G_STAGE_BYTES;
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        int row = it * 32 + (tid >> 2);
-        uint4 hi, mid, lo;
-        float r1[8];
-        split8(v[it], hi, mid);                         // hi and bf16(x - hi)
+    for (int d = 0; d < G_RAW - 1; ++d) issue(d);
+    int stage = 0; uint32_t phase = 0;
+    int slot = 0;
+    long long w_cp = 0, w_empty = 0;
+    const bool probe = p.dbg && blockIdx.x == 0 && tid == 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kbn; ++kb) {
+        issue(slot == 0 ? G_RAW - 1 : slot - 1);          // the slot converted in the previous iteration
+        long long c0 = probe ? clock64() : 0;
+        cp_async_wait<G_RAW - 1>();
+        long long c1 = probe ? clock64() : 0;
+        mbar_wait(&bar_empty[stage], phase ^ 1);
+        if (probe) { w_cp += c1 - c0; w_empty += clock64() - c1; }
+        uint8_t* sa = smem + stage * G_STAGE_BYTES;
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int row = it * 64 + r8;
+          const uint8_t* rs = raw + slot * G_RAW_BYTES + row * (G_BK * 4) + kc * 32;
+          float v[8];
+          *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(rs);
+          *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(rs + 16);
+          uint4 hi, mid, lo;
+          float r1[8];
+          split8(v, hi, mid);                             // hi and bf16(x - hi)
+          {
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
+            const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mid);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              r1[2 * j] = (v[2 * j] - __bfloat162float(h2[j].x)) - __bfloat162float(m2[j].x);
+              r1[2 * j + 1] = (v[2 * j + 1] - __bfloat162float(h2[j].y)) - __bfloat162float(m2[j].y);
+            }
+            uint32_t l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162 ll = __floats2bfloat162_rn(r1[2 * j], r1[2 * j + 1]);
+              l[j] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            lo = make_uint4(l[0], l[1], l[2], l[3]);
+          }
+          uint32_t off = (uint32_t)(row / 8) * G_A_SBO + (uint32_t)kc * LBO + (uint32_t)(row % 8) * 16;
+          *reinterpret_cast<uint4*>(sa + off) = hi;
+          *reinterpret_cast<uint4*>(sa + G_A_STAGE + off) = mid;
+          *reinterpret_cast<uint4*>(sa + 2 * G_A_STAGE + off) = lo;
+        }
+        proxy_fence();
+        mbar_arrive(&bar_a[stage]);
+        if (++stage == G_NST) { stage = 0; phase ^= 1; }
+        if (++slot == G_RAW) slot = 0;
+      }
+    }
+    cp_async_wait<0>();
+    if (probe) { p.dbg[5] = w_cp; p.dbg[6] = w_empty; }
+  } else if (warp >= G_W_EPI) {
+    // ===== epilogue: thread = row =====
+    const int q = warp - G_W_EPI;
+    const int row = q * 32 + lane;
+    int li = 0, nchunk = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
+      const int m0 = (tile / ntn) * G_BM, n0 = (tile % ntn) * p.bnt;
+      const int bn = min(p.bnt, p.N - n0);
+      const int m = m0 + row;
+      const uint32_t tlane = tbase + (uint32_t)(li & 1) * G_BNMAX + ((uint32_t)(q * 32) << 16);
+      const bool probe = p.dbg && blockIdx.x == 0 && tid == G_EPI_T0;
+      for (int i = tid - G_EPI_T0; i < bn; i += 128) bias_s[li & 1][i] = p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      long long c0 = probe ? clock64() : 0;
+      mbar_wait(&acc_full[li & 1], (uint32_t)((li >> 1) & 1));
+      long long c1 = probe ? clock64() : 0;
+      tc_fence_after();
+      // Sequence mode, aligned tile: its 128 rows are 128 consecutive sequences of ONE step, so 16 output columns are
+      // one contiguous 8 KB block of the lane-major layout.  Stage them in shared memory and let the bulk-copy
+      // engine write them: per-thread stores of this epilogue (one 128-byte line per warp instruction, a few in
+      // flight per warp) ran at ~0.5 TB/s chip-wide and were the whole kernel time (tools/gemm_probe.cu).
+      const bool blk = p.tm_ns > 0 && (p.tm_ns % G_BM) == 0 && (p.cr_base % G_BM) == 0 && m0 + G_BM <= p.M;
+      for (int c = 0; c < bn; c += 16) {
+        float a[16];
+        long long e0 = probe ? clock64() : 0;
+        tmem_ld16(tlane + c, a);
+        tmem_wait_ld();
+        long long e1 = probe ? clock64() : 0;
+        // bias + activation for the whole chunk first, branch-free: with the bias load, the ELU branch and the store
+        // interleaved per element the chunk was a chain of 16 exposed latencies (~2.4k cycles; ncu source page in
+        // profiles/) and the epilogue, not the MMAs, set the time of the sequence-mode GEMMs.
         {
-          const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&hi);
-          const __nv_bfloat162* m2 = reinterpret_cast<const __nv_bfloat162*>(&mid);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s[li & 1] + c);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            r1[2 * j] = (v[it][2 * j] - __bfloat162float(h2[j].x)) - __bfloat162float(m2[j].x);
-            r1[2 * j + 1] = (v[it][2 * j + 1] - __bfloat162float(h2[j].y)) - __bfloat162float(m2[j].y);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 bq = b4[q4];
+            a[4 * q4] += bq.x; a[4 * q4 + 1] += bq.y; a[4 * q4 + 2] += bq.z; a[4 * q4 + 3] += bq.w;
           }
-          uint32_t l[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 ll = __floats2bfloat162_rn(r1[2 * j], r1[2 * j + 1]);
-            l[j] = *reinterpret_cast<uint32_t*>(&ll);
-          }
-          lo = make_uint4(l[0], l[1], l[2], l[3]);
         }
-        uint32_t off = (uint32_t)(row / 8) * G_A_SBO + (uint32_t)kc * LBO + (uint32_t)(row % 8) * 16;
-        *reinterpret_cast<uint4*>(sa + off) = hi;
-        *reinterpret_cast<uint4*>(sa + G_A_STAGE + off) = mid;
-        *reinterpret_cast<uint4*>(sa + 2 * G_A_STAGE + off) = lo;
-      }
-      proxy_fence();
-      mbar_arrive(&bar_a[stage]);
-      if (++stage == G_NST) { stage = 0; phase ^= 1; }
+        if (p.act == 1) {
 #pragma unroll
-      for (int it = 0; it < 4; ++it)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[it][j] = nx[it][j];
-    }
-    // ---- epilogue: thread = row ----
-    mbar_wait(&bar_done, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int m = m0 + row;
-    const uint32_t tlane = tbase + ((uint32_t)(warp * 32) << 16);
-    for (int c = 0; c < bn; c += 16) {
-      float a[16];
-      tmem_ld16(tlane + c, a);
-      tmem_wait_ld();
-      if (m < p.M && p.tm_ns > 0) {
-        const int t = m / p.tm_ns, nabs = p.cr_base + m % p.tm_ns;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int col = n0 + c + j;
-          float r = a[j] + (p.bias ? __ldg(p.bias + col) : 0.f);
-          if (p.act == 1) r = r > 0.f ? r : expm1f(r);
-          if (col < p.ldT) p.outT[(((size_t)(nabs / TM) * STEPS + t) * p.ldT + col) * TM + (nabs % TM)] = r;
-          else p.outK[((size_t)nabs * STEPS + t) * (p.N - p.ldT) + (col - p.ldT)] = r;
-        }
-      } else if (m < p.M) {
-        float* o = p.C + (size_t)m * p.ldc + n0 + c;
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float4 r = make_float4(a[j] + b.x, a[j + 1] + b.y, a[j + 2] + b.z, a[j + 3] + b.w);
-          if (p.act == 1) {
-            r.x = r.x > 0.f ? r.x : expm1f(r.x); r.y = r.y > 0.f ? r.y : expm1f(r.y);
-            r.z = r.z > 0.f ? r.z : expm1f(r.z); r.w = r.w > 0.f ? r.w : expm1f(r.w);
+          for (int j = 0; j < 16; ++j) {
+            const float en = expm1f(fminf(a[j], 0.f));
+            a[j] = a[j] > 0.f ? a[j] : en;
           }
-          *reinterpret_cast<float4*>(o + j) = r;
+        }
+        if (blk && n0 + c + 16 <= p.ldT) {
+          float* ob = reinterpret_cast<float*>(outb + (nchunk % G_OUTB) * G_OUT_BYTES);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ob[j * G_BM + row] = a[j];
+          long long e2 = probe ? clock64() : 0;
+          proxy_fence();
+          long long e3 = probe ? clock64() : 0;
+          // the buffer the NEXT chunk will use must have been read out by its previous bulk store
+          if (tid == G_EPI_T0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(G_OUTB - 2) : "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (tid == G_EPI_T0) {
+            const int t = m0 / p.tm_ns, nb = (p.cr_base + m0 % p.tm_ns) / G_BM;
+            float* dst = p.outT + (((size_t)nb * STEPS + t) * p.ldT + (n0 + c)) * TM;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(ob)), "r"(G_OUT_BYTES) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          if (probe) { long long e4 = clock64(); p.dbg[9] += e1 - e0; p.dbg[10] += e2 - e1; p.dbg[11] += e3 - e2; p.dbg[12] += e4 - e3; }
+          ++nchunk;
+        } else if (m < p.M && p.tm_ns > 0) {
+          const int t = m / p.tm_ns, nabs = p.cr_base + m % p.tm_ns;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n0 + c + j;
+            if (col < p.ldT) p.outT[(((size_t)(nabs / TM) * STEPS + t) * p.ldT + col) * TM + (nabs % TM)] = a[j];
+            else p.outK[((size_t)nabs * STEPS + t) * (p.N - p.ldT) + (col - p.ldT)] = a[j];
+          }
+        } else if (m < p.M) {
+          float* o = p.C + (size_t)m * p.ldc + n0 + c;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
         }
       }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[li & 1]);
+      if (probe) { p.dbg[7] += c1 - c0; p.dbg[8] += clock64() - c1; }
     }
+    if (tid == G_EPI_T0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging buffers are read out before exit
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(256));
+  if (warp == G_W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512));
 }
 
 }  // namespace r4tc

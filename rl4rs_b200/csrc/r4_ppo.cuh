@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
   float* dv_s = dpre_s + TS * HID;              // [TS]
   __shared__ int64_t src[TS];
   __shared__ float stat_s[5];
+  __shared__ float stat_t[TS][5];               // per-sample terms of this tile, summed in sample order (deterministic)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* gout = partial + (size_t)blockIdx.x * L.n;
   const float* w1p = prm + L.o_w1;
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
       float* lg = lg_s + s * L.A;
       if (s >= nvalid) {
         for (int c = lane; c < L.A; c += 32) lg[c] = 0.f;
-        if (lane == 0) dv_s[s] = 0.f;
+        if (lane == 0) { dv_s[s] = 0.f; for (int k = 0; k < 5; ++k) stat_t[s][k] = 0.f; }
         continue;
       }
       const int64_t r = src[s];
@@ -285,11 +286,11 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
         dv_s[s] = dv;
         float tot = hp.mode == 0 ? (pl + hp.kl_coeff * kl + hp.vf_coeff * vl - hp.ent_coeff * ent)
                                  : (pl + hp.vf_coeff * vl - hp.ent_coeff * ent);
-        atomicAdd(&stat_s[0], pl); atomicAdd(&stat_s[1], vl); atomicAdd(&stat_s[2], kl);
-        atomicAdd(&stat_s[3], ent); atomicAdd(&stat_s[4], tot);
+        stat_t[s][0] = pl; stat_t[s][1] = vl; stat_t[s][2] = kl; stat_t[s][3] = ent; stat_t[s][4] = tot;
       }
     }
     __syncthreads();
+    if (tid < 5) { float a = stat_s[tid]; for (int k = 0; k < TS; ++k) a += stat_t[k][tid]; stat_s[tid] = a; }
     // ---- backward ----
     for (int col = tid; col < L.A; col += NT) {          // dW2[k][col], db2[col]
       float d[TS];
