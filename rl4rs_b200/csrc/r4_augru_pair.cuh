@@ -22,10 +22,6 @@
 #pragma once
 #include "r4_augru_tc.cuh"
 
-#ifndef R4P_EXP
-#define R4P_EXP 0          // development experiments (tools/augru_probe.cu); 0 = product
-#endif
-
 namespace r4tc {
 
 constexpr int P_RC = 64;                              // rows per CTA
@@ -81,7 +77,7 @@ __device__ __forceinline__ void cluster_sync_all() {
 // Wimg of a sequence here = [rank 2][24 stages][hi 8 KB | lo 8 KB] (build_pair_image), everything else as AugruTcParams.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru_pair(AugruTcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h, bar_rh, bar_r, bar_u, bar_c;
+  __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h0, bar_h1, bar_rh, bar_r, bar_u, bar_c;
   __shared__ uint32_t tmem_base_s;
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   uint8_t* sHhi = smem;                       // A operand: h
@@ -97,7 +93,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   if (tid == 0) {
     // the leader's "full" collects its own TMA (expect_tx arrival + bytes) and the peer's relay arrival
     for (int i = 0; i < P_NST; ++i) { mbar_init(&bar_full[i], rank == 0 ? 2 : 1); mbar_init(&bar_empty[i], 1); }
-    mbar_init(&bar_h, 16); mbar_init(&bar_rh, 16);          // 8 epilogue warps x 2 CTAs, one arrival each
+    mbar_init(&bar_h0, 16); mbar_init(&bar_h1, 16); mbar_init(&bar_rh, 16);          // 8 epilogue warps x 2 CTAs, one arrival each
     mbar_init(&bar_r, 1); mbar_init(&bar_u, 1); mbar_init(&bar_c, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -122,9 +118,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
           const uint8_t* src = img;
           for (int i = 0; i < P_STAGES_PER_STEP; ++i, src += P_STAGE_BYTES) {
             if (stage % P_CG == 0) mbar_wait(&bar_empty[stage / P_CG], phase ^ 1);
-#if R4P_EXP == 2
-            if (t > 0 || i >= P_NST) { mbar_arrive(&bar_full[stage]); if (++stage == P_NST) { stage = 0; phase ^= 1; } continue; }
-#endif
             mbar_expect_tx(&bar_full[stage], P_STAGE_BYTES);
             bulk_g2s(sB + stage * P_STAGE_BYTES, src, P_STAGE_BYTES, &bar_full[stage]);
             if (++stage == P_NST) { stage = 0; phase ^= 1; }
@@ -152,33 +145,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         const bool probe = p.dbg && blockIdx.x == 0 && blockIdx.y == 0;
         // One gate: 8 ring stages; per stage 2 K16 slices x (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo).  No tcgen05 fence per
         // stage: the operands come from TMA, the barrier wait alone orders them before the MMAs.
-        auto gemm = [&](uint32_t aHi, uint32_t aLo, uint32_t dcol) {
-          for (int kb = 0; kb < NKB; ++kb) {
+        // `perm`: the r and u gates walk the K blocks of h in the order 0,2,4,6,1,3,5,7 (P_KPERM) -- the order in which the
+        // epilogue finishes them (every thread owns two adjacent K blocks and writes the even one first) -- so the first
+        // half of the r gate overlaps the second half of the previous step's phase C.  `half_bar`: waited on before the
+        // second half.  The weight image is laid out in the same order (build_pair_image).
+        auto gemm = [&](uint32_t aHi, uint32_t aLo, uint32_t dcol, bool perm, uint64_t* half_bar, uint32_t half_par) {
+          for (int s8 = 0; s8 < NKB; ++s8) {
+            const int kb = perm ? ((s8 & 3) * 2 + (s8 >> 2)) : s8;
+            if (s8 == NKB / 2 && half_bar) { mbar_wait_cl(half_bar, half_par); tc_fence_after(); }
             if (probe) { long long a = clock64(); mbar_wait(&bar_full[stage], phase); w_full += clock64() - a; }
             else mbar_wait(&bar_full[stage], phase);
             const uint32_t b = bBase + stage * P_STAGE_BYTES;
 #pragma unroll
             for (int j = 0; j < KB / 16; ++j) {
               const uint64_t dbh = make_desc(b + j * 2 * LBO, LBO, B_SBO), dbl = make_desc(b + P_HALF_BYTES + j * 2 * LBO, LBO, B_SBO);
-#if R4P_EXP == 4
-              const uint32_t koff = 0;
-#else
               const uint32_t koff = (kb * (KB / 16) + j) * 2 * LBO;
-#endif
               const uint64_t dah = make_desc(aHi + koff, LBO, A_SBO), dal = make_desc(aLo + koff, LBO, A_SBO);
-#if R4P_EXP == 6
-              mma2_bf16(tbase + dcol, dah, dbh, idesc, (kb | j) ? 1u : 0u);
-              mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
-              mma2_bf16(tbase + dcol, dal, dbh, idesc, 1u);
-#elif R4P_EXP == 7
-              mma2_bf16(tbase + dcol, dal, dbh, idesc, (kb | j) ? 1u : 0u);
-              mma2_bf16(tbase + dcol, dah, dbh, idesc, 1u);
-              mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
-#else
-              mma2_bf16(tbase + dcol, dah, dbh, idesc, (kb | j) ? 1u : 0u);
+              mma2_bf16(tbase + dcol, dah, dbh, idesc, (s8 | j) ? 1u : 0u);
               mma2_bf16(tbase + dcol, dal, dbh, idesc, 1u);
               mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
-#endif
             }
             if (stage % P_CG == P_CG - 1) commit2(&bar_empty[stage / P_CG]);
             if (++stage == P_NST) { stage = 0; phase ^= 1; }
@@ -188,19 +173,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
           const uint32_t par = t & 1;
           long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? p.dbg + t * 16 : nullptr;
           if (dbg) dbg[0] = clock64();
-          mbar_wait_cl(&bar_h, par);      // both CTAs' h (hi/lo) of this step are in shared memory
+          mbar_wait_cl(&bar_h0, par);     // both CTAs' even K blocks of h (hi/lo) are in shared memory
           tc_fence_after();
           if (dbg) dbg[1] = clock64();
-          gemm(hHi, hLo, P_TC_R);
+          gemm(hHi, hLo, P_TC_R, true, &bar_h1, par);      // ... the odd ones by the time the second half starts
           commit2(&bar_r);
           if (dbg) dbg[2] = clock64();
-          gemm(hHi, hLo, P_TC_U);
+          gemm(hHi, hLo, P_TC_U, true, nullptr, 0);
           commit2(&bar_u);
           if (dbg) dbg[3] = clock64();
           mbar_wait_cl(&bar_rh, par);     // both CTAs' r*h written
           tc_fence_after();
           if (dbg) dbg[4] = clock64();
-          gemm(rHi, rLo, P_TC_C);
+          gemm(rHi, rLo, P_TC_C, false, nullptr, 0);
           commit2(&bar_c);
           if (dbg) { dbg[5] = clock64(); dbg[6] = w_full; dbg[7] = 0; w_full = 0; }
         }
@@ -222,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
     const float* st = S.scoresT + ((size_t)(m0 / TM) * STEPS) * TM + prow;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row_off = (uint32_t)(rl / 8) * A_SBO + (uint32_t)(rl % 8) * 16;
-    const uint32_t bar_h_leader = mapa_rank(smem_u32(&bar_h), 0), bar_rh_leader = mapa_rank(smem_u32(&bar_rh), 0);
+    const uint32_t bar_h0_leader = mapa_rank(smem_u32(&bar_h0), 0), bar_h1_leader = mapa_rank(smem_u32(&bar_h1), 0), bar_rh_leader = mapa_rank(smem_u32(&bar_rh), 0);
     float h[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) h[i] = 0.f;
@@ -234,7 +219,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
     }
     proxy_fence();
     __syncwarp();
-    if (lane == 0) { if (rank == 0) mbar_arrive(&bar_h); else arrive_cl_relaxed(bar_h_leader); }
+    if (lane == 0) {
+      if (rank == 0) { mbar_arrive(&bar_h0); mbar_arrive(&bar_h1); }
+      else { arrive_cl_relaxed(bar_h0_leader); arrive_cl_relaxed(bar_h1_leader); }
+    }
 
     for (int t = 0; t < STEPS; ++t) {
       const uint32_t par = t & 1;
@@ -272,12 +260,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
             uint4 hi, lo;
             split8(a[cur] + g * 8, hi, lo);
             uint32_t off = a_row_off + (uint32_t)((hc0 + ch * 16 + g * 8) / 8) * LBO;
-#if R4P_EXP != 3
             *reinterpret_cast<uint4*>(sRhi + off) = hi;
             *reinterpret_cast<uint4*>(sRlo + off) = lo;
-#else
-            if (hi.x == 0x12345 && lo.y == 0x777) *reinterpret_cast<uint4*>(sRhi + off) = hi;
-#endif
           }
         }
       }
@@ -344,6 +328,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
             *reinterpret_cast<uint4*>(sHhi + off) = hi;
             *reinterpret_cast<uint4*>(sHlo + off) = lo;
           }
+          if (ch == 1) {              // this thread's even K block of h' is complete: release the first half of the next r gate
+            proxy_fence();
+            __syncwarp();
+            if (lane == 0) { if (rank == 0) mbar_arrive(&bar_h0); else arrive_cl_relaxed(bar_h0_leader); }
+          }
         }
       }
 #undef R4P_LOADX
@@ -351,7 +340,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       proxy_fence();
       __syncwarp();
       if (dbg) dbg[14] = clock64();
-      if (lane == 0) { if (rank == 0) mbar_arrive(&bar_h); else arrive_cl_relaxed(bar_h_leader); }
+      if (lane == 0) { if (rank == 0) mbar_arrive(&bar_h1); else arrive_cl_relaxed(bar_h1_leader); }
     }
     if (valid) {
       float* o = S.out + (size_t)(m0 + prow) * p.out_ld + hc0;
@@ -372,10 +361,12 @@ inline void build_pair_image(const float* Wg, const float* Wc, uint8_t* img) {
     for (int mat = 0; mat < 3; ++mat)
       for (int kb = 0; kb < NKB; ++kb)
         for (int sp = 0; sp < 2; ++sp) {
+          // stage s8 of the r and u gates holds K block (s8 & 3) * 2 + (s8 >> 2): 0,2,4,6,1,3,5,7 (see gemm() in the kernel)
+          const int kbsrc = mat < 2 ? ((kb & 3) * 2 + (kb >> 2)) : kb;
           uint8_t* st = img + (size_t)rank * P_RANK_IMAGE_BYTES + (size_t)((mat * NKB + kb) * 2 + sp) * P_HALF_BYTES;
           for (int nl = 0; nl < P_NB; ++nl)
             for (int kk = 0; kk < KB; ++kk) {
-              const int k = kb * KB + kk, n = rank * P_NB + nl;
+              const int k = kbsrc * KB + kk, n = rank * P_NB + nl;
               float w = mat == 0 ? Wg[(size_t)k * 2 * HID + n] : (mat == 1 ? Wg[(size_t)k * 2 * HID + HID + n] : Wc[(size_t)k * HID + n]);
               uint16_t hi = host_bf16_bits(w);
               uint16_t v = sp == 0 ? hi : host_bf16_bits(w - host_bf16_val(hi));
