@@ -17,8 +17,9 @@ JSON keys beyond the base contract:
   env_only  the same rollout without the SGD pass.
   e2e       the reference-facing call with HOST buffers: README.md:14-21 loop, numpy actions in,
             numpy obs/mask/reward out, every copy inside the timed region.
-  roofline  the dominant kernel (k_augru_tc, the tcgen05 AUGRU recurrence) timed live with CUDA events on the
-            launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
+  roofline  the dominant kernel: the tcgen05 AUGRU recurrence -- k_augru_pair (2-CTA tcgen05.mma.cta_group::2) for the
+            observation passes, k_augru_tc for the multi-wave reward pass, one profile slot for both -- timed live
+            with CUDA events on the launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
             2*(256*512 + 256*256) against the measured bf16 GEMM peak.
   cpu_baseline  the oracle port (oracle/env_np.py + dien_np.py) on this box's host cores, bounded sample.
 """
@@ -320,7 +321,8 @@ def main():
         tp = os.path.join(ROOT, "profiles", "augru_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "k_augru_tc (AUGRU recurrence: tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators)",
+        roofline = {"kernel": "AUGRU recurrence, tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators: k_augru_pair "
+                              "(cta_group::2, observation passes) + k_augru_tc (reward pass)",
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
                     "peak_source": "%s bf16 GEMM, sustained (kernel timed inside a long step)" % peaks["source"],

@@ -275,7 +275,10 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   // The side stream (lowest priority) does the AUGRU-independent half of the feature vector: category attention +
   // dense tower.  It forks AFTER k_scores_tc and is fed after the AUGRU launch, so the AUGRU pairs (1 CTA per SM,
   // 128 SMs at 4096 rows) are resident first and the side kernels fill the remaining SMs instead of delaying them.
-  static const bool no_side = getenv("R4_NO_SIDE_STREAM") != nullptr;   // diagnostics: serialise for clean per-kernel times
+  // R4_NO_SIDE_STREAM / the per-kernel breakdown mode (r4_profile(2)) serialise everything on one stream: event pairs
+  // around a kernel on the low-priority side stream would time its wait for free SMs, not the kernel.
+  static const bool no_side_env = getenv("R4_NO_SIDE_STREAM") != nullptr;
+  const bool no_side = no_side_env || e->prof_mode == 2;
   static const bool side_early = getenv("R4_SIDE_EARLY") != nullptr;    // diagnostics: fork before k_query (old schedule)
   auto side_work = [&]() -> int {
     cudaStream_t ss = no_side ? st : e->side;
