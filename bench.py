@@ -261,7 +261,7 @@ def main():
 
     for _ in range(args.warmup):
         episode_device()
-    launches0 = eng.launch_count()
+    launches0 = eng.launch_count() + trainer.ops.launches
     eng.profile(1)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -270,7 +270,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     prof = eng.profile_read()
     eng.profile(0)
-    gpu_launches = eng.launch_count() - launches0
+    gpu_launches = eng.launch_count() + trainer.ops.launches - launches0   # env kernels + policy/learner kernels
     value = B * world * T * args.steps / (ms / 1e3)
     ms_env = timed(episode_env_only, args.steps)
     env_only = B * world * T * args.steps / (ms_env / 1e3)

@@ -824,11 +824,11 @@ int r4_policy_act(const float* params, const float* obs, const uint8_t* mask, in
   return R4_OK;
 }
 
-int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
-                   const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
-                   const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
-                   float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
-                   float* flat_grad, float* stats_accum, float stat_scale, void* stream) {
+static int policy_grad_impl(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                            const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                            const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                            float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                            float* flat_grad, float* stats_accum, float stat_scale, void* stream, bool reduce) {
   if (!params || !obs || !mask || !action || !old_logits || !adv || !target || !scratch || !flat_grad || n < 1 ||
       G < 1 || action_size < 2 || action_size > 512 || (mode == 0 && (!old_logp || !old_value)))
     return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: bad argument");
@@ -855,9 +855,20 @@ int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_
     r4ppo::k_policy_grad<false><<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
                                                                   old_value, adv, target, idx, n, partial, stat_partial);
   R4_PCHECK("k_policy_grad");
+  if (!reduce) return R4_OK;       // the caller folds the reduction into its optimiser kernel (r4_ppo_epoch)
   r4ppo::k_grad_reduce<<<(L.n + 255) / 256, 256, 0, S(stream)>>>(L.n, G, partial, flat_grad, stat_partial, stats_accum, stat_scale);
   R4_PCHECK("k_grad_reduce");
   return R4_OK;
+}
+
+int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                   const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                   const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                   float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                   float* flat_grad, float* stats_accum, float stat_scale, void* stream) {
+  return policy_grad_impl(mode, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, idx, n, action_size,
+                          clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv_n, scratch, G, flat_grad, stats_accum, stat_scale,
+                          stream, true);
 }
 
 int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
@@ -885,13 +896,21 @@ int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int
   const int G = std::max(1, std::min((mb + r4ppo::TS - 1) / r4ppo::TS, 148));
   const int np = r4ppo::make_layout(action_size).n;
   int steps = 0;
+  const bool fused = !(grad_clip > 0.f);      // global-norm clipping needs the reduced gradient first
+  if (!params || !m || !v || !flat_grad || !scratch) return fail(nullptr, R4_ERR_ARG, "r4_ppo_epoch: bad argument");
   for (int s = 0; s + mb <= n; s += mb, ++steps) {
-    int rc = r4_policy_grad(0, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, perm + s, mb,
-                            action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, 1.0f / mb, scratch, G, flat_grad,
-                            stats_accum, 1.0f / mb, stream);
+    int rc = policy_grad_impl(0, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, perm + s, mb,
+                              action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, 1.0f / mb, scratch, G, flat_grad,
+                              stats_accum, 1.0f / mb, stream, !fused);
     if (rc) return rc;
-    rc = r4_adam_step(params, flat_grad, m, v, np, step0 + steps + 1, lr, beta1, beta2, eps, 1.0f, grad_clip, norm_scratch, stream);
-    if (rc) return rc;
+    if (fused) {
+      r4ppo::k_reduce_adam<<<(np + 255) / 256, 256, 0, S(stream)>>>(np, G, scratch, flat_grad, scratch + (size_t)G * np, stats_accum,
+                                                                    1.0f / mb, params, m, v, step0 + steps + 1, lr, beta1, beta2, eps);
+      R4_PCHECK("k_reduce_adam");
+    } else {
+      rc = r4_adam_step(params, flat_grad, m, v, np, step0 + steps + 1, lr, beta1, beta2, eps, 1.0f, grad_clip, norm_scratch, stream);
+      if (rc) return rc;
+    }
   }
   return steps;
 }

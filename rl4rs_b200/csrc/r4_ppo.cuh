@@ -374,7 +374,19 @@ __global__ void k_grad_reduce(int n, int G, const float* __restrict__ partial, f
   }
 }
 
-// torch.optim.Adam (no weight decay, no amsgrad) with optional global-norm clipping (clip <= 0: off).
+// torch.optim.Adam (no weight decay, no amsgrad) on one parameter; shared by k_adam and k_reduce_adam so that the
+// fused and the two-kernel paths round identically.
+__device__ __forceinline__ void adam_update(float g, float& p, float& mi_io, float& vi_io, int step, float lr, float b1,
+                                            float b2, float eps) {
+  float mi = b1 * mi_io + (1.f - b1) * g;
+  float vi = b2 * vi_io + (1.f - b2) * g * g;
+  mi_io = mi; vi_io = vi;
+  float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+  p -= (lr / bc1) * (mi / denom);
+}
+
+// Adam with optional global-norm clipping (clip <= 0: off).
 // grad_scale multiplies the gradient first (1/world after a SUM all-reduce).  step is the 1-based count.
 __global__ void k_adam(int n, float* __restrict__ prm, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int step, float lr, float b1, float b2, float eps, float grad_scale,
@@ -387,12 +399,31 @@ __global__ void k_adam(int n, float* __restrict__ prm, const float* __restrict__
     float c = clip / (gn + 1e-6f);                       // torch clip_grad_norm_
     if (c < 1.f) g *= c;
   }
-  float mi = b1 * m[i] + (1.f - b1) * g;
-  float vi = b2 * v[i] + (1.f - b2) * g * g;
-  m[i] = mi; v[i] = vi;
-  float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
-  float denom = sqrtf(vi) / sqrtf(bc2) + eps;
-  prm[i] -= (lr / bc1) * (mi / denom);
+  float p = prm[i], mi = m[i], vi = v[i];
+  adam_update(g, p, mi, vi, step, lr, b1, b2, eps);
+  prm[i] = p; m[i] = mi; v[i] = vi;
+}
+
+// k_grad_reduce + k_adam (no clipping, grad_scale 1) in one launch: the single-GPU PPO epoch has nothing between them.
+__global__ void k_reduce_adam(int n, int G, const float* __restrict__ partial, float* __restrict__ flat,
+                              const float* __restrict__ stat_partial, float* __restrict__ stats_accum, float stat_scale,
+                              float* __restrict__ prm, float* __restrict__ m, float* __restrict__ v, int step, float lr,
+                              float b1, float b2, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float s = 0.f;
+    for (int c = 0; c < G; ++c) s += partial[(size_t)c * n + i];
+    flat[i] = s;
+    float g = s * 1.0f;
+    float p = prm[i], mi = m[i], vi = v[i];
+    adam_update(g, p, mi, vi, step, lr, b1, b2, eps);
+    prm[i] = p; m[i] = mi; v[i] = vi;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 5 && stats_accum) {
+    float s = 0.f;
+    for (int c = 0; c < G; ++c) s += stat_partial[c * 5 + threadIdx.x];
+    stats_accum[threadIdx.x] += s * stat_scale;
+  }
 }
 
 __global__ void k_sumsq(int n, const float* __restrict__ x, float* __restrict__ out) {

@@ -46,6 +46,7 @@ class KernelOps(object):
         self.scratch = z(148 * (n_params + 5))
         self.step = 0
         self.counter = 0
+        self.launches = 0                # kernels launched through this object (bench.py: gpu_launches)
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -60,6 +61,7 @@ class KernelOps(object):
                                     _p(action_i32), _p(logp), _p(value), _p(logits), self._stream())
         self._check(rc, "r4_policy_act")
         self.counter += n
+        self.launches += 1
 
     def policy_grad(self, mode, flat, data, idx, idx_offset, n, hp, inv_n, stat_scale, G=None):
         obs, mask, act, logp, logits, val, adv, target = data
@@ -69,6 +71,7 @@ class KernelOps(object):
                                      hp["clip"], hp["vf_clip"], hp["vf_coeff"], hp["kl_coeff"], hp["ent_coeff"], inv_n,
                                      _p(self.scratch), G, _p(self.grad), _p(self.stats), stat_scale, self._stream())
         self._check(rc, "r4_policy_grad")
+        self.launches += 2               # k_policy_grad + k_grad_reduce
 
     def ppo_epoch(self, flat, data, perm, n, mb, hp, lr, clip):
         """All minibatch steps of one SGD epoch in ONE library call (single-GPU learner)."""
@@ -80,6 +83,7 @@ class KernelOps(object):
         if rc < 0:
             self._check(rc, "r4_ppo_epoch")
         self.step += rc
+        self.launches += rc * (4 if clip else 2)   # k_policy_grad + k_reduce_adam, or + k_grad_reduce, k_sumsq, k_adam
         return rc
 
     def adam(self, flat, lr, grad_scale, clip):
@@ -87,6 +91,7 @@ class KernelOps(object):
         rc = self.lib.r4_adam_step(_p(flat), _p(self.grad), _p(self.m), _p(self.v), self.n, self.step, lr, 0.9, 0.999,
                                    1e-8, grad_scale, float(clip or 0.0), _p(self.norm), self._stream())
         self._check(rc, "r4_adam_step")
+        self.launches += 2 if clip else 1
 
 PPO_DEFAULTS = {"gamma": 1.0, "lambda": 1.0, "kl_coeff": 0.2, "sgd_minibatch_size": 256, "num_sgd_iter": 1,
                 "lr": 1e-4, "vf_loss_coeff": 0.5, "clip_param": 0.3, "vf_clip_param": 500.0, "kl_target": 0.01,
