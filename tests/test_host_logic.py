@@ -98,3 +98,36 @@ def test_gym_shim_registry():
     assert "SlateRecEnv-v0" in gymshim._REGISTRY and "SeqSlateRecEnv-v0" in gymshim._REGISTRY
     d = gymshim.spaces.Dict({"a": gymshim.spaces.Box(0, 1, shape=(3,)), "b": gymshim.spaces.Discrete(4)})
     assert d.contains(d.sample())
+
+
+def test_vector_env_wrapper_semantics():
+    """MyVectorEnvWrapper (rllib_vector_env.py:9-69): reset_at(0) resets the whole batch, reset_at(i>0) serves the
+    cached reset, vector_step forwards np.array(actions), get_unwrapped repeats the one env."""
+    from rl4rs_b200.utils.rllib_vector_env import MyVectorEnvWrapper
+
+    class FakeEnv(object):
+        observation_space, action_space = "obs_space", "act_space"
+
+        def __init__(self):
+            self.resets, self.last = 0, None
+
+        def reset(self):
+            self.resets += 1
+            return [{"obs": (self.resets, i)} for i in range(4)]
+
+        def step(self, a):
+            self.last = a
+            return ["o"] * 4, [0.0] * 4, [0] * 4, [{}] * 4
+
+        def render(self):
+            return "rendered"
+
+    env = FakeEnv()
+    v = MyVectorEnvWrapper(env, 4)
+    assert v.num_envs == 4 and v.observation_space == "obs_space" and v.action_space == "act_space"
+    assert v.vector_reset()[2] == {"obs": (1, 2)} and env.resets == 1
+    assert v.reset_at(0) == {"obs": (2, 0)} and env.resets == 2
+    assert v.reset_at(3) == {"obs": (2, 3)} and env.resets == 2          # served from the cache of reset_at(0)
+    obs, rew, done, info = v.vector_step([1, 2, 3, 4])
+    assert isinstance(env.last, np.ndarray) and env.last.tolist() == [1, 2, 3, 4] and len(obs) == 4
+    assert v.get_unwrapped() == [env] * 4 and v.try_render_at(1) == "rendered"
