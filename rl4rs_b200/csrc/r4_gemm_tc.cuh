@@ -288,9 +288,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
       long long c1 = probe ? clock64() : 0;
       tc_fence_after();
       // Sequence mode, aligned tile: its 128 rows are 128 consecutive sequences of ONE step, so 16 output columns are
-      // one contiguous 8 KB block of the lane-major layout.  Stage them in shared memory and let the bulk-copy
-      // engine write them: per-thread stores of this epilogue (one 128-byte line per warp instruction, a few in
-      // flight per warp) ran at ~0.5 TB/s chip-wide and were the whole kernel time (tools/gemm_probe.cu).
+      // one contiguous 8 KB block of the lane-major layout: stage them in shared memory ([column][row], conflict-free)
+      // and let the bulk-copy engine write the block -- one instruction by one thread instead of 16 x 128-byte warp
+      // stores per warp, and no store traffic in the epilogue warps' instruction stream.
       const bool blk = p.tm_ns > 0 && (p.tm_ns % G_BM) == 0 && (p.cr_base % G_BM) == 0 && m0 + G_BM <= p.M;
       for (int c = 0; c < bn; c += 16) {
         float a[16];
