@@ -3,7 +3,12 @@
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
 #ifdef PAIR
 #include "../rl4rs_b200/csrc/r4_augru_pair.cuh"
+#ifdef PAIRT
+#include "experiments/r4_augru_pair_templated.cuh"
+#define KERNEL k_augru_pair_t
+#else
 #define KERNEL k_augru_pair
+#endif
 #define KSMEM P_SMEM_BYTES
 #define KTHREADS NTHREADS
 #define GRIDX(t) (2 * (t))

@@ -20,59 +20,9 @@
 // Warp roles: 0-7 epilogue (TMEM lane quarter q = warp & 3, column half = warp >> 2; thread = one row x 64
 // hidden columns), 8 = MMA issuer (leader) / ring relay (peer), 9 = TMA producer, 10-11 idle.
 #pragma once
-#include "r4_augru_tc.cuh"
+#include "../../rl4rs_b200/csrc/r4_augru_pair.cuh"   // helpers (mma2_bf16, commit2, mbar_wait_cl, ...) + constants
 
 namespace r4tc {
-
-constexpr int P_RC = 64;                              // rows per CTA
-constexpr int P_NB = 128;                             // weight columns (B rows) per CTA
-constexpr int P_HALF_BYTES = P_NB * KB * 2;           // 8192: one split of one 32-deep K block of the CTA's 128 columns
-constexpr int P_STAGE_BYTES = 2 * P_HALF_BYTES;       // 16384: ring stage = [hi | lo] of one K block (6 MMAs, 384 cycles)
-constexpr int P_STAGES_PER_STEP = 3 * NKB;            // 24
-constexpr int P_NST = 6;
-#ifndef R4P_COMMIT_GROUP
-#define R4P_COMMIT_GROUP 1
-#endif
-constexpr int P_CG = R4P_COMMIT_GROUP;                // ring stages released per tcgen05.commit (must divide P_NST and 24)
-constexpr int P_A_BYTES = P_RC * HID * 2;             // 32768 per split
-constexpr int P_SMEM_BYTES = 4 * P_A_BYTES + P_NST * P_STAGE_BYTES + 128;
-constexpr int P_RANK_IMAGE_BYTES = P_STAGES_PER_STEP * P_STAGE_BYTES; // 393216 per CTA rank
-constexpr int P_TC_R = 0, P_TC_U = 128, P_TC_C = 256;                  // TMEM column bases of the gates
-
-__device__ __forceinline__ void mma2_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-               :: "r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
-}
-// completion of all earlier MMAs of this thread -> one arrival on the barrier at this offset in BOTH CTAs
-__device__ __forceinline__ void commit2(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-// acquire.cluster try_wait is expensive (a producer loop built on it issued one stage per ~450 cycles); it is used
-// only for the two per-step barriers the leader's MMA thread waits on, which collect remote relaxed arrivals.
-__device__ __forceinline__ void mbar_wait_cl(uint64_t* bar, uint32_t parity) {
-  asm volatile("{\n\t.reg .pred p;\n\tWAIT_LOOP:\n\t"
-               "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
-               "@p bra DONE;\n\tbra WAIT_LOOP;\n\tDONE:\n\t}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ uint32_t mapa_rank(uint32_t laddr, uint32_t rank) {
-  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank)); return r;
-}
-__device__ __forceinline__ void arrive_cl(uint32_t caddr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(caddr) : "memory");
-}
-// A remote arrive with .release.cluster blocks its thread ~320 cycles (tools/pair_probe.cu); .relaxed costs ~5.  The
-// relaxed form is enough where the data being published lives in the ARRIVING CTA's own shared memory and has
-// already been made visible to the async proxy (TMA completion, or fence.proxy.async by every writer + __syncwarp):
-// the consumer is this SM's tensor core, started by the leader only after it has observed the arrival.
-__device__ __forceinline__ void arrive_cl_relaxed(uint32_t caddr) {
-  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(caddr) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 
 // Descriptor of a SWIZZLE_NONE K-major operand split into its two words: `lo` carries the start address (>> 4, 14 bits)
 // and LBO, `hi` carries SBO and the version bit.  Advancing the operand by `bytes` is `lo + (bytes >> 4)` (shared
@@ -90,8 +40,14 @@ __device__ __forceinline__ uint64_t desc_of(uint32_t lo, uint32_t hi) { return (
 // The r and u gates walk the K blocks of h in the order 0,2,4,6,1,3,5,7 -- the order in which the epilogue finishes
 // them -- and the r gate waits for `half_bar` (the odd blocks) before its second half; build_pair_image lays the
 // weights out in the same order.  No tcgen05 fence per stage: the weights come from TMA.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .b32 r;\n\t.reg .pred p;\n\telect.sync r|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+
 template <int GATE>
-__device__ __forceinline__ void issue_gate(uint32_t tbase, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo, uint64_t* bar_full,
+__device__ __forceinline__ void issue_gate(uint32_t leader, uint32_t tbase, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo, uint64_t* bar_full,
                                            uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par) {
   constexpr uint32_t idesc = make_idesc(TM, HID);
   constexpr uint32_t dcol = GATE == 0 ? P_TC_R : (GATE == 1 ? P_TC_U : P_TC_C);
@@ -104,6 +60,7 @@ __device__ __forceinline__ void issue_gate(uint32_t tbase, uint32_t aHi_lo, uint
     const int kb = GATE < 2 ? ((s8 & 3) * 2 + (s8 >> 2)) : s8;
     if (GATE == 0 && s8 == NKB / 2) { mbar_wait_cl(half_bar, half_par); tc_fence_after(); }
     mbar_wait(&bar_full[stage], par);
+    if (leader) {
 #pragma unroll
     for (int j = 0; j < KB / 16; ++j) {
       const uint32_t bo = (uint32_t)(stage * P_STAGE_BYTES + j * 2 * LBO) >> 4;
@@ -115,11 +72,13 @@ __device__ __forceinline__ void issue_gate(uint32_t tbase, uint32_t aHi_lo, uint
       mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
     }
     commit2(&bar_empty[stage]);
+    }
+    __syncwarp();
   }
 }
 
 // Wimg of a sequence here = [rank 2][24 stages][hi 8 KB | lo 8 KB] (build_pair_image), everything else as AugruTcParams.
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru_pair(AugruTcParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru_pair_t(AugruTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h0, bar_h1, bar_rh, bar_r, bar_u, bar_c;
   __shared__ uint32_t tmem_base_s;
@@ -152,7 +111,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   const uint32_t tbase = tmem_base_s;
 
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");   // 4 control warps x 80 + 8 epilogue warps x 208: the increase (256 x 40) must fit in what the decrease frees (128 x 88)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 4 control warps x 80 + 8 epilogue warps x 208: the increase (256 x 40) must fit in what the decrease frees (128 x 88)
     if (warp == 9) {
       // ===== TMA producer: this CTA's half of the 24-stage weight stream of a step, 64 times =====
       if (lane == 0) {
@@ -180,14 +139,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         }
       }
     } else if (warp == 8) {
-      // ===== MMA issuer (leader CTA) =====
-      if (lane == 0) {
+      // ===== MMA issuer (leader CTA): the whole warp walks the loop in uniform control flow, ONE lane elected once issues
+      // (tools/experiments/issue_loop_sass.cu: back-to-back UTCHMMA, no ELECT / BRA.U.ANY wrapper per instruction) =====
+      const uint32_t leader = elect_one();
+      {
         const uint32_t hHi = smem_u32(sHhi), hLo = smem_u32(sHlo), rHi = smem_u32(sRhi), rLo = smem_u32(sRlo), bBase = smem_u32(sB);
         uint32_t hHi_d = desc_lo(hHi, LBO), hLo_d = desc_lo(hLo, LBO), rHi_d = desc_lo(rHi, LBO), rLo_d = desc_lo(rLo, LBO),
                  b_d = desc_lo(bBase, LBO);
         for (int t = 0; t < STEPS; ++t) {
           const uint32_t par = t & 1;
-          long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0) ? p.dbg + t * 16 : nullptr;
+          long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && leader) ? p.dbg + t * 16 : nullptr;
           if (dbg) dbg[0] = clock64();
           // keep the 144 descriptors of a step OUT of the loop-invariant set: hoisted, they live in local memory (this warp
           // has 80 registers) and every MMA pays a local load; rebuilt from these five words each costs one add
@@ -195,23 +156,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
           mbar_wait_cl(&bar_h0, par);     // both CTAs' even K blocks of h (hi/lo) are in shared memory
           tc_fence_after();
           if (dbg) dbg[1] = clock64();
-          issue_gate<0>(tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par);   // ... the odd ones by its second half
-          commit2(&bar_r);
+          issue_gate<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par);   // ... the odd ones by its second half
+          if (leader) commit2(&bar_r);
           if (dbg) dbg[2] = clock64();
-          issue_gate<1>(tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0);
-          commit2(&bar_u);
+          issue_gate<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0);
+          if (leader) commit2(&bar_u);
           if (dbg) dbg[3] = clock64();
           mbar_wait_cl(&bar_rh, par);     // both CTAs' r*h written
           tc_fence_after();
           if (dbg) dbg[4] = clock64();
-          issue_gate<2>(tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0);
-          commit2(&bar_c);
+          issue_gate<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0);
+          if (leader) commit2(&bar_c);
           if (dbg) { dbg[5] = clock64(); dbg[6] = 0; dbg[7] = 0; }
         }
       }
     }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
     // ===== epilogue warps: thread = (row of this CTA, 64 hidden columns) =====
     const int q = warp & 3, sub = warp >> 2;
     const int rl = (q & 1) * 32 + lane;                    // row inside this CTA
@@ -371,27 +332,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   __syncthreads();
   cluster_sync_all();                         // neither CTA frees TMEM / exits while the pair's MMAs or arrivals are in flight
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512));
-}
-
-// host: fp32 recurrent weights -> [rank 2][mat r,u,c][8 K blocks][hi, lo] stages of 128 columns x 32 K (8 KB).
-// Wg: [256][512] rows = h index, columns [r | u];  Wc: [256][256].
-inline void build_pair_image(const float* Wg, const float* Wc, uint8_t* img) {
-  for (int rank = 0; rank < 2; ++rank)
-    for (int mat = 0; mat < 3; ++mat)
-      for (int kb = 0; kb < NKB; ++kb)
-        for (int sp = 0; sp < 2; ++sp) {
-          // stage s8 of the r and u gates holds K block (s8 & 3) * 2 + (s8 >> 2): 0,2,4,6,1,3,5,7 (see gemm() in the kernel)
-          const int kbsrc = mat < 2 ? ((kb & 3) * 2 + (kb >> 2)) : kb;
-          uint8_t* st = img + (size_t)rank * P_RANK_IMAGE_BYTES + (size_t)((mat * NKB + kb) * 2 + sp) * P_HALF_BYTES;
-          for (int nl = 0; nl < P_NB; ++nl)
-            for (int kk = 0; kk < KB; ++kk) {
-              const int k = kbsrc * KB + kk, n = rank * P_NB + nl;
-              float w = mat == 0 ? Wg[(size_t)k * 2 * HID + n] : (mat == 1 ? Wg[(size_t)k * 2 * HID + HID + n] : Wc[(size_t)k * HID + n]);
-              uint16_t hi = host_bf16_bits(w);
-              uint16_t v = sp == 0 ? hi : host_bf16_bits(w - host_bf16_val(hi));
-              memcpy(st + (nl / 8) * B_SBO + (kk / 8) * LBO + (nl % 8) * 16 + (kk % 8) * 2, &v, 2);
-            }
-        }
 }
 
 }  // namespace r4tc
