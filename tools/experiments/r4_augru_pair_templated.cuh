@@ -22,6 +22,10 @@
 #pragma once
 #include "../../rl4rs_b200/csrc/r4_augru_pair.cuh"   // helpers (mma2_bf16, commit2, mbar_wait_cl, ...) + constants
 
+#ifndef R4PT_DEEPX
+#define R4PT_DEEPX 0     // 1: load all 64 inputs of a gate phase BEFORE waiting for the gate (next-round experiment)
+#endif
+
 namespace r4tc {
 
 // Descriptor of a SWIZZLE_NONE K-major operand split into its two words: `lo` carries the start address (>> 4, 14 bits)
@@ -111,7 +115,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   const uint32_t tbase = tmem_base_s;
 
   if (warp >= 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 4 control warps x 80 + 8 epilogue warps x 208: the increase (256 x 40) must fit in what the decrease frees (128 x 88)
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // frees 128 x 128 registers = what 232 for the 256 epilogue threads takes
     if (warp == 9) {
       // ===== TMA producer: this CTA's half of the 24-stage weight stream of a step, 64 times =====
       if (lane == 0) {
@@ -221,8 +225,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
 #define R4P_LOADX(dst, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg(xs + (size_t)((colbase) + j) * TM)
       // ---- phase R (overlaps the u MMAs): r*h -> its own A operand ----
       {
+#if R4PT_DEEPX
+        float x[4][16], a[2][16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) { R4P_LOADX(x[c4], hc0 + c4 * 16); }
+#else
         float x[2][16], a[2][16];
         R4P_LOADX(x[0], hc0);
+#endif
         if (dbg) dbg[8] = clock64();
         mbar_wait(&bar_r, par);
         if (dbg) dbg[9] = clock64();
@@ -232,9 +242,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         for (int ch = 0; ch < 4; ++ch) {
           const int cur = ch & 1, nxt = cur ^ 1;
           tmem_wait_ld();
+#if R4PT_DEEPX
+          if (ch < 3) tmem_ld16(tlane + P_TC_R + tcol + (ch + 1) * 16, a[nxt]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[ch][j]) * h[ch * 16 + j];
+#else
           if (ch < 3) { R4P_LOADX(x[nxt], hc0 + (ch + 1) * 16); tmem_ld16(tlane + P_TC_R + tcol + (ch + 1) * 16, a[nxt]); }
 #pragma unroll
           for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[cur][j]) * h[ch * 16 + j];
+#endif
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint4 hi, lo;
@@ -252,8 +268,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       if (dbg) dbg[10] = clock64();
       // ---- phase U (overlaps the c MMAs): E = 1 + exp(-(acc_u + Xu)) back into TMEM ----
       {
+#if R4PT_DEEPX
+        float x[4][16], a[2][16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) { R4P_LOADX(x[c4], HID + hc0 + c4 * 16); }
+#else
         float x[2][16], a[2][16];
         R4P_LOADX(x[0], HID + hc0);
+#endif
         mbar_wait(&bar_u, par);
         if (dbg) dbg[11] = clock64();
         tc_fence_after();
@@ -262,10 +284,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         for (int ch = 0; ch < 4; ++ch) {
           const int cur = ch & 1, nxt = cur ^ 1;
           tmem_wait_ld();
+#if R4PT_DEEPX
+          if (ch < 3) tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, a[nxt]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            a[cur][j] = 1.0f + ex2_approx(fminf(-1.4426950408889634f * (a[cur][j] + x[ch][j]), 60.0f));
+#else
           if (ch < 3) { R4P_LOADX(x[nxt], HID + hc0 + (ch + 1) * 16); tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, a[nxt]); }
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             a[cur][j] = 1.0f + ex2_approx(fminf(-1.4426950408889634f * (a[cur][j] + x[cur][j]), 60.0f));
+#endif
           tmem_st16(tlane + P_TC_U + tcol + ch * 16, a[cur]);
         }
         tmem_wait_st();
@@ -273,8 +302,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       if (dbg) dbg[12] = clock64();
       // ---- phase C: c = tanh(acc_c + Xc) = 1 - 2/(1 + F), u = 1/E with ONE reciprocal of E*F ----
       {
+#if R4PT_DEEPX
+        float x[4][16], a[2][16], u[2][16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) { R4P_LOADX(x[c4], 2 * HID + hc0 + c4 * 16); }
+#else
         float x[2][16], a[2][16], u[2][16];
         R4P_LOADX(x[0], 2 * HID + hc0);
+#endif
         mbar_wait(&bar_c, par);
         if (dbg) dbg[13] = clock64();
         tc_fence_after();
@@ -285,13 +320,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
           const int cur = ch & 1, nxt = cur ^ 1;
           tmem_wait_ld();
           if (ch < 3) {
+#if !R4PT_DEEPX
             R4P_LOADX(x[nxt], 2 * HID + hc0 + (ch + 1) * 16);
+#endif
             tmem_ld16(tlane + P_TC_C + tcol + (ch + 1) * 16, a[nxt]);
             tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, u[nxt]);
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float F = 1.0f + ex2_approx(fminf(2.8853900817779268f * (a[cur][j] + x[cur][j]), 60.0f));
+            const float F = 1.0f + ex2_approx(fminf(2.8853900817779268f * (a[cur][j] + x[R4PT_DEEPX ? ch : cur][j]), 60.0f));
             const float E = u[cur][j];
             const float rc = rcp_approx(E * F);                      // E, F <= 1 + 2^60: the product is finite
             const float c = fmaf(-2.0f, rc * E, 1.0f);               // tanh
