@@ -145,6 +145,11 @@ int r4_profile(r4_env* env, int mode);
 int r4_profile_read(r4_env* env, int slot, const char** name, double* ms, int64_t* launches, double* work);
 /* ABI version of the build */
 int r4_abi_version(void);
+/* Which AUGRU kernel an observation / reward pass of `ctas` = 2 x ceil(rows / 128) tile-sequences runs on a device
+ * with `sms` multiprocessors: 1 = k_augru_tc (one CTA per tile), 2 = k_augru_pair (2-CTA tcgen05.mma.cta_group::2).
+ * Pure host arithmetic, exposed so the choice is testable and so a caller can predict the rounding regime of a launch
+ * (the two kernels agree to the parity tolerance, not bit for bit).  No reference counterpart. */
+int r4_augru_kernel_for(int ctas, int sms);
 
 /* ---- policy + learner (K12): MyMaskActionsModel (rllib_mask_model.py:41-62) and the RLlib PPO / A2C losses ----
  * Stateless: every pointer is caller-owned DEVICE memory.  Flat parameter layout:

@@ -49,6 +49,7 @@ EXPORTS = {
     "r4_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "r4_abi_version": (C.c_int, []),
+    "r4_augru_kernel_for": (C.c_int, [C.c_int, C.c_int]),
     "r4_policy_num_params": (C.c_int, [C.c_int]),
     "r4_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

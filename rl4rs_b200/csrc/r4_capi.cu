@@ -229,12 +229,15 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
 // SMs idle (a 4096-row observation pass: 64 tiles on 148 SMs) and loses on multi-wave launches (the reward pass,
 // batch x 9 rows).  Measured per wave: pair 0.75 ms, single 1.13 ms (tools/augru_probe.cu) -> compare 2*waves vs 3*waves.
 // R4_AUGRU_SINGLE=1 / R4_AUGRU_PAIR=1 force one kernel (A/B runs).
+static bool augru_rule_single(int ctas, int sms) {
+  const int w_single = (ctas + sms - 1) / sms, w_pair = (ctas + sms / 2 - 1) / (sms / 2);
+  return 3 * w_single <= 2 * w_pair;
+}
 static bool augru_use_single(int ctas) {
   static const int force = getenv("R4_AUGRU_SINGLE") ? 1 : (getenv("R4_AUGRU_PAIR") ? 2 : 0);
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   if (force) return force == 1;
-  const int w_single = (ctas + sms - 1) / sms, w_pair = (ctas + sms / 2 - 1) / (sms / 2);
-  return 3 * w_single <= 2 * w_pair;
+  return augru_rule_single(ctas, sms);
 }
 
 // One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
@@ -762,6 +765,8 @@ int r4_nearest_neighbor(r4_env* e, const void* action, int action_is_f64, int n,
 int r4_cur_steps(const r4_env* e) { return e ? e->cur_steps : -1; }
 const int32_t* r4_prev_actions(const r4_env* e) { return e ? e->prev_actions : nullptr; }
 int64_t r4_launch_count(const r4_env* e) { return e ? e->launches : 0; }
+
+int r4_augru_kernel_for(int ctas, int sms) { return (ctas < 1 || sms < 2) ? 0 : (augru_rule_single(ctas, sms) ? 1 : 2); }
 
 int r4_profile(r4_env* e, int mode) {
   if (!e || mode < 0 || mode > 2) return fail(e, R4_ERR_ARG, "r4_profile: mode must be 0, 1 or 2");

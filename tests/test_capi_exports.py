@@ -63,3 +63,19 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(d, f)).read()
                 assert not pat.search(src), os.path.join(d, f)
+
+
+def test_augru_kernel_choice_rule():
+    """r4_augru_kernel_for: the 2-CTA pair kernel (2) exactly when the one-CTA kernel (1) would leave SMs idle.
+    B200 (148 SMs): a 4096-row observation pass = 64 tile-sequences -> pair; the 36 864-row reward pass = 576 ->
+    one-CTA kernel (4 waves against 8 pair waves); 8192-row passes = 128 -> one-CTA (1 wave against 2)."""
+    from rl4rs_b200 import _capi
+    lib = _capi.load_library()
+    f = lib.r4_augru_kernel_for
+    assert f(64, 148) == 2 and f(2, 148) == 2 and f(74, 148) == 2
+    assert f(576, 148) == 1 and f(128, 148) == 1 and f(148, 148) == 1
+    assert f(75, 148) == 1                       # 2 pair waves (1.5 units) against 1 single wave (1.13)
+    assert f(0, 148) == 0 and f(64, 1) == 0      # bad arguments
+    for ctas in range(1, 1200, 7):               # never picks the slower one under the measured 2 : 3 wave-time ratio
+        ws, wp = -(-ctas // 148), -(-ctas // 74)
+        assert f(ctas, 148) == (1 if 3 * ws <= 2 * wp else 2)
