@@ -150,6 +150,14 @@ int r4_abi_version(void);
  * Pure host arithmetic, exposed so the choice is testable and so a caller can predict the rounding regime of a launch
  * (the two kernels agree to the parity tolerance, not bit for bit).  No reference counterpart. */
 int r4_augru_kernel_for(int ctas, int sms);
+/* Process-wide kernel-choice overrides for parity tests and A/B timing (no reference counterpart):
+ *   "augru_kernel"     0 = by r4_augru_kernel_for (default), 1 = always k_augru_tc, 2 = always the 2-CTA pair kernel
+ *   "augru_pair_impl"  which pair kernel: 1 = k_augru_pair2 as built (default), 2..4 = its other template variants
+ *                      (<RELAY,TMAP> = <0,1> <1,0> <0,0>)
+ *   "augru_cost_single" / "augru_cost_pair"  the per-wave cost ratio r4_augru_kernel_for compares (positive ints)
+ * The environment variables R4_AUGRU_SINGLE / R4_AUGRU_PAIR / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE give the initial
+ * values.  Returns 0, or R4_ERR_ARG for an unknown key / out-of-range value. */
+int r4_set_option(const char* key, int value);
 
 /* ---- policy + learner (K12): MyMaskActionsModel (rllib_mask_model.py:41-62) and the RLlib PPO / A2C losses ----
  * Stateless: every pointer is caller-owned DEVICE memory.  Flat parameter layout:

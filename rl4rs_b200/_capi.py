@@ -50,6 +50,7 @@ EXPORTS = {
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "r4_abi_version": (C.c_int, []),
     "r4_augru_kernel_for": (C.c_int, [C.c_int, C.c_int]),
+    "r4_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "r4_policy_num_params": (C.c_int, [C.c_int]),
     "r4_policy_act": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -90,3 +91,9 @@ def check(lib, handle, rc, what):
     if rc != 0:
         msg = lib.r4_last_error(handle)
         raise R4Error("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def set_option(key, value):
+    """r4_set_option: process-wide kernel-choice override (parity tests / A-B timing)."""
+    lib = load_library()
+    check(lib, None, lib.r4_set_option(key.encode(), int(value)), "r4_set_option(%s)" % key)

@@ -1,0 +1,417 @@
+// r4_augru_pair2.cuh -- second generation of the 2-CTA AUGRU recurrence (deepctr VecAttGRUCell, nets/utils.py:123-124).
+// Same arithmetic, TMEM / shared-memory layout and weight image as k_augru_pair (r4_augru_pair.cuh); what changed is
+// everything around the tensor pipe, each item answering a measurement of round 1:
+//   * issue loop: the whole MMA warp walks the step in uniform control flow, ONE lane elected once (elect.sync) issues,
+//     ring stage / mbarrier parity / operand offsets are compile-time constants (a step = 24 ring uses = 4 revolutions
+//     of the 6 stages, so they repeat every step).  Round 1: ~100 SASS instructions of descriptor arithmetic + an
+//     ELECT/BRA.U.ANY wrapper per MMA paced the pair MMAs at ~105 cycles; this form issues at 52-65.
+//   * rolling input prefetch: the epilogue keeps the inputs of the NEXT gate phase in registers (x[4][16]); a chunk is
+//     reloaded with the next phase's columns the moment it has been consumed, so every L2 load has a whole phase
+//     (~2 k cycles) to land.  Round 1: a 1-deep pipeline over 16-column chunks left each phase (R 5.3 k, U 4.8 k,
+//     C 5.5 k cycles) bound by L2 latency, and the phases run back to back on the same 8 warps.
+//   * hand-over with release semantics (RELAY = 1, default): the peer's epilogue warps arrive on a barrier in their OWN
+//     CTA (cta scope, cheap); one relay lane per barrier (warps 10 / 11 of the peer, idle otherwise) forwards each
+//     completed phase to the leader with mbarrier.arrive.release.cluster.  The ~320-cycle cost of a cluster-scope
+//     release is paid by the relay lane, not by 8 epilogue warps, and the chain  st.shared -> fence.proxy.async ->
+//     arrive(release.cta) -> wait(acquire.cta) -> arrive(release.cluster) -> wait(acquire.cluster) -> tcgen05.mma
+//     is a happens-before chain in the PTX memory model (round-1 advisor finding: a relaxed remote arrive is not).
+//     RELAY = 0 keeps the relaxed direct arrive as an opt-in fast path (-DR4P2_RELAY=0).
+//   * weight ring by tensor-map TMA (TMAP = 1, default): both CTAs issue cp.async.bulk.tensor.2d.cta_group::2 for
+//     their own half of the stage with the LEADER's "full" barrier as the completion target, the leader's producer
+//     posts one expect_tx for both halves.  No relay thread, no remote arrive: the transaction count is the signal.
+//     The image is viewed as a 2-D tensor of 1 KB rows, a stage is a 256 x 16 box of u32 (16 KB, dense).
+#pragma once
+#include <cuda.h>
+#include "r4_augru_pair.cuh"
+
+#ifndef R4P2_RELAY
+#define R4P2_RELAY 1
+#endif
+#ifndef R4P2_TMAP
+#define R4P2_TMAP 1
+#endif
+
+namespace r4tc {
+
+struct AugruPairParams {
+  AugruTcParams b;
+  CUtensorMap tmap[2];        // per sequence: the pair weight image as [rows of 1 KB][256 x u32] (TMAP variants only)
+};
+
+// Descriptor of a SWIZZLE_NONE K-major operand split into its two words: `lo` carries the start address (>> 4, 14 bits)
+// and LBO, `hi` carries SBO and the version bit.  Advancing the operand by `bytes` is `lo + (bytes >> 4)` (shared
+// memory is < 256 KB, the address field cannot carry out), so a descriptor costs ONE add in the issue loop.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr >> 4) & 0x3fffu) | ((lbo >> 4) << 16); }
+__device__ __forceinline__ constexpr uint32_t desc_hi(uint32_t sbo) { return ((sbo >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ uint64_t desc_of(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .b32 r;\n\t.reg .pred p;\n\telect.sync r|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred;
+}
+
+// this CTA's 16 KB box of the weight image -> own shared memory, completion bytes -> the barrier at `mbar_cluster`
+// (a shared::cluster address: the leader's "full" barrier for both CTAs of the pair)
+__device__ __forceinline__ void tma_box_cg2(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t mbar_cluster) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar_cluster) : "memory");
+}
+
+constexpr int P2_TM_ROW_BYTES = 1024;                             // tensor-map row = 256 x u32
+constexpr int P2_TM_BOX_ROWS = P_STAGE_BYTES / P2_TM_ROW_BYTES;   // 16 rows per ring stage
+
+// One gate of one step: 8 ring stages x 2 K16 slices x (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo).  The r and u gates walk
+// the K blocks of h in the order 0,2,4,6,1,3,5,7 -- the order in which the epilogue finishes them -- and the r gate
+// waits for `half_bar` (the odd blocks) before its second half; build_pair_image lays the weights out in the same order.
+// No tcgen05 fence per stage: the weights come from TMA.
+template <int GATE>
+__device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo,
+                                            uint64_t* bar_full, uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par) {
+  constexpr uint32_t idesc = make_idesc(TM, HID);
+  constexpr uint32_t dcol = GATE == 0 ? P_TC_R : (GATE == 1 ? P_TC_U : P_TC_C);
+  constexpr uint32_t a_hi = desc_hi(A_SBO), b_hi = desc_hi(B_SBO);
+#pragma unroll
+  for (int s8 = 0; s8 < NKB; ++s8) {
+    const int u = GATE * NKB + s8;
+    const int stage = u % P_NST;
+    const uint32_t par = (uint32_t)((u / P_NST) & 1);
+    const int kb = GATE < 2 ? ((s8 & 3) * 2 + (s8 >> 2)) : s8;
+    if (GATE == 0 && s8 == NKB / 2) { mbar_wait_cl(half_bar, half_par); tc_fence_after(); }
+    mbar_wait(&bar_full[stage], par);
+    if (leader) {
+#pragma unroll
+      for (int j = 0; j < KB / 16; ++j) {
+        const uint32_t bo = (uint32_t)(stage * P_STAGE_BYTES + j * 2 * LBO) >> 4;
+        const uint32_t ao = (uint32_t)((kb * (KB / 16) + j) * 2 * LBO) >> 4;
+        const uint64_t dbh = desc_of(b_lo + bo, b_hi), dbl = desc_of(b_lo + bo + (P_HALF_BYTES >> 4), b_hi);
+        const uint64_t dah = desc_of(aHi_lo + ao, a_hi), dal = desc_of(aLo_lo + ao, a_hi);
+        mma2_bf16(tbase + dcol, dah, dbh, idesc, (s8 | j) ? 1u : 0u);
+        mma2_bf16(tbase + dcol, dal, dbh, idesc, 1u);
+        mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
+      }
+      commit2(&bar_empty[stage]);
+    }
+    __syncwarp();
+  }
+}
+
+template <int RELAY, int TMAP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_constant__ AugruPairParams pp) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h0, bar_h1, bar_rh, bar_r, bar_u, bar_c;
+  __shared__ uint32_t tmem_base_s;
+  const AugruTcParams& p = pp.b;
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  uint8_t* sHhi = smem;                       // A operand: h
+  uint8_t* sHlo = smem + P_A_BYTES;
+  uint8_t* sRhi = smem + 2 * P_A_BYTES;       // A operand: r*h
+  uint8_t* sRlo = smem + 3 * P_A_BYTES;
+  uint8_t* sB = smem + 4 * P_A_BYTES;
+  const AugruTcSeq& S = p.s[blockIdx.y];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m0 = (blockIdx.x >> 1) * TM;      // the pair's 128-row tile
+
+  if (tid == 0) {
+    // "full": TMAP -> only the leader's barrier is used: one expect_tx arrival covering both CTAs' bytes;
+    //         else the leader's collects its own TMA (expect_tx arrival) and the peer's relay arrival.
+    for (int i = 0; i < P_NST; ++i) { mbar_init(&bar_full[i], (rank == 0 && !TMAP) ? 2 : 1); mbar_init(&bar_empty[i], 1); }
+    // hand-over barriers: RELAY -> 8 local warps (+ 1 relay arrival on the leader); else 8 warps x 2 CTAs on the leader
+    const int nh = RELAY ? (rank == 0 ? 9 : 8) : 16;
+    mbar_init(&bar_h0, nh); mbar_init(&bar_h1, nh); mbar_init(&bar_rh, nh);
+    mbar_init(&bar_r, 1); mbar_init(&bar_u, 1); mbar_init(&bar_c, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // the peer's barriers exist before anyone arrives remotely
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t bar_h0_leader = mapa_rank(smem_u32(&bar_h0), 0), bar_h1_leader = mapa_rank(smem_u32(&bar_h1), 0),
+                 bar_rh_leader = mapa_rank(smem_u32(&bar_rh), 0);
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // frees 128 x 128 registers = what 232 for the 256 epilogue threads takes
+    if (warp == 9) {
+      // ===== TMA producer: this CTA's half of the 24-stage weight stream of a step, 64 times =====
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        if (TMAP) {
+          const CUtensorMap* tm = &pp.tmap[blockIdx.y];
+          const uint32_t full0_leader = mapa_rank(smem_u32(&bar_full[0]), 0);
+          const uint32_t sB_u = smem_u32(sB);
+          for (int t = 0; t < STEPS; ++t) {
+            int row = (int)rank * P_STAGES_PER_STEP * P2_TM_BOX_ROWS;
+            for (int i = 0; i < P_STAGES_PER_STEP; ++i, row += P2_TM_BOX_ROWS) {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              if (rank == 0) mbar_expect_tx(&bar_full[stage], 2 * P_STAGE_BYTES);
+              tma_box_cg2(sB_u + stage * P_STAGE_BYTES, tm, 0, row, full0_leader + stage * 8);
+              if (++stage == P_NST) { stage = 0; phase ^= 1; }
+            }
+          }
+        } else {
+          const uint8_t* img = S.Wimg + (size_t)rank * P_RANK_IMAGE_BYTES;
+          for (int t = 0; t < STEPS; ++t) {
+            const uint8_t* src = img;
+            for (int i = 0; i < P_STAGES_PER_STEP; ++i, src += P_STAGE_BYTES) {
+              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_expect_tx(&bar_full[stage], P_STAGE_BYTES);
+              bulk_g2s(sB + stage * P_STAGE_BYTES, src, P_STAGE_BYTES, &bar_full[stage]);
+              if (++stage == P_NST) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 8 && rank == 1) {
+      // ===== ring relay (only without the tensor map): tell the leader that this CTA's copy of stage s has landed =====
+      if (!TMAP && lane == 0) {
+        const uint32_t remote0 = mapa_rank(smem_u32(&bar_full[0]), 0);
+        int stage = 0; uint32_t phase = 0;
+        for (int i = 0; i < STEPS * P_STAGES_PER_STEP; ++i) {
+          mbar_wait(&bar_full[stage], phase);
+          arrive_cl_relaxed(remote0 + stage * 8);
+          if (++stage == P_NST) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 8) {
+      // ===== MMA issuer (leader CTA): uniform control flow, one elected lane issues =====
+      const uint32_t leader = elect_one();
+      uint32_t hHi_d = desc_lo(smem_u32(sHhi), LBO), hLo_d = desc_lo(smem_u32(sHlo), LBO), rHi_d = desc_lo(smem_u32(sRhi), LBO),
+               rLo_d = desc_lo(smem_u32(sRlo), LBO), b_d = desc_lo(smem_u32(sB), LBO);
+      for (int t = 0; t < STEPS; ++t) {
+        const uint32_t par = t & 1;
+        long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && leader) ? p.dbg + t * 16 : nullptr;
+        if (dbg) dbg[0] = clock64();
+        // keep the 144 descriptors of a step OUT of the loop-invariant set: hoisted, they live in local memory (this warp
+        // has 40 registers) and every MMA pays a local load; rebuilt from these five words each costs one add
+        asm volatile("" : "+r"(hHi_d), "+r"(hLo_d), "+r"(rHi_d), "+r"(rLo_d), "+r"(b_d));
+        mbar_wait_cl(&bar_h0, par);     // both CTAs' even K blocks of h (hi/lo) are in shared memory
+        tc_fence_after();
+        if (dbg) dbg[1] = clock64();
+        issue_gate2<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par);   // ... the odd ones by its second half
+        if (leader) commit2(&bar_r);
+        if (dbg) dbg[2] = clock64();
+        issue_gate2<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0);
+        if (leader) commit2(&bar_u);
+        if (dbg) dbg[3] = clock64();
+        mbar_wait_cl(&bar_rh, par);     // both CTAs' r*h written
+        tc_fence_after();
+        if (dbg) dbg[4] = clock64();
+        issue_gate2<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0);
+        if (leader) commit2(&bar_c);
+        if (dbg) { dbg[5] = clock64(); dbg[6] = 0; dbg[7] = 0; }
+      }
+    } else if (RELAY && rank == 1 && lane == 0) {
+      // ===== hand-over relays (peer CTA): forward each completed local phase with a cluster-scope release =====
+      // A local phase k+1 cannot complete before phase k has been forwarded: it needs the leader's next MMAs, which wait
+      // for this very arrival.  warp 11: h0 (the latency-critical one); warp 10: r*h and h1, in their order in time.
+      if (warp == 11) {
+        for (int k = 0; k <= STEPS; ++k) { mbar_wait(&bar_h0, k & 1); arrive_cl(bar_h0_leader); }
+      } else {
+        mbar_wait(&bar_h1, 0); arrive_cl(bar_h1_leader);
+        for (int t = 0; t < STEPS; ++t) {
+          mbar_wait(&bar_rh, t & 1); arrive_cl(bar_rh_leader);
+          mbar_wait(&bar_h1, (t + 1) & 1); arrive_cl(bar_h1_leader);
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // ===== epilogue warps: thread = (row of this CTA, 64 hidden columns) =====
+    const int q = warp & 3, sub = warp >> 2;
+    const int rl = (q & 1) * 32 + lane;                    // row inside this CTA
+    const int prow = (int)rank * P_RC + rl;                // row inside the pair's 128-row tile
+    const int hc0 = (q >> 1) * 128 + sub * 64;             // first hidden column of this thread
+    const uint32_t tcol = (uint32_t)sub * 64;              // TMEM column offset inside a gate
+    int r = m0 + prow;
+    const bool valid = r < p.R;
+    if (!valid) r = p.R - 1;
+    const int ci = S.shared ? 0 : (p.row0 + r) / p.div;
+    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM + (ci % TM);
+    const float* st = S.scoresT + ((size_t)(m0 / TM) * STEPS) * TM + prow;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row_off = (uint32_t)(rl / 8) * A_SBO + (uint32_t)(rl % 8) * 16;
+    const bool local_arrive = RELAY || rank == 0;          // arrive on this CTA's own barrier (else: relaxed, on the leader's)
+    float h[64], x[4][16];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) h[i] = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {                          // h0 = 0 into the A operand
+      uint32_t off = a_row_off + (uint32_t)((hc0 + g * 8) / 8) * LBO;
+      *reinterpret_cast<uint4*>(sHhi + off) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sHlo + off) = make_uint4(0, 0, 0, 0);
+    }
+    proxy_fence();
+    __syncwarp();
+    if (lane == 0) {
+      if (local_arrive) { mbar_arrive(&bar_h0); mbar_arrive(&bar_h1); }
+      else { arrive_cl_relaxed(bar_h0_leader); arrive_cl_relaxed(bar_h1_leader); }
+    }
+#define R4P2_LOADX(dst, base, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg((base) + (size_t)((colbase) + j) * TM)
+    // rolling input buffer: x[ch] always holds chunk ch of the NEXT phase to run (here: the r gate of step 0)
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) { R4P2_LOADX(x[c4], xt, hc0 + c4 * 16); }
+    float one_minus_s = 1.0f - __ldg(st);
+
+    for (int t = 0; t < STEPS; ++t) {
+      const uint32_t par = t & 1;
+      long long* dbg = (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) ? p.dbg + t * 16 : nullptr;
+      const float* xs = xt + (size_t)t * XT_COLS * TM;
+      const bool more = t + 1 < STEPS;
+      const float* xs_next = xs + (more ? (size_t)XT_COLS * TM : 0);
+      const float oms_next = 1.0f - __ldg(st + (size_t)(more ? t + 1 : t) * TM);
+      // Pull this CTA's half of the NEXT step's input lines (768 columns x 2 lines) from HBM into L2.
+      if (more) {
+        const float* xn = S.XT + (((size_t)(ci / TM) * STEPS + (t + 1)) * XT_COLS) * TM;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          const int id = i * 256 + tid;                    // 1536 lines: (column, 32-lane group of this CTA)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(id >> 1) * TM + (rank * 2 + (id & 1)) * 32));
+        }
+      }
+      // ---- phase R (overlaps the u MMAs): r*h -> its own A operand; x[] <- the u gate's inputs ----
+      {
+        float a[2][16];
+        if (dbg) dbg[8] = clock64();
+        mbar_wait(&bar_r, par);
+        if (dbg) dbg[9] = clock64();
+        tc_fence_after();
+        tmem_ld16(tlane + P_TC_R + tcol, a[0]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int cur = ch & 1, nxt = cur ^ 1;
+          tmem_wait_ld();
+          if (ch < 3) tmem_ld16(tlane + P_TC_R + tcol + (ch + 1) * 16, a[nxt]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[ch][j]) * h[ch * 16 + j];
+          R4P2_LOADX(x[ch], xs, HID + hc0 + ch * 16);
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 hi, lo;
+            split8(a[cur] + g * 8, hi, lo);
+            uint32_t off = a_row_off + (uint32_t)((hc0 + ch * 16 + g * 8) / 8) * LBO;
+            *reinterpret_cast<uint4*>(sRhi + off) = hi;
+            *reinterpret_cast<uint4*>(sRlo + off) = lo;
+          }
+        }
+      }
+      tc_fence_before();
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) { if (local_arrive) mbar_arrive(&bar_rh); else arrive_cl_relaxed(bar_rh_leader); }
+      if (dbg) dbg[10] = clock64();
+      // ---- phase U (overlaps the c MMAs): E = 1 + exp(-(acc_u + Xu)) back into TMEM; x[] <- the c gate's inputs ----
+      {
+        float a[2][16];
+        mbar_wait(&bar_u, par);
+        if (dbg) dbg[11] = clock64();
+        tc_fence_after();
+        tmem_ld16(tlane + P_TC_U + tcol, a[0]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int cur = ch & 1, nxt = cur ^ 1;
+          tmem_wait_ld();
+          if (ch < 3) tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, a[nxt]);
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            a[cur][j] = 1.0f + ex2_approx(fminf(-1.4426950408889634f * (a[cur][j] + x[ch][j]), 60.0f));
+          R4P2_LOADX(x[ch], xs, 2 * HID + hc0 + ch * 16);
+          tmem_st16(tlane + P_TC_U + tcol + ch * 16, a[cur]);
+        }
+        tmem_wait_st();
+      }
+      if (dbg) dbg[12] = clock64();
+      // ---- phase C: c = tanh(acc_c + Xc) = 1 - 2/(1 + F), u = 1/E with ONE reciprocal of E*F; x[] <- next step's r inputs ----
+      {
+        float a[2][16], u[2][16];
+        mbar_wait(&bar_c, par);
+        if (dbg) dbg[13] = clock64();
+        tc_fence_after();
+        tmem_ld16(tlane + P_TC_C + tcol, a[0]);
+        tmem_ld16(tlane + P_TC_U + tcol, u[0]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const int cur = ch & 1, nxt = cur ^ 1;
+          tmem_wait_ld();
+          if (ch < 3) {
+            tmem_ld16(tlane + P_TC_C + tcol + (ch + 1) * 16, a[nxt]);
+            tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, u[nxt]);
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float F = 1.0f + ex2_approx(fminf(2.8853900817779268f * (a[cur][j] + x[ch][j]), 60.0f));
+            const float E = u[cur][j];
+            const float rc = rcp_approx(E * F);                      // E, F <= 1 + 2^60: the product is finite
+            const float c = fmaf(-2.0f, rc * E, 1.0f);               // tanh
+            const float up = one_minus_s * (rc * F);                 // (1 - s) sigmoid
+            const float hn = fmaf(up, h[ch * 16 + j] - c, c);        // u' h + (1 - u') c
+            h[ch * 16 + j] = hn;
+            a[cur][j] = hn;
+          }
+          R4P2_LOADX(x[ch], xs_next, hc0 + ch * 16);      // (last step: a harmless re-read of this step's lines)
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 hi, lo;
+            split8(a[cur] + g * 8, hi, lo);
+            uint32_t off = a_row_off + (uint32_t)((hc0 + ch * 16 + g * 8) / 8) * LBO;
+            *reinterpret_cast<uint4*>(sHhi + off) = hi;
+            *reinterpret_cast<uint4*>(sHlo + off) = lo;
+          }
+          if (ch == 1) {              // this thread's even K block of h' is complete: release the first half of the next r gate
+            proxy_fence();
+            __syncwarp();
+            if (lane == 0) { if (local_arrive) mbar_arrive(&bar_h0); else arrive_cl_relaxed(bar_h0_leader); }
+          }
+        }
+      }
+      tc_fence_before();
+      proxy_fence();
+      __syncwarp();
+      if (dbg) dbg[14] = clock64();
+      if (lane == 0) { if (local_arrive) mbar_arrive(&bar_h1); else arrive_cl_relaxed(bar_h1_leader); }
+      one_minus_s = oms_next;
+    }
+#undef R4P2_LOADX
+    if (valid) {
+      float* o = S.out + (size_t)(m0 + prow) * p.out_ld + hc0;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                         // neither CTA frees TMEM / exits while the pair's MMAs or arrivals are in flight
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512));
+}
+
+// host: the pair weight image of one sequence (2 ranks x 24 stages x 16 KB, device pointer) as a tensor map of
+// [768 rows][256 x u32]; box = 256 x 16 = one ring stage.  cuTensorMapEncodeTiled is fetched through the runtime
+// (cudaGetDriverEntryPoint), so the library does not link libcuda.  Returns 0 on success.
+inline int make_pair_tensor_map(const void* dev_img, CUtensorMap* out) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeFn>(f);
+  }();
+  if (!fn) return 1;
+  const cuuint64_t gdim[2] = {256, (cuuint64_t)(2 * P_RANK_IMAGE_BYTES / P2_TM_ROW_BYTES)};
+  const cuuint64_t gstride[1] = {P2_TM_ROW_BYTES};
+  const cuuint32_t box[2] = {256, (cuuint32_t)P2_TM_BOX_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult rc = fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(dev_img), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : 2;
+}
+
+}  // namespace r4tc

@@ -4,6 +4,7 @@
 #include "r4_kernels.cuh"
 #include "r4_augru_tc.cuh"
 #include "r4_augru_pair.cuh"
+#include "r4_augru_pair2.cuh"
 #include "r4_gemm_tc.cuh"
 #include "r4_scores_tc.cuh"
 #include "r4_gru_tc.cuh"
@@ -42,6 +43,8 @@ struct PerSeq {
   uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr, *gru_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
   uint8_t* au_pair_img = nullptr;   // the same weights tiled per CTA rank for the 2-CTA kernel (r4_augru_pair.cuh)
   uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
+  CUtensorMap au_pair_tmap;    // au_pair_img as a 2-D tensor of 1 KB rows (r4_augru_pair2.cuh: tensor-map TMA ring)
+  bool au_pair_tmap_ok = false;
   float abk = 0.f;
 };
 
@@ -224,21 +227,33 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
   return R4_OK;
 }
 
-// Which AUGRU kernel runs `ctas` = 2 x row tiles of work.  The 2-CTA pair kernel finishes a 128-row tile in ~0.66 of
-// the time of the one-CTA kernel but occupies two SMs for it, so it wins exactly when the one-CTA kernel would leave
-// SMs idle (a 4096-row observation pass: 64 tiles on 148 SMs) and loses on multi-wave launches (the reward pass,
-// batch x 9 rows).  Measured per wave: pair 0.75 ms, single 1.13 ms (tools/augru_probe.cu) -> compare 2*waves vs 3*waves.
-// R4_AUGRU_SINGLE=1 / R4_AUGRU_PAIR=1 force one kernel (A/B runs).
+// Kernel-choice options (r4_set_option; the environment gives the initial values).
+struct AugruOpts {
+  int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel
+  int pair_impl = 1;      // 1 = k_augru_pair2<R4P2_RELAY, R4P2_TMAP>, 2..4 = <0,1> <1,0> <0,0>
+  int cost_single = 3, cost_pair = 2;   // per-wave cost ratio, measured
+  AugruOpts() {
+    if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2;
+    if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
+    if (const char* e = getenv("R4_AUGRU_RULE")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { cost_single = a; cost_pair = b; } }
+  }
+};
+AugruOpts& augru_opts() { static AugruOpts o; return o; }
+
+// Which AUGRU kernel runs `ctas` = 2 x row tiles of work.  The 2-CTA pair kernel finishes a 128-row tile faster than the
+// one-CTA kernel but occupies two SMs for it: compare cost_single * waves(ctas, sms) with cost_pair * waves(ctas, sms / 2).
 static bool augru_rule_single(int ctas, int sms) {
+  const AugruOpts& o = augru_opts();
   const int w_single = (ctas + sms - 1) / sms, w_pair = (ctas + sms / 2 - 1) / (sms / 2);
-  return 3 * w_single <= 2 * w_pair;
+  return o.cost_single * w_single <= o.cost_pair * w_pair;
 }
 static bool augru_use_single(int ctas) {
-  static const int force = getenv("R4_AUGRU_SINGLE") ? 1 : (getenv("R4_AUGRU_PAIR") ? 2 : 0);
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+  const int force = augru_opts().force;
   if (force) return force == 1;
   return augru_rule_single(ctas, sms);
 }
+static int augru_pair_impl() { return augru_opts().pair_impl; }
 
 // One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
 int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const float* dense,
@@ -308,9 +323,19 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   R4_LAUNCH_CHECK(e, "k_scores_tc");
   if (!no_side && !side_early) R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
+    const dim3 pgrid(rtiles * 2, 2);
     if (augru_use_single(2 * rtiles)) r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp);
-    else r4tc::k_augru_pair<<<dim3(rtiles * 2, 2), r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(rp); }
-  R4_LAUNCH_CHECK(e, "k_augru_tc");
+    else {
+      r4tc::AugruPairParams pp;
+      pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
+      switch (augru_pair_impl()) {
+        case 2: r4tc::k_augru_pair2<0, 1><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
+        case 3: r4tc::k_augru_pair2<1, 0><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
+        case 4: r4tc::k_augru_pair2<0, 0><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
+        default: r4tc::k_augru_pair2<R4P2_RELAY, R4P2_TMAP><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
+      }
+    } }
+  R4_LAUNCH_CHECK(e, augru_use_single(2 * rtiles) ? "k_augru_tc" : "k_augru_pair");
   if (!no_side && !side_early && (rc = side_work())) return rc;
   if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
@@ -454,6 +479,10 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
@@ -614,6 +643,11 @@ int r4_finalize_weights(r4_env* e, void* stream) {
     if ((rc = upload(e, img, &w.au_img))) return rc;
     r4tc::build_pair_image(awgh.data(), awch.data(), img.data());
     if ((rc = upload(e, img, &w.au_pair_img))) return rc;
+    {
+      int trc = r4tc::make_pair_tensor_map(w.au_pair_img, &w.au_pair_tmap);
+      w.au_pair_tmap_ok = trc == 0;
+      if (trc) return fail(e, R4_ERR_CUDA, "r4_finalize_weights: cuTensorMapEncodeTiled failed for the AUGRU pair weight image");
+    }
     std::vector<float> vb1(ab1, ab1 + AH1), vw2(aw2, aw2 + AH1 * AH2), vb2(ab2, ab2 + AH2), vkv(akv, akv + AH2);
     if ((rc = upload(e, wx, &w.gru_wx)) || (rc = upload(e, bx, &w.gru_bx)) || (rc = upload(e, wgh, &w.gru_wgh)) ||
         (rc = upload(e, wch, &w.gru_wch)) || (rc = upload(e, awx, &w.au_wx)) || (rc = upload(e, abx, &w.au_bx)) ||
@@ -765,6 +799,18 @@ int r4_nearest_neighbor(r4_env* e, const void* action, int action_is_f64, int n,
 int r4_cur_steps(const r4_env* e) { return e ? e->cur_steps : -1; }
 const int32_t* r4_prev_actions(const r4_env* e) { return e ? e->prev_actions : nullptr; }
 int64_t r4_launch_count(const r4_env* e) { return e ? e->launches : 0; }
+
+int r4_set_option(const char* key, int value) {
+  if (!key) return fail(nullptr, R4_ERR_ARG, "r4_set_option: null key");
+  AugruOpts& o = augru_opts();
+  const std::string k(key);
+  if (k == "augru_kernel" && value >= 0 && value <= 2) o.force = value;
+  else if (k == "augru_pair_impl" && value >= 1 && value <= 4) o.pair_impl = value;
+  else if (k == "augru_cost_single" && value > 0) o.cost_single = value;
+  else if (k == "augru_cost_pair" && value > 0) o.cost_pair = value;
+  else return fail(nullptr, R4_ERR_ARG, "r4_set_option: unknown key or value out of range: " + k);
+  return R4_OK;
+}
 
 int r4_augru_kernel_for(int ctas, int sms) { return (ctas < 1 || sms < 2) ? 0 : (augru_rule_single(ctas, sms) ? 1 : 2); }
 

@@ -96,6 +96,16 @@ class Engine(object):
 
     def _load_log(self, log):
         assert isinstance(log, LogSoA)
+        # Ids index the embedding tables, the price table and action_emb on the device: reject what the reference's
+        # TF Embedding lookup / dict lookup would reject on the CPU (out-of-range or negative ids) once, here.
+        H = int(self.config.get("category_hash_size", 100000))
+        for name, arr, hi in (("user_protrait ids", log.user_cat, H), ("user_seqfeature ids", log.user_seq, H),
+                              ("exposed_items", log.items, self.A)):
+            a = np.asarray(arr)
+            if a.size and (a.min() < 0 or a.max() >= hi):
+                raise ValueError("log %s out of range [0, %d): min %d, max %d" % (name, hi, a.min(), a.max()))
+        if log.items.shape[1] < (self.P if self.seq else min(self.T, self.P)):
+            raise ValueError("log rows carry %d exposed items, the env needs at least %d" % (log.items.shape[1], self.P))
         self.log = log
         dev = self.device
         self.d_cat = torch.from_numpy(np.ascontiguousarray(log.user_cat, dtype=np.int32)).to(dev)
@@ -115,10 +125,11 @@ class Engine(object):
         self.mask = z((B, self.A), torch.uint8) if self.rllib else None
         self.reward = z((B,), torch.float64)
         self.chosen = z((B,), torch.int32)
-        self.cat = z((B, 21), torch.int32) if self.raw else None
-        self.dense = z((B, 432), torch.float32) if self.raw else None
-        self.seqf = z((B, 2, 64), torch.int32) if self.raw else None
-        self.click_p = z((B, 9), torch.float32) if self.info_fetch else None
+        c = self.config
+        self.cat = z((B, int(c.get("category_feature_num", 21))), torch.int32) if self.raw else None
+        self.dense = z((B, int(c.get("dense_feature_num", 432))), torch.float32) if self.raw else None
+        self.seqf = z((B, int(c.get("seq_num", 2)), int(c.get("maxlen", 64))), torch.int32) if self.raw else None
+        self.click_p = z((B, self.P), torch.float32) if self.info_fetch else None
         self.masked = z((B, self.P if self.seq else self.T), torch.int32) if self.d3rl else None
         self.out = _capi.R4Out(
             obs=_ptr(self.obs), action_mask=_ptr(self.mask), reward=_ptr(self.reward), done=None,
@@ -136,6 +147,8 @@ class Engine(object):
     def reset(self, rows):
         """rows: int array [B] of log rows (host) or an int32 device tensor."""
         if isinstance(rows, torch.Tensor):
+            # device-resident row indices are TRUSTED (checking them would cost a host synchronisation per reset):
+            # the caller guarantees 0 <= rows < log.n, as trainer.py / dataset.py do
             self.rows.copy_(rows.to(torch.int32), non_blocking=True)
         else:
             rows = np.asarray(rows)

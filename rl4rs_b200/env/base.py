@@ -22,14 +22,33 @@ from ..utils.datautil import FeatureUtil
 
 
 def single_elem_support(func):
-    """batch_size == 1 returns scalars instead of 1-element lists (base.py:9-23)."""
-    type_list = (list, tuple, np.ndarray)
+    """batch_size == 1 returns scalars instead of 1-element lists (base.py:9-23).  The reference only ever sees lists;
+    the 'numpy' / 'torch' output formats hand out arrays, tensors and dicts of them, so the unwrapping is per element:
+    a 1-long list / tuple / array / tensor becomes its element, a dict is unwrapped value by value, everything else
+    (the shared info dict, scalars) is passed through."""
+    seq_types = (list, tuple, np.ndarray)
+
+    def is_batch1(x):
+        if isinstance(x, seq_types):
+            return len(x) == 1
+        return hasattr(x, "is_cuda") and x.dim() >= 1 and x.shape[0] == 1       # torch tensor
+
+    def unwrap(x):
+        if isinstance(x, dict):
+            return {k: (v[0] if is_batch1(v) else v) for k, v in x.items()}
+        return x[0] if is_batch1(x) else x
 
     def wrapper(*args, **kwargs):
         res = func(*args, **kwargs)
-        if type(res) in type_list and len(res) == 1:
+        if isinstance(res, tuple) and len(res) == 4:       # step(): (obs, reward, done, info), element by element
+            if is_batch1(res[1]) or is_batch1(res[2]):     # (the reference hands back a LIST of 4 here: base.py:19-21)
+                return [unwrap(x) for x in res]
+            return res
+        if isinstance(res, dict):                          # numpy / torch observation dict
+            return unwrap(res) if all(is_batch1(v) for v in res.values()) else res
+        if is_batch1(res):
             return res[0]
-        elif type(res) in type_list and len(res) and type(res[0]) in type_list and len(res[0]) == 1:
+        if isinstance(res, seq_types) and len(res) and isinstance(res[0], seq_types) and len(res[0]) == 1:
             return [x[0] for x in res]
         return res
 

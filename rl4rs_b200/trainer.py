@@ -144,7 +144,12 @@ class _TrainerBase(object):
         self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
         self.ops = KernelOps(self.A, self.device, self.policy.n_params) if self.use_kernels else None
         self._act_i32 = torch.zeros(self.B, dtype=torch.int32, device=self.device)
-        self._seed = seed
+        # shared `seed` for the parameter init and the minibatch permutation; the exploration noise is per rank
+        # (k_policy_act hashes seed ^ counter+row: the same seed would give rank r row i the noise of rank 0 row i)
+        rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self._seed = (seed * 1000003 + rank) & 0x7fffffffffffffff
+        if rank and not self.use_kernels:
+            torch.manual_seed(seed * 1000003 + rank)
         self.buf = RolloutBuffer(self.T, self.B, self.A, self.device)
         self.iteration = 0
         self.timesteps_total = 0

@@ -47,8 +47,13 @@ class FeatureUtil(object):
         ``pad_sequences(..., maxlen)`` does at datautil.py:43-46; portrait splits into 10
         categorical ids (parsed float -> int, slate.py:77 + datautil.py:49) and 32 dense floats
         (f64 text -> f32, datautil.py:52-58)."""
-        lines = [ln.rstrip() for ln in lines]
-        lines = [ln for ln in lines if ln]
+        lines = [ln.rstrip("\r\n") for ln in lines]
+        # the reference's reader treats the FIRST empty line as end of file and rewinds (base.py:85-88): rows behind a
+        # blank line are never served, so they are not ingested either
+        for i, ln in enumerate(lines):
+            if not ln.strip():
+                lines = lines[:i]
+                break
         n = len(lines)
         S = len(lines[0].split("@")[3].split(",")) if n else 9
         ts = np.zeros(n, np.int64)
@@ -81,9 +86,11 @@ class FeatureUtil(object):
                 raise ValueError("line %d: user_protrait has %d values, expected 42" % (i, len(p)))
             user_cat[i] = p[:10].astype(np.int64)
             user_dense[i] = p[10:].astype(np.float32)
-        return LogSoA(timestamp=ts, session_id=sess, sequence_id=sid, user_cat=user_cat,
-                      user_dense=user_dense, user_seq=user_seq, seq_len=seq_len, items=items,
-                      feedback=feedback, hist=hist)
+        log = LogSoA(timestamp=ts, session_id=sess, sequence_id=sid, user_cat=user_cat,
+                     user_dense=user_dense, user_seq=user_seq, seq_len=seq_len, items=items,
+                     feedback=feedback, hist=hist)
+        log.lines = list(lines)          # the record strings: samples.records / to_string() (base.py:28-31,56-57)
+        return log
 
     @staticmethod
     def load_log(path, maxlen=64):

@@ -24,3 +24,25 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Parity margins of this session (golden_util.MARGINS): printed, and kept as gpurun_out/parity_margins.json."""
+    try:
+        import json
+        import golden_util
+        if not golden_util.MARGINS:
+            return
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_margins.json"), "w") as f:
+            json.dump(golden_util.MARGINS, f, indent=1, sort_keys=True)
+        tr = session.config.pluginmanager.get_plugin("terminalreporter")
+        if tr:
+            tr.write_line("")
+            tr.write_line("parity margins (floored err/bound <= 1 is the assertion; plain = element-wise |err|/|ref|):")
+            for k, m in sorted(golden_util.MARGINS.items()):
+                tr.write_line("  %-44s n=%-9d floored %.3f  plain rel max %.3g at |ref|=%.3g (row rms %.3g)" % (
+                    k[:44], m["n"], m["floored_err_over_bound"], m["plain_rel_max"], m["plain_rel_at_abs_ref"], m["row_rms_there"]))
+    except Exception as exc:      # never turn a reporting problem into a test failure
+        print("parity margin report failed:", exc)

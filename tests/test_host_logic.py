@@ -131,3 +131,27 @@ def test_vector_env_wrapper_semantics():
     obs, rew, done, info = v.vector_step([1, 2, 3, 4])
     assert isinstance(env.last, np.ndarray) and env.last.tolist() == [1, 2, 3, 4] and len(obs) == 4
     assert v.get_unwrapped() == [env] * 4 and v.try_render_at(1) == "rendered"
+
+
+def test_single_elem_support_numpy_and_dict_formats():
+    """B == 1 with the array / dict output formats (round-1 advisor): per-element unwrapping, info dict passed through."""
+    obs = {"obs": np.zeros((1, 256), np.float32), "action_mask": np.ones((1, 284), np.uint8)}
+    f = single_elem_support(lambda: (obs, np.array([0.5]), np.array([1]), {}))
+    o, r, d, info = f()
+    assert o["obs"].shape == (256,) and o["action_mask"].shape == (284,) and r == 0.5 and d == 1 and info == {}
+    f = single_elem_support(lambda: (np.zeros((1, 256), np.float32), np.array([0.0]), np.array([0]), {"click_p": np.zeros((1, 9))}))
+    o, r, d, info = f()
+    assert o.shape == (256,) and info["click_p"].shape == (9,)
+    two = (np.zeros((2, 256)), np.zeros(2), np.zeros(2), {})
+    assert single_elem_support(lambda: two)() is two
+    assert single_elem_support(lambda: obs)()["obs"].shape == (256,)
+
+
+def test_parse_log_stops_at_first_blank_line_and_keeps_records():
+    """base.py:85-88: the reference's reader treats the first empty line as EOF; records stay available as strings."""
+    cat = synth.make_catalog()
+    log = synth.make_log(6, catalog=cat, keep_hist=True)
+    recs = synth.render_records(log, cat)
+    parsed = FeatureUtil.parse_log(recs[:4] + ["", recs[4], recs[5]])
+    assert parsed.n == 4 and parsed.lines == recs[:4]
+    assert FeatureUtil.parse_log(recs + [""]).n == 6

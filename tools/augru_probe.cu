@@ -3,7 +3,16 @@
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
 #ifdef PAIR
 #include "../rl4rs_b200/csrc/r4_augru_pair.cuh"
-#ifdef PAIRT
+#ifdef PAIR2
+#include "../rl4rs_b200/csrc/r4_augru_pair2.cuh"
+#ifndef P2RELAY
+#define P2RELAY 1
+#endif
+#ifndef P2TMAP
+#define P2TMAP 1
+#endif
+#define KERNEL (k_augru_pair2<P2RELAY, P2TMAP>)
+#elif defined(PAIRT)
 #include "experiments/r4_augru_pair_templated.cuh"
 #define KERNEL k_augru_pair_t
 #else
@@ -86,10 +95,17 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(dimg, img.data(), img.size(), cudaMemcpyHostToDevice));
   CK(cudaMemset(dout, 0, (size_t)R * 256 * 4));
   CK(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, KSMEM));
+#ifdef PAIR2
+  CUtensorMap tmap;
+  { int trc = make_pair_tensor_map(dimg, &tmap); if (trc) { printf("make_pair_tensor_map failed: %d\n", trc); return 1; } }
+#define LAUNCH(grid, prm) do { AugruPairParams pp_; pp_.b = (prm); pp_.tmap[0] = tmap; pp_.tmap[1] = tmap; KERNEL<<<grid, KTHREADS, KSMEM>>>(pp_); } while (0)
+#else
+#define LAUNCH(grid, prm) KERNEL<<<grid, KTHREADS, KSMEM>>>(prm)
+#endif
   AugruTcParams p{};
   p.s[0] = {dXT, dimg, dsT, dout, 0}; p.s[1] = p.s[0];
   p.R = R; p.row0 = 0; p.div = div; p.out_ld = 256;
-  KERNEL<<<dim3(GRIDX(rtiles), 1), KTHREADS, KSMEM>>>(p);
+  LAUNCH(dim3(GRIDX(rtiles), 1), p);
   CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
   std::vector<float> hout((size_t)R * 256);
   CK(cudaMemcpy(hout.data(), dout, hout.size() * 4, cudaMemcpyDeviceToHost));
@@ -117,7 +133,7 @@ int main(int argc, char** argv) {
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int it = 0; it < 3; ++it) {
       cudaEventRecord(e0);
-      KERNEL<<<dim3(GRIDX(timing_tiles), 1), KTHREADS, KSMEM>>>(q);
+      LAUNCH(dim3(GRIDX(timing_tiles), 1), q);
       cudaEventRecord(e1); CK(cudaDeviceSynchronize());
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       double flops = (double)RT * 64 * 2.0 * (256 * 512 + 256 * 256);
