@@ -30,6 +30,12 @@
 #ifndef R4P2_TMAP
 #define R4P2_TMAP 1
 #endif
+#ifndef R4P2_PRESCALE
+#define R4P2_PRESCALE 0   // 1: the cached input halves arrive pre-multiplied (r, u columns by -log2(e), c columns by 2 log2(e)),
+#endif                    //    so a gate pre-activation in the exp2 domain is ONE fma(acc, scale, x') instead of add + mul
+#ifndef R4P2_SWPIPE
+#define R4P2_SWPIPE 0     // 1: the bf16 split + shared-memory store of chunk k-1 is issued next to the MUFU section of chunk k
+#endif
 
 namespace r4tc {
 
@@ -94,6 +100,23 @@ __device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uin
     }
     __syncwarp();
   }
+}
+
+constexpr float P2_NL2E = -1.4426950408889634f, P2_2L2E = 2.8853900817779268f;
+// gate pre-activation in the exp2 domain: scale * (acc + x); with R4P2_PRESCALE x already carries the scale
+__device__ __forceinline__ float preact2(float acc, float x, float scale) {
+#if R4P2_PRESCALE
+  return fmaf(acc, scale, x);
+#else
+  return scale * (acc + x);
+#endif
+}
+// 8 fp32 -> bf16 hi / lo core-matrix rows of an A operand
+__device__ __forceinline__ void split_store8(const float* v, uint8_t* hi_base, uint8_t* lo_base, uint32_t off) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(hi_base + off) = hi;
+  *reinterpret_cast<uint4*>(lo_base + off) = lo;
 }
 
 template <int RELAY, int TMAP>
@@ -276,7 +299,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       }
       // ---- phase R (overlaps the u MMAs): r*h -> its own A operand; x[] <- the u gate's inputs ----
       {
-        float a[2][16];
+        float a[R4P2_SWPIPE ? 3 : 2][16];
+        constexpr int NA = R4P2_SWPIPE ? 3 : 2;
         if (dbg) dbg[8] = clock64();
         mbar_wait(&bar_r, par);
         if (dbg) dbg[9] = clock64();
@@ -284,20 +308,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         tmem_ld16(tlane + P_TC_R + tcol, a[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int cur = ch & 1, nxt = cur ^ 1;
+          const int cur = ch % NA, nxt = (ch + 1) % NA;
           tmem_wait_ld();
           if (ch < 3) tmem_ld16(tlane + P_TC_R + tcol + (ch + 1) * 16, a[nxt]);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[ch][j]) * h[ch * 16 + j];
+          for (int j = 0; j < 16; ++j)
+            a[cur][j] = rcp_approx(1.0f + ex2_approx(preact2(a[cur][j], x[ch][j], P2_NL2E))) * h[ch * 16 + j];
           R4P2_LOADX(x[ch], xs, HID + hc0 + ch * 16);
+          const int sc = R4P2_SWPIPE ? ch - 1 : ch;      // chunk whose operand rows are written now
+          if (sc >= 0) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 hi, lo;
-            split8(a[cur] + g * 8, hi, lo);
-            uint32_t off = a_row_off + (uint32_t)((hc0 + ch * 16 + g * 8) / 8) * LBO;
-            *reinterpret_cast<uint4*>(sRhi + off) = hi;
-            *reinterpret_cast<uint4*>(sRlo + off) = lo;
+            for (int g = 0; g < 2; ++g)
+              split_store8(a[sc % NA] + g * 8, sRhi, sRlo, a_row_off + (uint32_t)((hc0 + sc * 16 + g * 8) / 8) * LBO);
           }
+        }
+        if (R4P2_SWPIPE) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            split_store8(a[3 % NA] + g * 8, sRhi, sRlo, a_row_off + (uint32_t)((hc0 + 3 * 16 + g * 8) / 8) * LBO);
         }
       }
       tc_fence_before();
@@ -319,7 +347,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
           if (ch < 3) tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, a[nxt]);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            a[cur][j] = 1.0f + ex2_approx(fminf(-1.4426950408889634f * (a[cur][j] + x[ch][j]), 60.0f));
+            a[cur][j] = 1.0f + ex2_approx(fminf(preact2(a[cur][j], x[ch][j], P2_NL2E), 60.0f));
           R4P2_LOADX(x[ch], xs, 2 * HID + hc0 + ch * 16);
           tmem_st16(tlane + P_TC_U + tcol + ch * 16, a[cur]);
         }
@@ -328,7 +356,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       if (dbg) dbg[12] = clock64();
       // ---- phase C: c = tanh(acc_c + Xc) = 1 - 2/(1 + F), u = 1/E with ONE reciprocal of E*F; x[] <- next step's r inputs ----
       {
-        float a[2][16], u[2][16];
+        float a[R4P2_SWPIPE ? 3 : 2][16], u[2][16];
+        constexpr int NA = R4P2_SWPIPE ? 3 : 2;
         mbar_wait(&bar_c, par);
         if (dbg) dbg[13] = clock64();
         tc_fence_after();
@@ -336,16 +365,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         tmem_ld16(tlane + P_TC_U + tcol, u[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int cur = ch & 1, nxt = cur ^ 1;
+          const int cur = ch % NA, nxt = (ch + 1) % NA, ucur = ch & 1, unxt = ucur ^ 1;
           tmem_wait_ld();
           if (ch < 3) {
             tmem_ld16(tlane + P_TC_C + tcol + (ch + 1) * 16, a[nxt]);
-            tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, u[nxt]);
+            tmem_ld16(tlane + P_TC_U + tcol + (ch + 1) * 16, u[unxt]);
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float F = 1.0f + ex2_approx(fminf(2.8853900817779268f * (a[cur][j] + x[ch][j]), 60.0f));
-            const float E = u[cur][j];
+            const float F = 1.0f + ex2_approx(fminf(preact2(a[cur][j], x[ch][j], P2_2L2E), 60.0f));
+            const float E = u[ucur][j];
             const float rc = rcp_approx(E * F);                      // E, F <= 1 + 2^60: the product is finite
             const float c = fmaf(-2.0f, rc * E, 1.0f);               // tanh
             const float up = one_minus_s * (rc * F);                 // (1 - s) sigmoid
@@ -354,19 +383,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
             a[cur][j] = hn;
           }
           R4P2_LOADX(x[ch], xs_next, hc0 + ch * 16);      // (last step: a harmless re-read of this step's lines)
+          const int sc = R4P2_SWPIPE ? ch - 1 : ch;
+          if (sc >= 0) {
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 hi, lo;
-            split8(a[cur] + g * 8, hi, lo);
-            uint32_t off = a_row_off + (uint32_t)((hc0 + ch * 16 + g * 8) / 8) * LBO;
-            *reinterpret_cast<uint4*>(sHhi + off) = hi;
-            *reinterpret_cast<uint4*>(sHlo + off) = lo;
+            for (int g = 0; g < 2; ++g)
+              split_store8(a[sc % NA] + g * 8, sHhi, sHlo, a_row_off + (uint32_t)((hc0 + sc * 16 + g * 8) / 8) * LBO);
           }
-          if (ch == 1) {              // this thread's even K block of h' is complete: release the first half of the next r gate
+          if (sc == 1) {              // this thread's even K block of h' is complete: release the first half of the next r gate
             proxy_fence();
             __syncwarp();
             if (lane == 0) { if (local_arrive) mbar_arrive(&bar_h0); else arrive_cl_relaxed(bar_h0_leader); }
           }
+        }
+        if (R4P2_SWPIPE) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g)
+            split_store8(a[3 % NA] + g * 8, sHhi, sHlo, a_row_off + (uint32_t)((hc0 + 3 * 16 + g * 8) / 8) * LBO);
         }
       }
       tc_fence_before();

@@ -173,8 +173,8 @@ class RecSimBase(ABC):
         pass
 
     def reload_model(self, model_file):
-        """base.py:148-151: load another checkpoint (.npz W-table) into the running simulator."""
-        w = dict(np.load(model_file))
+        """base.py:148-151: load another checkpoint (Saver prefix or .npz W-table) into the running simulator."""
+        w = self.load_model_file(model_file, self.config)
         self.engine._load_weights(w)
         self.model = w
 

@@ -154,8 +154,17 @@ class SlateRecEnv(RecSimBase):
             raise NotImplementedError("only the 'dien' simulator is built (SURVEY.md section 8f n4)")
         w = config.get("weights")
         if w is None:
-            w = dict(np.load(config["model_file"]))
+            w = self.load_model_file(config["model_file"], config)
         return w
+
+    @staticmethod
+    def load_model_file(model_file, config):
+        """``model_file``: a TF1 ``tf.train.Saver`` prefix as the reference restores it (base.py:148-151; files
+        ``<prefix>.index`` + ``<prefix>.data-*``, README.md:124-137), or an .npz of the W-table."""
+        from ..utils import tf_checkpoint
+        if tf_checkpoint.is_saver_prefix(model_file):
+            return tf_checkpoint.load_dien_checkpoint(model_file, config, name_map=config.get("variable_name_map"))
+        return dict(np.load(model_file))
 
     # slate.py:244-279
     def obs_fn(self, state):

@@ -70,8 +70,13 @@ int main(int argc, char** argv) {
   for (auto& s : sc) s = 0.5f + frand(0.5f);
   int ctiles = (ncache + TM - 1) / TM, rtiles = (R + TM - 1) / TM;
   std::vector<float> XT((size_t)ctiles * 64 * 768 * TM, 0.f), sT((size_t)rtiles * 64 * TM, 0.f);
+#if defined(PAIR2) && R4P2_PRESCALE
+#define XSCALE(col) ((col) < 512 ? -1.4426950408889634f : 2.8853900817779268f)
+#else
+#define XSCALE(col) 1.0f
+#endif
   for (int c = 0; c < ncache; ++c) for (int t = 0; t < 64; ++t) for (int col = 0; col < 768; ++col)
-    XT[(((size_t)(c / TM) * 64 + t) * 768 + col) * TM + c % TM] = X[((size_t)c * 64 + t) * 768 + col];
+    XT[(((size_t)(c / TM) * 64 + t) * 768 + col) * TM + c % TM] = XSCALE(col) * X[((size_t)c * 64 + t) * 768 + col];
   for (int r = 0; r < R; ++r) for (int t = 0; t < 64; ++t) sT[((size_t)(r / TM) * 64 + t) * TM + r % TM] = sc[(size_t)r * 64 + t];
   std::vector<uint8_t> img; build_image(Wg, Wc, img);
   // CPU reference (f64)
