@@ -6,21 +6,29 @@
 
 A "step" is ONE EPISODE of the batched env: reset (row sampling, user-history GRU-1 + input
 projections) followed by max_steps x env.step (act, feature assembly, DIEN forward, reward/done),
-over `batch_per_gpu` env rows per GPU = batch x max_steps transitions.  N = 1 runs BASELINE
-configs[1]: SlateRecEnv-v0, batch 4096, PPO discrete (mask policy rollout + SGD pass), synthetic
-283-item catalog, synthetic log/weights of the dataset's shape (no dataset/checkpoint offline).
+over `batch_per_gpu` env rows per GPU = batch x max_steps transitions.
+
+Workloads (BASELINE.json configs; defaults give configs[1] at N = 1 and the north-star point at N = 8):
+  default            SlateRecEnv-v0, PPO discrete; batch/GPU 4096 at N = 1 (configs[1]), 8192 at N > 1
+                     (N = 8: global batch 65 536, the north_star point)            -- override with --batch-per-gpu
+  --env seqslate --algo a2c --batch-per-gpu 16384      configs[2]  SeqSlateRecEnv-v0 A2C, 3 pages
+  --conti --gpus 4                                     configs[3]  continuous actions + masked kNN, 4 x 8192
+  --env seqslate --gpus 8                              configs[4]  SeqSlateRecEnv-v0 PPO, 8 x 8192
 
 JSON keys beyond the base contract:
-  value     one PPO iteration, device-resident: masked SoftQ rollout of a vector episode (policy + env on the GPU)
-            followed by the minibatch-256 SGD pass, all hand-written kernels; nothing crosses PCIe in the timed
-            region except 16 KB of row indices per reset and the 144 KB minibatch permutation.
-  env_only  the same rollout without the SGD pass.
+  value     one training iteration, device-resident: SoftQ rollout of a vector episode (policy + env on the GPU)
+            followed by the learner pass (PPO: minibatch SGD epoch; A2C: one step), all hand-written kernels; for
+            N > 1 the gradient exchange is the library's own peer-memory kernel (NCCL only as a fallback).
+            --conti has no learner in scope (the reference's continuous-action learners are DDPG/TD3): value is the
+            rollout with behaviour-policy embeddings + noise through the masked kNN.
+  env_only  the same rollout without the learner pass.
   e2e       the reference-facing call with HOST buffers: README.md:14-21 loop, numpy actions in,
             numpy obs/mask/reward out, every copy inside the timed region.
-  roofline  the dominant kernel: the tcgen05 AUGRU recurrence -- k_augru_pair (2-CTA tcgen05.mma.cta_group::2) for the
-            observation passes, k_augru_tc for the multi-wave reward pass, one profile slot for both -- timed live
-            with CUDA events on the launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
-            2*(256*512 + 256*256) against the measured bf16 GEMM peak.
+  roofline  the dominant kernel: the tcgen05 AUGRU recurrence (k_augru_pair2 / k_augru_tc, one profile slot), timed
+            live with CUDA events on the launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
+            2*(256*512 + 256*256) against the measured sustained bf16 GEMM peak.
+  hbm_8d    SURVEY.md section 8(d)'s own HBM figure: transitions/s x algorithmic bytes per transition
+            (176 768 B Slate-9, 170 565 B Seq-27) / (N x measured HBM peak), for `value` and `env_only`.
   cpu_baseline  the oracle port (oracle/env_np.py + dien_np.py) on this box's host cores, bounded sample.
 """
 import argparse
@@ -29,7 +37,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -40,14 +47,19 @@ if ROOT not in sys.path:
 
 METRIC = "env transitions/sec (SlateRecEnv-v0, batch x steps)"
 UNIT = "transitions/s"
+BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}
+CPU_THREADS = 16                                                # BLAS threads of the CPU arm (fixed: run-to-run spread)
 
 
-def base_config(B, seq=False, max_steps=None):
-    return {"epoch": 1, "maxlen": 64, "batch_size": B, "action_size": 284, "class_num": 2,
-            "dense_feature_num": 432, "category_feature_num": 21, "category_hash_size": 100000,
-            "seq_num": 2, "emb_size": 128, "hidden_units": 128, "page_items": 9,
-            "max_steps": max_steps or (27 if seq else 9), "action_emb_size": 32,
-            "is_eval": False, "cache_size": 2048, "support_rllib_mask": True}
+def base_config(B, seq=False, max_steps=None, conti=False):
+    cfg = {"epoch": 1, "maxlen": 64, "batch_size": B, "action_size": 284, "class_num": 2,
+           "dense_feature_num": 432, "category_feature_num": 21, "category_hash_size": 100000,
+           "seq_num": 2, "emb_size": 128, "hidden_units": 128, "page_items": 9,
+           "max_steps": max_steps or (27 if seq else 9), "action_emb_size": 32,
+           "is_eval": False, "cache_size": 2048, "support_rllib_mask": True}
+    if conti:
+        cfg["support_conti_env"] = True
+    return cfg
 
 
 def load_peaks():
@@ -107,32 +119,69 @@ class ClockSampler(object):
         return out
 
 
-def cpu_reference_episode(B, seq, log, catalog, weights, episodes, warmup):
-    """The reference's CPU path (oracle port, all host threads NumPy/OpenBLAS can use): offline-action
-    replay episodes of B rows.  Returns (transitions/s, seconds, cores)."""
+class _TimedDien(object):
+    """Wraps the oracle's network so the CPU arm can report its host-Python vs NN split."""
+
+    def __init__(self, dien):
+        self.d, self.nn_s = dien, 0.0
+
+    def _t(self, fn, feat):
+        t0 = time.perf_counter()
+        out = fn(feat)
+        self.nn_s += time.perf_counter() - t0
+        return out
+
+    def obs_layer(self, feat):
+        return self._t(self.d.obs_layer, feat)
+
+    def reward_layer(self, feat):
+        return self._t(self.d.reward_layer, feat)
+
+
+def cpu_reference_episodes(B, seq, log, catalog, weights, episodes, warmup, threads=CPU_THREADS):
+    """The reference's CPU path (oracle port; NumPy/OpenBLAS pinned to `threads` threads): offline-action replay
+    episodes of B rows.  -> dict(value tr/s from the MEDIAN episode, per-episode times, NN share, threads)."""
     from oracle.dien_np import DienOracle
     from oracle.env_np import OracleEnv
+    try:
+        from threadpoolctl import threadpool_limits
+    except Exception:
+        threadpool_limits = None
     cfg = dict(base_config(B, seq), is_eval=False, cache_size=min(2048, log.n))
-    np.random.seed(0)
-    env = OracleEnv(cfg, log, catalog, DienOracle(weights, np.float32), seq=seq)
+    threads = max(1, min(threads, os.cpu_count() or 1))
     T = cfg["max_steps"]
 
-    def episode():
-        env.reset()
-        for _ in range(T):
-            env.step(env.offline_action)
+    def run():
+        np.random.seed(0)
+        net = _TimedDien(DienOracle(weights, np.float32))
+        env = OracleEnv(cfg, log, catalog, net, seq=seq)
+        times, nn = [], []
+        for ep in range(warmup + episodes):
+            net.nn_s = 0.0
+            t0 = time.perf_counter()
+            env.reset()
+            for _ in range(T):
+                env.step(env.offline_action)
+            if ep >= warmup:
+                times.append(time.perf_counter() - t0)
+                nn.append(net.nn_s)
+        return times, nn
 
-    for _ in range(warmup):
-        episode()
-    t0 = time.perf_counter()
-    for _ in range(episodes):
-        episode()
-    dt = time.perf_counter() - t0
-    return B * T * episodes / dt, dt, os.cpu_count()
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=threads):
+            times, nn = run()
+    else:
+        times, nn = run()
+    med = float(np.median(times))
+    return {"value": B * T / med, "episode_s": [round(t, 3) for t in times], "median_s": med, "total_s": float(sum(times)),
+            "spread": float((max(times) - min(times)) / med) if med > 0 else 0.0,
+            "nn_share": float(sum(nn) / max(sum(times), 1e-9)), "threads": threads, "host_cores": os.cpu_count(),
+            "transitions_per_episode": B * T}
 
 
 def run_reference(args):
-    """--impl reference: the oracle port of the reference's CPU env, bounded sample per step."""
+    """--impl reference: the oracle port of the reference's CPU env; one step = one episode of a bounded row sample.
+    Also reports BASELINE configs[0] itself (batch 32, the README loop) over 3 episodes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -142,28 +191,43 @@ def run_reference(args):
     cat = synth.make_catalog()
     log = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=cat)
     w = synth.make_weights(base_config(Bs, seq))
-    tps, dt, cores = cpu_reference_episode(Bs, seq, log, cat, w, args.steps, args.warmup)
+    r = cpu_reference_episodes(Bs, seq, log, cat, w, max(args.steps, 1), max(args.warmup, 1))
+    c1 = cpu_reference_episodes(32, seq, log, cat, w, 3, 1)
     T = base_config(Bs, seq)["max_steps"]
-    sample = "%d of %d env rows per step (one offline-action replay episode, %d transitions)" % (Bs, args.batch_per_gpu, Bs * T)
-    line = {"impl": "reference", "metric": METRIC, "value": tps, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+    sample = ("%d of %d env rows per step (one offline-action replay episode = %d transitions); median of %d episodes, "
+              "spread (max-min)/median %.2f, NN share of the time %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"
+              % (Bs, args.batch_per_gpu, Bs * T, len(r["episode_s"]), r["spread"], r["nn_share"], r["threads"], r["host_cores"]))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["median_s"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, seq),
-            "cpu_baseline": {"value": tps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": tps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
+                             "episode_s": r["episode_s"], "nn_share": r["nn_share"],
+                             "configs0_batch32": {"value": c1["value"], "episode_s": c1["episode_s"], "nn_share": c1["nn_share"]}},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
 def workload_config(args, seq):
     T = 27 if seq else 9
-    return {"workload": "%s batch=%d/GPU x max_steps=%d, PPO discrete (MyMaskActionsModel, SoftQ T=1 rollout + "
-                        "minibatch-256 SGD pass per episode), DIEN simulator, synthetic 283-item catalog + "
-                        "synthetic log (seed 1234) + synthetic weights (seed 4321)"
-                        % ("SeqSlateRecEnv-v0" if seq else "SlateRecEnv-v0", args.batch_per_gpu, T),
+    env = "SeqSlateRecEnv-v0" if seq else "SlateRecEnv-v0"
+    if args.conti:
+        learner = "continuous actions (behaviour-policy embeddings + N(0, 0.3) noise) through the masked kNN; no learner pass"
+    elif args.algo == "a2c":
+        learner = "A2C (MyMaskActionsModel, SoftQ T=1 rollout + one summed-loss step, grad clip 10)"
+    else:
+        learner = ("PPO discrete (MyMaskActionsModel, SoftQ T=1 rollout + one SGD epoch, sgd_minibatch_size %d TOTAL = %d per GPU)"
+                   % (args.sgd_minibatch, args.sgd_minibatch // max(args.gpus, 1)))
+    return {"workload": "%s batch=%d/GPU x max_steps=%d, %s, DIEN simulator, synthetic 283-item catalog + synthetic log "
+                        "(seed 1234) + synthetic weights (seed 4321)" % (env, args.batch_per_gpu, T, learner),
             "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * args.gpus,
-            "max_steps": T, "simulator": "dien", "category_hash_size": 100000,
+            "max_steps": T, "simulator": "dien", "algo": "none" if args.conti else args.algo,
+            "sgd_minibatch_size_total": None if (args.conti or args.algo != "ppo") else args.sgd_minibatch,
+            "category_hash_size": 100000,
             "parallelism": "env rows sharded by contiguous blocks, dp%d, no data-path collective" % args.gpus,
+            "per_n_defaults": "batch/GPU 4096 at N=1 (BASELINE configs[1]), 8192 at N>1 (N=8: north_star global batch 65 536); "
+                              "PPO sgd_minibatch_size 256 x N so that an iteration is 144 x (batch/4096) optimizer steps at every N",
             "l2": "per-step working set (AUGRU input-projection cache ~0.21 MB/row, 0.87 GB at batch 4096) "
                   "exceeds the 126 MB L2; no explicit flush"}
 
@@ -185,11 +249,21 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--env", default="slate", choices=["slate", "seqslate"])
-    ap.add_argument("--batch-per-gpu", type=int, default=4096)
+    ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c"])
+    ap.add_argument("--conti", action="store_true", help="continuous actions + masked kNN (BASELINE configs[3]); no learner")
+    ap.add_argument("--batch-per-gpu", type=int, default=None, help="default: 4096 at N=1, 8192 at N>1")
+    ap.add_argument("--sgd-minibatch", type=int, default=None, help="PPO sgd_minibatch_size, TOTAL over GPUs (default 256 x N)")
     ap.add_argument("--cpu-sample-rows", type=int, default=128)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", help="also print a per-kernel time breakdown (stderr)")
     args = ap.parse_args()
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1:
+        args.gpus = world_env
+    if args.batch_per_gpu is None:
+        args.batch_per_gpu = 4096 if args.gpus == 1 else 8192
+    if args.sgd_minibatch is None:
+        args.sgd_minibatch = 256 * args.gpus
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
@@ -202,20 +276,18 @@ def main():
     from rl4rs_b200 import synth, gymshim
     from rl4rs_b200.env.slate import SlateRecEnv, SlateState
     from rl4rs_b200.env.seqslate import SeqSlateRecEnv, SeqSlateState
-    from rl4rs_b200.trainer import PPOTrainer
+    from rl4rs_b200.trainer import PPOTrainer, A2CTrainer
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus and world > 1:
-        args.gpus = world
+    world = world_env
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     seq = args.env == "seqslate"
     B = args.batch_per_gpu
-    cfg = base_config(B, seq)
+    cfg = base_config(B, seq, conti=args.conti)
     T = cfg["max_steps"]
     catalog = synth.make_catalog()
     # the log is generated once from the single seed; rank r samples from its own slice of it
@@ -231,15 +303,25 @@ def main():
     env = make("torch")
     env.seed(rank)
     eng = env.sim.engine
-    trainer = PPOTrainer({}, env, seed=0)      # modelfree_train.py:179-217 hyper-parameters
+    trainer, learner_launches = None, (lambda: 0)
+    if args.conti:
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
 
-    def episode_device():
-        # one PPO iteration: device-resident rollout of a vector episode (masked SoftQ sampling) +
-        # the SGD pass (minibatch 256, 1 epoch) with the flat-gradient all-reduce when N > 1
-        return trainer.train()
+        def rollout_conti():
+            env.reset()
+            for _ in range(T):
+                a = env.offline_action                                  # logged items' embeddings, f64 [B, 32] on the device
+                a = a + 0.3 * torch.randn(a.shape, generator=gen, device=dev, dtype=a.dtype)
+                obs, reward, done, info = env.step(a)
+            return reward
 
-    def episode_env_only():
-        return trainer.rollout(explore=True)
+        episode_device = episode_env_only = rollout_conti
+    else:
+        trainer = (PPOTrainer({"sgd_minibatch_size": args.sgd_minibatch}, env, seed=0) if args.algo == "ppo"
+                   else A2CTrainer({}, env, seed=0))                     # modelfree_train.py:179-217 / :248-304
+        learner_launches = lambda: trainer.ops.launches
+        episode_device = trainer.train                                   # rollout + learner pass
+        episode_env_only = lambda: trainer.rollout(explore=True)
 
     def barrier():
         if world > 1:
@@ -261,7 +343,7 @@ def main():
 
     for _ in range(args.warmup):
         episode_device()
-    launches0 = eng.launch_count() + trainer.ops.launches
+    launches0 = eng.launch_count() + learner_launches()
     eng.profile(1)
     clocks = ClockSampler(local_rank)
     if rank == 0:
@@ -270,7 +352,7 @@ def main():
     clk = clocks.stop() if rank == 0 else None
     prof = eng.profile_read()
     eng.profile(0)
-    gpu_launches = eng.launch_count() + trainer.ops.launches - launches0   # env kernels + policy/learner kernels
+    gpu_launches = eng.launch_count() + learner_launches() - launches0   # env kernels + policy/learner kernels
     value = B * world * T * args.steps / (ms / 1e3)
     ms_env = timed(episode_env_only, args.steps)
     env_only = B * world * T * args.steps / (ms_env / 1e3)
@@ -282,7 +364,7 @@ def main():
     def episode_host():
         obs = env_h.reset()
         for _ in range(T):
-            a = env_h.offline_action                      # numpy int (D2H) -- the logged policy
+            a = env_h.offline_action                      # numpy (D2H) -- the logged policy (ids, or embeddings with --conti)
             obs, reward, done, info = env_h.step(a)       # H2D actions, D2H obs + mask + reward
         return reward
 
@@ -290,8 +372,9 @@ def main():
         episode_host()
     ms_h = timed(episode_host, args.steps)
     e2e = B * world * T * args.steps / (ms_h / 1e3)
-    h2d = B * 4 + T * B * 4
-    d2h = (T + 1) * (B * 256 * 4 + B * 284) + T * (B * 8 + B * 4)
+    act_bytes = B * 32 * 8 if args.conti else B * 4
+    h2d = B * 4 + T * act_bytes
+    d2h = (T + 1) * (B * 256 * 4 + B * 284) + T * (B * 8 + act_bytes)
 
     # ---- per-kernel breakdown (untimed extra episode) -------------------------------------------
     kernels = None
@@ -306,28 +389,35 @@ def main():
             for k in sorted(kernels, key=lambda k: -k["ms"]):
                 sys.stderr.write("%-44s %9.3f ms %5.1f%%  launches %d\n" % (k["name"], k["ms"], 100 * k["ms"] / tot, k["launches"]))
 
+    exchange = None
+    if trainer is not None and world > 1:
+        exchange = "peer-memory kernel (r4_comm)" if (trainer.comm is not None and trainer.comm.ok) else "nccl all_reduce per step (fallback: %s)" % (trainer.comm.why if trainer.comm else "no kernels")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     peaks = load_peaks()
-    au = [p for p in prof if p["name"].startswith("k_augru_tc")]
+    au = [p for p in prof if p["name"].startswith("k_augru")]
     roofline = None
     if au:
         au = au[0]
         achieved = au["work"] / (au["ms"] / 1e3) / 1e12
         peak = peaks["bf16_tflops_sustained"]
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "augru_traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-        roofline = {"kernel": "AUGRU recurrence, tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators: k_augru_pair "
-                              "(cta_group::2, observation passes) + k_augru_tc (reward pass)",
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        roofline = {"kernel": "AUGRU recurrence, tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators: k_augru_pair2 "
+                              "(cta_group::2) / k_augru_tc, chosen per launch by r4_augru_kernel_for",
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": traffic_src or "profiles/augru_traffic.json (ncu --set full capture of an observation-pass launch, committed; not re-measured in this run)",
                     "peak_source": "%s bf16 GEMM, sustained (kernel timed inside a long step)" % peaks["source"],
                     "launches": au["launches"], "avg_launch_ms": au["ms"] / au["launches"],
                     "share_of_step": au["ms"] / ms}
+    bpt = BYTES_PER_TRANSITION.get(T, 176768)
+    hbm = peaks["hbm_gbs"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -336,28 +426,28 @@ def main():
                     "ms_per_step": ms_h / args.steps,
                     "loop": "README.md:14-21: action = env.offline_action; env.step(action); numpy in/out"},
             "gpu_launches": gpu_launches, "roofline": roofline,
+            "hbm_8d": {"bound": "hbm", "bytes_per_transition": bpt, "peak": hbm, "unit": "GB/s", "n_gpus": world,
+                       "achieved_value": value * bpt / 1e9, "frac_value": value * bpt / 1e9 / (world * hbm),
+                       "achieved_env_only": env_only * bpt / 1e9, "frac_env_only": env_only * bpt / 1e9 / (world * hbm),
+                       "note": "SURVEY.md 8(d): transitions/s x algorithmic bytes per transition / (N x measured HBM peak); the DIEN "
+                               "simulator is tensor-bound (111.5 MFLOP per row-forward), so this fraction is small by construction"},
             "env_only": {"value": env_only, "unit": UNIT, "ms_per_step": ms_env / args.steps,
-                         "note": "same rollout without the PPO SGD pass (policy sampling still on the GPU)"}}
+                         "note": "same rollout without the learner pass (policy sampling still on the GPU)"}}
+    if exchange:
+        line["gradient_exchange"] = exchange
     if kernels:
         tot = sum(k["ms"] for k in kernels)
         line["kernels"] = [{"name": k["name"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 4),
                             "launches": k["launches"]} for k in sorted(kernels, key=lambda k: -k["ms"])]
-        # feature-gather path against the HBM roofline (G = 83 732 B / row-forward)
-        gk = [k for k in kernels if k["name"] in ("k_scores_tc", "k_cat_attn", "k_assemble")]
-        if gk:
-            rows = (T + 1) * B + B * T           # obs rows + reward rows of one episode
-            gms = sum(k["ms"] for k in gk)
-            gb = rows * 83732 / (gms / 1e3) / 1e9
-            line["roofline_gather"] = {"kernels": [k["name"] for k in gk], "bound": "hbm", "achieved": gb,
-                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gb / peaks["hbm_gbs"],
-                                       "bytes_per_row_forward": 83732, "rows": rows, "ms": gms}
     if world == 1 and not args.no_cpu_baseline:
         Bs = args.cpu_sample_rows
         clog = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=catalog)
-        tps, dt, cores = cpu_reference_episode(Bs, seq, clog, catalog, weights, episodes=2, warmup=1)
-        line["cpu_baseline"] = {"value": tps, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "2 offline-replay episodes of %d env rows (%d transitions), %.1f s, "
-                                          "NumPy/OpenBLAS threads" % (Bs, 2 * Bs * T, dt)}
+        r = cpu_reference_episodes(Bs, seq, clog, catalog, weights, episodes=3, warmup=1)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                "sample": "median of 3 offline-replay episodes of %d env rows (%d transitions each) after 1 warm-up, "
+                                          "%.1f s, spread %.2f, NN share %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"
+                                          % (Bs, Bs * T, r["total_s"], r["spread"], r["nn_share"], r["threads"], r["host_cores"]),
+                                "episode_s": r["episode_s"], "nn_share": r["nn_share"]}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -193,6 +193,38 @@ int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int
                  float* v, int step0, float lr, float beta1, float beta2, float eps, float grad_clip,
                  float* norm_scratch, void* stream);
 
+/* ---- data-parallel learner: gradient exchange over NVLink peer memory (no reference counterpart:
+ * the reference's multi-worker path is Ray's object store, modelfree_train.py:181,403-405) ----------------------
+ * One communicator per rank (= process = GPU).  r4_comm_create allocates this rank's inbox + flags on the CURRENT
+ * device; r4_comm_handle exports it (64 bytes = cudaIpcMemHandle_t) for the caller to all-gather by any means
+ * (torch.distributed here); r4_comm_open maps every peer's allocation (handles in rank order, world x 64 bytes).
+ * After that the SGD steps of an epoch need no host-side collective: r4_ppo_epoch_dist enqueues, per minibatch,
+ * the gradient kernel and ONE kernel that reduces the local partials, pushes them into every rank's inbox, waits
+ * for the peers' flags, sums in rank order and applies Adam (replicas stay bit-identical).  Every rank must call
+ * it with the same n, mb and hyper-parameters.  mb = minibatch size PER RANK; the loss is the mean over
+ * mb x world samples (RLlib: sgd_minibatch_size is the total over devices). */
+typedef struct r4_comm r4_comm;
+int r4_comm_create(int rank, int world, int n_params, r4_comm** out);
+int r4_comm_handle(r4_comm* comm, void* handle_out_64);
+int r4_comm_open(r4_comm* comm, const void* handles, int n_handles);
+void r4_comm_destroy(r4_comm* comm);
+int r4_ppo_epoch_dist(r4_comm* comm, float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                      const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                      const float* target, const int64_t* perm, int n, int mb, int action_size, float clip,
+                      float vf_clip, float vf_coeff, float kl_coeff, float ent_coeff, float* scratch, float* flat_grad,
+                      float* stats_accum, float* m, float* v, int step0, float lr, float beta1, float beta2, float eps,
+                      void* stream);
+/* The exchange alone: partial gradients of ONE r4_policy_grad-style launch (scratch, G as there; the caller ran the
+ * gradient kernel through r4_policy_grad_partial) -> flat_grad = sum over ranks (A2C: global-norm clipping and Adam
+ * follow through r4_adam_step). */
+int r4_policy_grad_partial(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                           const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                           const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                           float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                           void* stream);
+int r4_grad_exchange(r4_comm* comm, const float* scratch, int G, int action_size, float* flat_grad, float* stats_accum,
+                     float stat_scale, void* stream);
+
 /* ---- the simulator alone (nets/dien.py:8-45), for parity tests and kernel benchmarks ------- */
 /* seq i32[R,2,64], dense f32[R,432], cat i32[R,21] (device) -> obs f32[R,256], probs f32[R,2]
  * (either may be NULL).  Runs the uncached path: GRU-1 is recomputed for every row. */

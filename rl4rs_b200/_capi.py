@@ -58,6 +58,15 @@ EXPORTS = {
                        [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "r4_ppo_epoch": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 3 + [C.c_float] * 5 + [C.c_void_p] * 5 + [C.c_int] +
                      [C.c_float] * 5 + [C.c_void_p, C.c_void_p]),
+    "r4_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "r4_comm_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r4_comm_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "r4_comm_destroy": (None, [C.c_void_p]),
+    "r4_ppo_epoch_dist": (C.c_int, [C.c_void_p] * 11 + [C.c_int] * 3 + [C.c_float] * 5 + [C.c_void_p] * 5 + [C.c_int] +
+                          [C.c_float] * 4 + [C.c_void_p]),
+    "r4_policy_grad_partial": (C.c_int, [C.c_int] + [C.c_void_p] * 10 + [C.c_int, C.c_int] + [C.c_float] * 6 +
+                               [C.c_void_p, C.c_int, C.c_void_p]),
+    "r4_grad_exchange": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "r4_adam_step": (C.c_int, [C.c_void_p] * 4 + [C.c_int, C.c_int] + [C.c_float] * 6 + [C.c_void_p, C.c_void_p]),
     "r4_dien_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
 }

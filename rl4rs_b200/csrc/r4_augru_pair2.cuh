@@ -255,7 +255,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
     const bool valid = r < p.R;
     if (!valid) r = p.R - 1;
     const int ci = S.shared ? 0 : (p.row0 + r) / p.div;
-    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM + (ci % TM);
+    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM;
+    const int ln4 = (ci % TM) * 4;
     const float* st = S.scoresT + ((size_t)(m0 / TM) * STEPS) * TM + prow;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row_off = (uint32_t)(rl / 8) * A_SBO + (uint32_t)(rl % 8) * 16;
@@ -275,7 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
       if (local_arrive) { mbar_arrive(&bar_h0); mbar_arrive(&bar_h1); }
       else { arrive_cl_relaxed(bar_h0_leader); arrive_cl_relaxed(bar_h1_leader); }
     }
-#define R4P2_LOADX(dst, base, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg((base) + (size_t)((colbase) + j) * TM)
+#define R4P2_LOADX(dst, base, colbase) load_x16(dst, (base), (colbase), ln4)
     // rolling input buffer: x[ch] always holds chunk ch of the NEXT phase to run (here: the r gate of step 0)
 #pragma unroll
     for (int c4 = 0; c4 < 4; ++c4) { R4P2_LOADX(x[c4], xt, hc0 + c4 * 16); }
@@ -293,8 +294,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         const float* xn = S.XT + (((size_t)(ci / TM) * STEPS + (t + 1)) * XT_COLS) * TM;
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          const int id = i * 256 + tid;                    // 1536 lines: (column, 32-lane group of this CTA)
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(id >> 1) * TM + (rank * 2 + (id & 1)) * 32));
+          const int id = i * 256 + tid;                    // 1536 lines: (column quad, 8 lines of this CTA's 64 lanes x 16 B)
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(id >> 3) * 4 * TM + rank * (P_RC * 4) + (id & 7) * 32));
         }
       }
       // ---- phase R (overlaps the u MMAs): r*h -> its own A operand; x[] <- the u gate's inputs ----

@@ -123,8 +123,18 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// 16 consecutive columns (colbase % 16 == 0) of one lane of a lane-major tile-step in the quad layout
+// [col / 4][lane][col % 4] (r4_gemm_tc.cuh: xt_index): four 128-bit loads.  `ts` = tile-step base, `ln4` = lane * 4.
+__device__ __forceinline__ void load_x16(float* dst, const float* ts, int colbase, int ln4) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(ts + (size_t)(colbase + 4 * g) * TM + ln4));
+    dst[4 * g] = v.x; dst[4 * g + 1] = v.y; dst[4 * g + 2] = v.z; dst[4 * g + 3] = v.w;
+  }
+}
+
 struct AugruTcSeq {
-  const float* XT;        // transposed input halves [n_tiles_cached, 64, 768, 128]  (tile, step, column, lane)
+  const float* XT;        // transposed input halves [n_tiles_cached, 64, 768 / 4, 128, 4]  (tile, step, column quad, lane, column % 4)
   const uint8_t* Wimg;    // pre-tiled bf16 hi/lo weight image, W_IMAGE_BYTES, stream order u, r, c
   const float* scoresT;   // [n_row_tiles, 64, 128]
   float* out;             // final state, row stride out_ld
@@ -243,7 +253,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {
     const bool valid = r < p.R;
     if (!valid) r = p.R - 1;
     const int ci = S.shared ? 0 : (p.row0 + r) / p.div;
-    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM + (ci % TM);
+    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM;
+    const int ln4 = (ci % TM) * 4;
     const float* st = S.scoresT + ((size_t)((m0 + row) / TM) * STEPS) * TM + row;   // this CTA's tile
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row_off = (uint32_t)(row / 8) * A_SBO + (uint32_t)(row % 8) * 16;
@@ -274,7 +285,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {
       }
       // Each phase walks its 128 columns in 8 chunks of 16 with a 2-deep software pipeline: the TMEM
       // load and the coalesced X loads of chunk ch+1 are in flight while chunk ch is computed.
-#define R4_LOADX(dst, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg(xs + (size_t)((colbase) + j) * TM)
+#define R4_LOADX(dst, colbase) load_x16(dst, xs, (colbase), ln4)
       // ---- phase U: u' = (1 - s) sigmoid(acc_u + Xu) -> back into TMEM ----
       {
         float x[2][16], a[2][16];

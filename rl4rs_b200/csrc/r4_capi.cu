@@ -9,6 +9,7 @@
 #include "r4_scores_tc.cuh"
 #include "r4_gru_tc.cuh"
 #include "r4_ppo.cuh"
+#include "r4_comm.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -231,7 +232,7 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
 struct AugruOpts {
   int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel
   int pair_impl = 1;      // 1 = k_augru_pair2<R4P2_RELAY, R4P2_TMAP>, 2..4 = <0,1> <1,0> <0,0>
-  int cost_single = 3, cost_pair = 2;   // per-wave cost ratio, measured
+  int cost_single = 15, cost_pair = 8;  // per-wave cost ratio, measured: 1.19 ms (k_augru_tc) : 0.64 ms (k_augru_pair2<1,1>), tools/augru_probe.cu
   AugruOpts() {
     if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2;
     if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
@@ -478,7 +479,6 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
@@ -962,6 +962,135 @@ int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int
       rc = r4_adam_step(params, flat_grad, m, v, np, step0 + steps + 1, lr, beta1, beta2, eps, 1.0f, grad_clip, norm_scratch, stream);
       if (rc) return rc;
     }
+  }
+  return steps;
+}
+
+// ---- data-parallel learner: peer-memory gradient exchange (r4_comm.cuh) -------------------------------------
+}  // extern "C"
+
+struct r4_comm {
+  int rank = 0, world = 1, n = 0, nblk = 0, device = 0;
+  void* base = nullptr;
+  size_t inbox_bytes = 0, bytes = 0;
+  r4comm::Peers peers{};
+  std::vector<void*> opened;
+  uint32_t seq = 0;
+  bool ready = false;
+};
+
+extern "C" {
+
+int r4_comm_create(int rank, int world, int n_params, r4_comm** out) {
+  if (!out || world < 1 || world > r4comm::MAX_WORLD || rank < 0 || rank >= world || n_params < 1)
+    return fail(nullptr, R4_ERR_ARG, "r4_comm_create: bad argument (world <= 16)");
+  *out = nullptr;
+  r4_comm* c = new r4_comm();
+  c->rank = rank; c->world = world; c->n = n_params; c->nblk = (n_params + r4comm::BLK - 1) / r4comm::BLK;
+  cudaGetDevice(&c->device);
+  c->inbox_bytes = (((size_t)2 * world * n_params * 4) + 255) & ~(size_t)255;
+  c->bytes = c->inbox_bytes + (size_t)2 * world * c->nblk * 4;
+  cudaError_t st = cudaMalloc(&c->base, c->bytes);
+  if (st == cudaSuccess) st = cudaMemset(c->base, 0, c->bytes);
+  if (st == cudaSuccess) st = cudaDeviceSynchronize();
+  if (st != cudaSuccess) { if (c->base) cudaFree(c->base); delete c; return fail(nullptr, R4_ERR_CUDA, std::string("r4_comm_create: ") + cudaGetErrorString(st)); }
+  c->peers.inbox[rank] = reinterpret_cast<float*>(c->base);
+  c->peers.flags[rank] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(c->base) + c->inbox_bytes);
+  c->ready = world == 1;
+  *out = c;
+  return R4_OK;
+}
+
+int r4_comm_handle(r4_comm* c, void* handle_out_64) {
+  if (!c || !handle_out_64) return fail(nullptr, R4_ERR_ARG, "r4_comm_handle: null argument");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  cudaError_t st = cudaIpcGetMemHandle(&h, c->base);
+  if (st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(st));
+  memcpy(handle_out_64, &h, 64);
+  return R4_OK;
+}
+
+int r4_comm_open(r4_comm* c, const void* handles, int n_handles) {
+  if (!c || !handles || n_handles != c->world) return fail(nullptr, R4_ERR_ARG, "r4_comm_open: need one handle per rank");
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->world; ++r) {
+    if (r == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, reinterpret_cast<const uint8_t*>(handles) + (size_t)r * 64, 64);
+    void* p = nullptr;
+    cudaError_t st = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (st != cudaSuccess) {
+      cudaGetLastError();
+      return fail(nullptr, R4_ERR_CUDA, std::string("cudaIpcOpenMemHandle(rank ") + std::to_string(r) + "): " + cudaGetErrorString(st));
+    }
+    c->opened.push_back(p);
+    c->peers.inbox[r] = reinterpret_cast<float*>(p);
+    c->peers.flags[r] = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(p) + c->inbox_bytes);
+  }
+  c->ready = true;
+  return R4_OK;
+}
+
+void r4_comm_destroy(r4_comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (void* p : c->opened) cudaIpcCloseMemHandle(p);
+  if (c->base) cudaFree(c->base);
+  delete c;
+}
+
+int r4_policy_grad_partial(int mode, const float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                           const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                           const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
+                           float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
+                           void* stream) {
+  return policy_grad_impl(mode, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, idx, n, action_size,
+                          clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv_n, scratch, G, scratch /*unused*/, nullptr, 0.f,
+                          stream, false);
+}
+
+static int exchange_launch(r4_comm* c, const float* scratch, int G, int np, float* flat, float* stats_accum, float stat_scale,
+                           int do_adam, float* params, float* m, float* v, int step, float lr, float b1, float b2, float eps,
+                           void* stream) {
+  if (!c->ready) return fail(nullptr, R4_ERR_STATE, "r4_comm: open the peers' handles first (r4_comm_open)");
+  if (np != c->n) return fail(nullptr, R4_ERR_ARG, "r4_comm: parameter count differs from the communicator's");
+  ++c->seq;
+  r4comm::k_exchange_adam<<<c->nblk, r4comm::BLK, 0, S(stream)>>>(np, G, scratch, flat, scratch + (size_t)G * np, stats_accum,
+                                                                  stat_scale, c->peers, c->rank, c->world, c->seq, do_adam,
+                                                                  params, m, v, step, lr, b1, b2, eps);
+  R4_PCHECK("k_exchange_adam");
+  return R4_OK;
+}
+
+int r4_grad_exchange(r4_comm* c, const float* scratch, int G, int action_size, float* flat_grad, float* stats_accum,
+                     float stat_scale, void* stream) {
+  if (!c || !scratch || !flat_grad || G < 1) return fail(nullptr, R4_ERR_ARG, "r4_grad_exchange: bad argument");
+  return exchange_launch(c, scratch, G, r4ppo::make_layout(action_size).n, flat_grad, stats_accum, stat_scale, 0, nullptr, nullptr,
+                         nullptr, 0, 0.f, 0.f, 0.f, 0.f, stream);
+}
+
+int r4_ppo_epoch_dist(r4_comm* c, float* params, const float* obs, const uint8_t* mask, const int64_t* action,
+                      const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
+                      const float* target, const int64_t* perm, int n, int mb, int action_size, float clip,
+                      float vf_clip, float vf_coeff, float kl_coeff, float ent_coeff, float* scratch, float* flat_grad,
+                      float* stats_accum, float* m, float* v, int step0, float lr, float beta1, float beta2, float eps,
+                      void* stream) {
+  if (!c || !params || !perm || !m || !v || !scratch || n < 1 || mb < 1 || mb > n || step0 < 0)
+    return fail(nullptr, R4_ERR_ARG, "r4_ppo_epoch_dist: bad argument");
+  const int G = std::max(1, std::min((mb + r4ppo::TS - 1) / r4ppo::TS, 148));
+  const int np = r4ppo::make_layout(action_size).n;
+  const float inv = 1.0f / ((float)mb * (float)c->world);
+  int steps = 0;
+  for (int s = 0; s + mb <= n; s += mb, ++steps) {
+    int rc = policy_grad_impl(0, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, perm + s, mb,
+                              action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv, scratch, G, scratch, nullptr, 0.f,
+                              stream, false);
+    if (rc) return rc;
+    rc = exchange_launch(c, scratch, G, np, flat_grad, stats_accum, inv, 1, params, m, v, step0 + steps + 1, lr, beta1, beta2,
+                         eps, stream);
+    if (rc) return rc;
   }
   return steps;
 }

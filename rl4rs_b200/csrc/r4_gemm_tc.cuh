@@ -67,6 +67,11 @@ inline void build_gemm_image(const float* W /*[K][N]*/, int K, int N, uint8_t* i
   }
 }
 
+// element (tile-step base, column, lane) of a lane-major tile, in floats; ld = columns per step
+__host__ __device__ __forceinline__ size_t xt_index(size_t tile_step, int ld, int col, int lane) {
+  return (tile_step * ld + (size_t)(col & ~3)) * TM + (size_t)lane * 4 + (col & 3);
+}
+
 struct GemmTcParams {
   const float* A; int lda; const int32_t* gather;
   const uint8_t* Wimg; const float* bias; float* C; int ldc;
@@ -76,6 +81,9 @@ struct GemmTcParams {
   // recurrent kernels read: columns < ldT -> outT[((nabs/128) * 64 + t) * ldT + col) * 128 + nabs % 128],
   // columns >= ldT -> outK[(nabs * 64 + t) * (N - ldT) + col - ldT], nabs = cr_base + n.  Consecutive threads are
   // consecutive sequences of one step, so both reads and transposed writes stay coalesced.
+  // Inside a tile-step the columns are grouped in QUADS, [col / 4][lane][col % 4] (xt_index below): a recurrent
+  // kernel's thread (= lane) reads 4 consecutive columns with ONE 128-bit load (ncu, round 2: with one 32-bit load per
+  // column the AUGRU epilogue spent 18 % of its cycles in lg_throttle, 192 LDGs per thread and step).
   int tm_ns, cr_base, ldT; float* outT; float* outK;
   int bnt = G_BNMAX;          // n-tile width of the weight image (build_gemm_image)
   long long* dbg = nullptr;   // development probe (tools/gemm_probe.cu): per-role wait/busy cycles of CTA 0
@@ -319,7 +327,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
         if (blk && n0 + c + 16 <= p.ldT) {
           float* ob = reinterpret_cast<float*>(outb + (nchunk % G_OUTB) * G_OUT_BYTES);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) ob[j * G_BM + row] = a[j];
+          for (int j4 = 0; j4 < 4; ++j4)      // [column quad][row][4]: the quad layout of the lane-major tiles
+            *reinterpret_cast<float4*>(ob + j4 * G_BM * 4 + row * 4) = make_float4(a[4 * j4], a[4 * j4 + 1], a[4 * j4 + 2], a[4 * j4 + 3]);
           long long e2 = probe ? clock64() : 0;
           proxy_fence();
           long long e3 = probe ? clock64() : 0;
@@ -339,7 +348,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + c + j;
-            if (col < p.ldT) p.outT[(((size_t)(nabs / TM) * STEPS + t) * p.ldT + col) * TM + (nabs % TM)] = a[j];
+            if (col < p.ldT) p.outT[xt_index((size_t)(nabs / TM) * STEPS + t, p.ldT, col, nabs % TM)] = a[j];
             else p.outK[((size_t)nabs * STEPS + t) * (p.N - p.ldT) + (col - p.ldT)] = a[j];
           }
         } else if (m < p.M) {

@@ -43,7 +43,7 @@ inline void build_gru_image(const float* Wg, const float* Wc, uint8_t* img) {
 }
 
 struct GruTcParams {
-  const float* XT;        // [ceil(n/128), 64, 384, 128]  input halves (+bias), lane-major tiles
+  const float* XT;        // [ceil(n/128), 64, 384 / 4, 128, 4]  input halves (+bias), lane-major tiles, quad layout
   const uint8_t* Wimg;    // G1_IMAGE_BYTES
   float* H;               // [n, 64, 128] outputs of every step
   int n;
@@ -151,7 +151,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
     int n = m0 + row;
     const bool valid = n < p.n;
     if (!valid) n = p.n - 1;
-    const float* xt = p.XT + ((size_t)(n / TM) * STEPS) * G1_XT_COLS * TM + (n % TM);
+    const float* xt = p.XT + ((size_t)(n / TM) * STEPS) * G1_XT_COLS * TM;
+    const int ln4 = (n % TM) * 4;
     float* hout = p.H + (size_t)n * STEPS * GH + c0;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row_off = (uint32_t)(row / 8) * G1_A_SBO + (uint32_t)(row % 8) * 16;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
     for (int t = 0; t < STEPS; ++t) {
       const uint32_t par = t & 1;
       const float* xs = xt + (size_t)t * G1_XT_COLS * TM;
-#define R4_LOADX(dst, colbase) _Pragma("unroll") for (int j = 0; j < 16; ++j) dst[j] = __ldg(xs + (size_t)((colbase) + j) * TM)
+#define R4_LOADX(dst, colbase) load_x16(dst, xs, (colbase), ln4)
       // ---- phase R: r*h -> its own operand buffer ----
       {
         float x[2][16], a[2][16];

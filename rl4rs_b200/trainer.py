@@ -86,12 +86,83 @@ class KernelOps(object):
         self.launches += rc * (4 if clip else 2)   # k_policy_grad + k_reduce_adam, or + k_grad_reduce, k_sumsq, k_adam
         return rc
 
+    def ppo_epoch_dist(self, comm, flat, data, perm, n, mb_local, hp, lr):
+        """All minibatch steps of one SGD epoch of a data-parallel learner in ONE library call: per step the gradient
+        kernel + the fused peer-memory exchange / Adam kernel (csrc/r4_comm.cuh); no NCCL, no host round trip."""
+        obs, mask, act, logp, logits, val, adv, target = data
+        rc = self.lib.r4_ppo_epoch_dist(comm.h, _p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv),
+                                        _p(target), _p(perm), n, mb_local, self.A, hp["clip"], hp["vf_clip"], hp["vf_coeff"],
+                                        hp["kl_coeff"], hp["ent_coeff"], _p(self.scratch), _p(self.grad), _p(self.stats),
+                                        _p(self.m), _p(self.v), self.step, lr, 0.9, 0.999, 1e-8, self._stream())
+        if rc < 0:
+            self._check(rc, "r4_ppo_epoch_dist")
+        self.step += rc
+        self.launches += rc * 2          # k_policy_grad + k_exchange_adam
+        return rc
+
+    def policy_grad_exchange(self, comm, mode, flat, data, n, hp, inv_n, stat_scale):
+        """One gradient over n local samples, summed over the ranks through peer memory into self.grad (A2C)."""
+        obs, mask, act, logp, logits, val, adv, target = data
+        G = max(1, min((n + 3) // 4, 148))
+        rc = self.lib.r4_policy_grad_partial(mode, _p(flat), _p(obs), _p(mask), _p(act), _p(logp), _p(logits), _p(val), _p(adv),
+                                             _p(target), C.c_void_p(0), n, self.A, hp["clip"], hp["vf_clip"], hp["vf_coeff"],
+                                             hp["kl_coeff"], hp["ent_coeff"], inv_n, _p(self.scratch), G, self._stream())
+        self._check(rc, "r4_policy_grad_partial")
+        rc = self.lib.r4_grad_exchange(comm.h, _p(self.scratch), G, self.A, _p(self.grad), _p(self.stats), stat_scale, self._stream())
+        self._check(rc, "r4_grad_exchange")
+        self.launches += 2
+
     def adam(self, flat, lr, grad_scale, clip):
         self.step += 1
         rc = self.lib.r4_adam_step(_p(flat), _p(self.grad), _p(self.m), _p(self.v), self.n, self.step, lr, 0.9, 0.999,
                                    1e-8, grad_scale, float(clip or 0.0), _p(self.norm), self._stream())
         self._check(rc, "r4_adam_step")
         self.launches += 2 if clip else 1
+
+class PeerComm(object):
+    """The learner's gradient exchange over NVLink peer memory (include/rl4rs_b200.h: r4_comm_*).  Every rank exports
+    its inbox with cudaIpcGetMemHandle; the 64-byte handles are all-gathered ONCE through torch.distributed; after that
+    the SGD steps use no host-side collective.  ``ok`` is False (on every rank) when peer mapping is not possible on this
+    box -- the trainer then keeps the NCCL all-reduce per step and says so."""
+
+    def __init__(self, n_params, device):
+        from . import _capi
+        self.lib = _capi.load_library()
+        self.h, self.ok, self.why = None, False, ""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2 or device.type != "cuda":
+            return
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if os.environ.get("R4_NO_PEER_COMM"):
+            self.why = "disabled by R4_NO_PEER_COMM"
+            return
+        h = C.c_void_p()
+        good = self.lib.r4_comm_create(rank, world, n_params, C.byref(h)) == 0
+        buf = (C.c_uint8 * 64)()
+        good = good and self.lib.r4_comm_handle(h, buf) == 0
+        mine = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        if good:
+            blob = torch.cat(every).cpu().numpy().tobytes()
+            good = self.lib.r4_comm_open(h, blob, world) == 0
+        if not good:
+            self.why = (self.lib.r4_last_error(None) or b"?").decode()
+        flag = torch.tensor([1 if good else 0], device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)            # all ranks take the same path
+        self.ok = bool(flag.item())
+        if self.ok:
+            self.h = h
+        elif h:
+            self.lib.r4_comm_destroy(h)
+        if not self.ok and rank == 0:
+            import sys
+            sys.stderr.write("rl4rs_b200: peer-memory gradient exchange unavailable (%s); using NCCL all-reduce per SGD step\n" % self.why)
+
+    def close(self):
+        if self.h:
+            self.lib.r4_comm_destroy(self.h)
+            self.h = None
+
 
 PPO_DEFAULTS = {"gamma": 1.0, "lambda": 1.0, "kl_coeff": 0.2, "sgd_minibatch_size": 256, "num_sgd_iter": 1,
                 "lr": 1e-4, "vf_loss_coeff": 0.5, "clip_param": 0.3, "vf_clip_param": 500.0, "kl_target": 0.01,
@@ -143,6 +214,7 @@ class _TrainerBase(object):
         self.use_kernels = self.device.type == "cuda" and (config or {}).get("use_kernels", True)
         self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
         self.ops = KernelOps(self.A, self.device, self.policy.n_params) if self.use_kernels else None
+        self.comm = PeerComm(self.policy.n_params, self.device) if self.use_kernels else None
         self._act_i32 = torch.zeros(self.B, dtype=torch.int32, device=self.device)
         # shared `seed` for the parameter init and the minibatch permutation; the exploration noise is per rank
         # (k_policy_act hashes seed ^ counter+row: the same seed would give rank r row i the noise of rank 0 row i)
@@ -187,12 +259,23 @@ class _TrainerBase(object):
             x /= _world()
         return float(x)
 
+    def _global_means(self, named):
+        """{name: 0-d tensor or float} -> {name: float mean over ranks}: ONE collective and ONE host synchronisation."""
+        keys = list(named)
+        x = torch.stack([torch.as_tensor(named[k], dtype=torch.float64, device=self.device).detach().reshape(()) for k in keys])
+        if _world() > 1:
+            dist.all_reduce(x, op=dist.ReduceOp.SUM)
+            x /= _world()
+        return dict(zip(keys, x.tolist()))
+
     def train(self):
         buf = self.rollout(explore=True)
         stats = self.learn(buf)
         self.iteration += 1
         self.timesteps_total += self.T * self.B * _world()
-        ep_rew = self._global_mean(buf.reward.sum(0).mean())
+        ep_rew = stats.pop("_episode_reward_mean", None)
+        if ep_rew is None:
+            ep_rew = self._global_mean(buf.reward.sum(0).mean())
         stats.update({"episode_reward_mean": ep_rew, "training_iteration": self.iteration,
                       "timesteps_this_iter": self.T * self.B * _world(), "timesteps_total": self.timesteps_total,
                       "episodes_this_iter": self.B * _world()})
@@ -299,10 +382,14 @@ class PPOTrainer(_TrainerBase):
         if _world() > 1:
             ms = torch.stack([mean, sq]); dist.all_reduce(ms); ms /= _world(); mean, sq = ms[0], ms[1]
         adv = (adv - mean) / torch.clamp((sq - mean ** 2).clamp_min(0).sqrt(), min=1e-4)
-        mb = min(c["sgd_minibatch_size"], n)
+        # RLlib: sgd_minibatch_size is the TOTAL over devices; every rank contributes sgd_minibatch_size / world samples
+        # of its own shard to each SGD step (multi-GPU tower semantics) and the loss is the mean over all of them
+        mb = min(max(c["sgd_minibatch_size"] // _world(), 1), n)
         data = (obs, mask, act, logp, logits, val, adv, target)
         agg, steps = (self._sgd_kernels if self.use_kernels else self._sgd_eager)(data, n, mb)
-        out = {k: self._global_mean(v / max(steps, 1)) for k, v in agg.items()}
+        named = {k: v / max(steps, 1) for k, v in agg.items()}
+        named["_episode_reward_mean"] = buf.reward.sum(0).mean()
+        out = self._global_means(named)
         # adaptive KL (RLlib KLCoeffMixin.update_kl)
         if out.get("kl", 0.0) > 2.0 * c["kl_target"]:
             self.kl_coeff *= 1.5
@@ -337,8 +424,9 @@ class PPOTrainer(_TrainerBase):
         return agg, steps
 
     def _sgd_kernels(self, data, n, mb):
-        """One launch pair per minibatch: r4_policy_grad (forward, RLlib surrogate loss, hand-derived backward,
-        deterministic reduction) + r4_adam_step; the flat-gradient all-reduce (N > 1) sits between them."""
+        """Per minibatch: the gradient kernel (forward, RLlib surrogate loss, hand-derived backward) and ONE kernel that
+        reduces, exchanges over peer memory (N > 1) and applies Adam -- the whole epoch is one library call
+        (r4_ppo_epoch / r4_ppo_epoch_dist).  Fallback without peer memory: NCCL all-reduce between two launches."""
         c = self.config
         ops = self.ops
         data = tuple(d.contiguous() for d in data)
@@ -351,6 +439,9 @@ class PPOTrainer(_TrainerBase):
             perm = self._perm(n, data[0].device).contiguous()
             if w == 1:
                 steps += ops.ppo_epoch(self.policy.flat, data, perm, n, mb, hp, c["lr"], c["grad_clip"])
+                continue
+            if self.comm is not None and self.comm.ok and not c["grad_clip"]:
+                steps += ops.ppo_epoch_dist(self.comm, self.policy.flat, data, perm, n, mb, hp, c["lr"])
                 continue
             for s in range(0, n - mb + 1, mb):
                 ops.policy_grad(0, self.policy.flat, data, perm, s, mb, hp, 1.0 / mb, 1.0 / mb)
@@ -396,16 +487,20 @@ class A2CTrainer(_TrainerBase):
                     flat(adv).contiguous(), flat(target).contiguous())
             hp = {"clip": 0.0, "vf_clip": 0.0, "vf_coeff": c["vf_loss_coeff"], "kl_coeff": 0.0, "ent_coeff": c["entropy_coeff"]}
             ops.stats.zero_()
-            ops.policy_grad(1, self.policy.flat, data, None, 0, n, hp, 1.0, 1.0)
-            if w > 1:
-                dist.all_reduce(ops.grad, op=dist.ReduceOp.SUM)                # summed loss over the global batch
+            if w > 1 and self.comm is not None and self.comm.ok:
+                ops.policy_grad_exchange(self.comm, 1, self.policy.flat, data, n, hp, 1.0, 1.0)   # summed over the ranks
+            else:
+                ops.policy_grad(1, self.policy.flat, data, None, 0, n, hp, 1.0, 1.0)
+                if w > 1:
+                    dist.all_reduce(ops.grad, op=dist.ReduceOp.SUM)            # summed loss over the global batch
             gn = ops.grad.norm()
             ops.adam(self.policy.flat, c["lr"], 1.0, c["grad_clip"])
             st = ops.stats
-            out = {"policy_loss": self._global_mean(st[0]) * w, "vf_loss": self._global_mean(st[1]) * w,
-                   "entropy": self._global_mean(st[3]) * w, "total_loss": self._global_mean(st[4]) * w,
-                   "grad_gnorm": float(gn), "sgd_steps": 1}
-            return out
+            g = self._global_means({"policy_loss": st[0], "vf_loss": st[1], "entropy": st[3], "total_loss": st[4], "gn": gn,
+                                    "_episode_reward_mean": buf.reward.sum(0).mean()})
+            return {"policy_loss": g["policy_loss"] * w, "vf_loss": g["vf_loss"] * w, "entropy": g["entropy"] * w,
+                    "total_loss": g["total_loss"] * w, "grad_gnorm": g["gn"], "sgd_steps": 1,
+                    "_episode_reward_mean": g["_episode_reward_mean"]}
         if self.policy.flat.grad is not None:
             self.policy.flat.grad.zero_()
         total, st = self.loss(flat(buf.obs), flat(buf.mask), flat(buf.action), flat(adv), flat(target))

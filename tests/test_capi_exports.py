@@ -67,15 +67,22 @@ def test_product_never_imports_oracle():
 
 def test_augru_kernel_choice_rule():
     """r4_augru_kernel_for: the 2-CTA pair kernel (2) exactly when the one-CTA kernel (1) would leave SMs idle.
-    B200 (148 SMs): a 4096-row observation pass = 64 tile-sequences -> pair; the 36 864-row reward pass = 576 ->
-    one-CTA kernel (4 waves against 8 pair waves); 8192-row passes = 128 -> one-CTA (1 wave against 2)."""
+    Measured wave times 1.19 ms (one-CTA) : 0.64 ms (pair), i.e. cost 15 : 8.  B200 (148 SMs): a 4096-row observation
+    pass = 64 tile-sequences -> pair; the 36 864-row reward pass = 576 -> one-CTA kernel (4 waves against 8 pair waves);
+    8192-row passes = 128 -> one-CTA (1 wave against 2)."""
     from rl4rs_b200 import _capi
     lib = _capi.load_library()
     f = lib.r4_augru_kernel_for
     assert f(64, 148) == 2 and f(2, 148) == 2 and f(74, 148) == 2
     assert f(576, 148) == 1 and f(128, 148) == 1 and f(148, 148) == 1
-    assert f(75, 148) == 1                       # 2 pair waves (1.5 units) against 1 single wave (1.13)
+    assert f(75, 148) == 1                       # 2 pair waves (16 units) against 1 single wave (15)
     assert f(0, 148) == 0 and f(64, 1) == 0      # bad arguments
-    for ctas in range(1, 1200, 7):               # never picks the slower one under the measured 2 : 3 wave-time ratio
+    for ctas in range(1, 1200, 7):               # never picks the slower one under the measured wave-time ratio
         ws, wp = -(-ctas // 148), -(-ctas // 74)
-        assert f(ctas, 148) == (1 if 3 * ws <= 2 * wp else 2)
+        assert f(ctas, 148) == (1 if 15 * ws <= 8 * wp else 2)
+    # r4_set_option: overrides are validated, and the rule follows the cost ratio it is given
+    assert lib.r4_set_option(b"augru_cost_single", 3) == 0 and lib.r4_set_option(b"augru_cost_pair", 1) == 0
+    assert f(576, 148) == 2
+    assert lib.r4_set_option(b"augru_cost_single", 15) == 0 and lib.r4_set_option(b"augru_cost_pair", 8) == 0
+    assert lib.r4_set_option(b"augru_kernel", 7) != 0 and lib.r4_set_option(b"no_such_key", 1) != 0
+    assert lib.r4_set_option(b"augru_kernel", 0) == 0

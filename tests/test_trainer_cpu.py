@@ -104,10 +104,10 @@ def _prepare(tr):
             tr.buf.logp[t].copy_(torch.log_softmax(logits, -1).gather(1, tr.buf.action[t].unsqueeze(1)).squeeze(1))
 
 
-def _worker(rank, world, algo, init_file, out_dir):
+def _worker(rank, world, algo, init_file, out_dir, mb=288):
     dist.init_process_group("gloo", init_method="file://" + init_file, rank=rank, world_size=world)
     per = 32 // world
-    tr = get_rl_model(algo, {"sgd_minibatch_size": 288 // world, "shuffle_sequences": False},
+    tr = get_rl_model(algo, {"sgd_minibatch_size": mb, "shuffle_sequences": False},      # the TOTAL over the ranks (RLlib)
                       env=FakeEnv(per), device="cpu")
     _fill(tr.buf, 7, rank * per, (rank + 1) * per)
     _prepare(tr)
@@ -141,4 +141,28 @@ def test_world_size_2_gloo_matches_single_learner(algo):
     # (Adam's first step is lr*sign(g): a coordinate whose gradient is ~0 may flip sign)
     big = g2.abs() > 1e-3 * g2.abs().max()
     assert torch.allclose(r0["flat"][big], single.policy.flat.detach()[big], atol=2e-6)
+    assert abs(r0["stats"]["total_loss"] - st["total_loss"]) <= 1e-4 * max(1.0, abs(st["total_loss"]))
+
+
+def test_world_size_2_minibatch_is_the_total_over_ranks():
+    """RLlib semantics (modelfree_train.py:197: "Total SGD batch size across all devices"): with sgd_minibatch_size = 96
+    two ranks take 48 of their own samples per SGD step, and three such steps land on the parameters of ONE learner
+    that walks the full batch in minibatches of 96 (unshuffled, a minibatch = 3 time steps x all 32 rows = the union
+    of the two ranks' minibatches of that step)."""
+    d = tempfile.mkdtemp()
+    mp.spawn(_worker, args=(2, "PPO", os.path.join(d, "init"), d, 96), nprocs=2, join=True)
+    r0, r1 = torch.load(os.path.join(d, "r0.pt")), torch.load(os.path.join(d, "r1.pt"))
+    assert torch.equal(r0["flat"], r1["flat"]) and r0["stats"]["sgd_steps"] == 3
+    single = get_rl_model("PPO", {"sgd_minibatch_size": 96, "shuffle_sequences": False}, env=FakeEnv(32), device="cpu")
+    _fill(single.buf, 7, 0, 32)
+    _prepare(single)
+    p0 = single.policy.flat.detach().clone()
+    st = single.learn(single.buf)
+    assert st["sgd_steps"] == 3
+    step = (single.policy.flat.detach() - p0).abs()
+    diff = (r0["flat"] - single.policy.flat.detach()).abs()
+    # three Adam steps of lr 1e-4 move a coordinate by up to 3e-4; the two runs differ by fp32 summation order only,
+    # except where a gradient coordinate is at rounding-noise level (Adam's sign-like first steps): bound the bulk
+    assert step.max() > 1e-4
+    assert (diff <= 2e-6).float().mean() > 0.99, float((diff <= 2e-6).float().mean())
     assert abs(r0["stats"]["total_loss"] - st["total_loss"]) <= 1e-4 * max(1.0, abs(st["total_loss"]))

@@ -3,6 +3,9 @@
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
 #ifdef PAIR
 #include "../rl4rs_b200/csrc/r4_augru_pair.cuh"
+#ifndef PAIR2
+#define PAIR2            // the first-generation pair kernel is gone: -DPAIR means k_augru_pair2
+#endif
 #ifdef PAIR2
 #include "../rl4rs_b200/csrc/r4_augru_pair2.cuh"
 #ifndef P2RELAY
@@ -12,11 +15,6 @@
 #define P2TMAP 1
 #endif
 #define KERNEL (k_augru_pair2<P2RELAY, P2TMAP>)
-#elif defined(PAIRT)
-#include "experiments/r4_augru_pair_templated.cuh"
-#define KERNEL k_augru_pair_t
-#else
-#define KERNEL k_augru_pair
 #endif
 #define KSMEM P_SMEM_BYTES
 #define KTHREADS NTHREADS
@@ -76,7 +74,7 @@ int main(int argc, char** argv) {
 #define XSCALE(col) 1.0f
 #endif
   for (int c = 0; c < ncache; ++c) for (int t = 0; t < 64; ++t) for (int col = 0; col < 768; ++col)
-    XT[(((size_t)(c / TM) * 64 + t) * 768 + col) * TM + c % TM] = XSCALE(col) * X[((size_t)c * 64 + t) * 768 + col];
+    XT[(((size_t)(c / TM) * 64 + t) * 768 + (col & ~3)) * TM + (c % TM) * 4 + (col & 3)] = XSCALE(col) * X[((size_t)c * 64 + t) * 768 + col];   // quad layout (r4_gemm_tc.cuh: xt_index)
   for (int r = 0; r < R; ++r) for (int t = 0; t < 64; ++t) sT[((size_t)(r / TM) * 64 + t) * TM + r % TM] = sc[(size_t)r * 64 + t];
   std::vector<uint8_t> img; build_image(Wg, Wc, img);
   // CPU reference (f64)
