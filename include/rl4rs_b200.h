@@ -45,6 +45,11 @@ enum {
 };
 
 enum { R4_ENV_SLATE = 0, R4_ENV_SEQSLATE = 1 };   /* rl4rs/__init__.py:10-18 */
+/* config['algo'] (slate.py:239-242): which rl4rs/nets/<algo>.py graph the simulator is.
+ *   DIEN  nets/dien.py:8-45   (sequence GRU/attention/AUGRU + dense tower + category attention; tensor-bound)
+ *   DNN   nets/dnn.py:8-45    (mean-pooled category embeddings + dense tower + FC 256 + simulator_obs; gather-bound:
+ *                              the sequence branch of that graph does not reach the output and is not evaluated) */
+enum { R4_SIM_DIEN = 0, R4_SIM_DNN = 1 };
 
 /* The config dict of the reference scripts (simulator_eval.py:9-12, modelfree_train.py:32-37). */
 typedef struct {
@@ -63,6 +68,7 @@ typedef struct {
   int32_t emb_size;             /* 128 */
   int32_t hidden_units;         /* 128 */
   int32_t max_rows_per_pass;    /* 0 = default; bound on simulator rows per launch group */
+  int32_t simulator;            /* R4_SIM_DIEN | R4_SIM_DNN (ABI version >= 2) */
 } r4_config;
 
 /* Per-call output buffers (device, caller-owned).  NULL = not wanted.
@@ -125,6 +131,11 @@ int r4_offline_reward(r4_env* env, double* reward, void* stream);
 
 /* SlateState.get_violation (slate.py:133-147 / seqslate.py:52-69): i32[B] of 0/1. */
 int r4_violation(r4_env* env, int32_t* out, void* stream);
+
+/* The raw feature rows of the CURRENT state -- what RecState.state hands to obs_fn (slate.py:90-106, built by
+ * slate.py:67-83,203-213 and padded by FeatureUtil.feature_extraction, datautil.py:34-69) -- without a simulator
+ * pass: cat i32[B,21], dense f32[B,432], seq i32[B,2,64] (any may be NULL).  For custom obs_fn plug-ins. */
+int r4_features(r4_env* env, int32_t* cat, float* dense, int32_t* seq, void* stream);
 
 /* SlateState.get_nearest_neighbor (static, unmasked; slate.py:180-184; tutorial.ipynb:251-254) */
 int r4_nearest_neighbor(r4_env* env, const void* action, int action_is_f64, int n, int32_t* out,

@@ -11,13 +11,15 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr
 
 FLAG_RLLIB_MASK, FLAG_D3RL_MASK, FLAG_CONTI, FLAG_ONEHOT, FLAG_RAWSTATE, FLAG_INFO_FETCH = 1, 2, 4, 8, 16, 32
 ENV_SLATE, ENV_SEQSLATE = 0, 1
+SIM_DIEN, SIM_DNN = 0, 1
+SIMULATORS = {"dien": SIM_DIEN, "dnn": SIM_DNN}
 
 
 class R4Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "env_kind", "flags", "batch_size", "max_steps", "page_items", "action_size", "action_emb_size",
         "maxlen", "seq_num", "dense_feature_num", "category_feature_num", "category_hash_size",
-        "emb_size", "hidden_units", "max_rows_per_pass")]
+        "emb_size", "hidden_units", "max_rows_per_pass", "simulator")]
 
 
 class R4Out(C.Structure):
@@ -40,6 +42,7 @@ EXPORTS = {
     "r4_offline_action": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r4_offline_reward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "r4_violation": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r4_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r4_nearest_neighbor": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "r4_cur_steps": (C.c_int, [C.c_void_p]),
     "r4_prev_actions": (C.c_void_p, [C.c_void_p]),

@@ -5,6 +5,7 @@
 #include "r4_augru_tc.cuh"
 #include "r4_augru_pair.cuh"
 #include "r4_augru_pair2.cuh"
+#include "r4_augru_pp.cuh"
 #include "r4_gemm_tc.cuh"
 #include "r4_scores_tc.cuh"
 #include "r4_gru_tc.cuh"
@@ -69,6 +70,8 @@ struct r4_env {
   float *emb_cat = nullptr, *emb_seq = nullptr, *w1 = nullptr, *b1 = nullptr, *w2 = nullptr, *b2 = nullptr;
   float *wo = nullptr, *bo = nullptr, *wr = nullptr, *br = nullptr;
   uint8_t *w1_img = nullptr, *w2_img = nullptr, *wo_img = nullptr;   // tensor-core images (r4_gemm_tc.cuh)
+  int sim = R4_SIM_DIEN;                                             // config['algo']: which simulator graph
+  float* fcb = nullptr; uint8_t *fc_img = nullptr;                   // dnn: the unnamed Dense(256, ELU) of nets/dnn.py:34
   PerSeq ps[2];
   bool weights_ready = false;
   std::vector<void*> owned;
@@ -176,12 +179,14 @@ constexpr int HEAD_BNT = 128;
 
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
-         int ldT = 0, float* outT = nullptr, float* outK = nullptr, int bnt = r4tc::G_BNMAX) {
+         int ldT = 0, float* outT = nullptr, float* outK = nullptr, int bnt = r4tc::G_BNMAX,
+         const float* A2 = nullptr, const int32_t* gather2 = nullptr, int k2_start = 0, int g2_n = 0) {
   if (M <= 0) return R4_OK;
   if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
   r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act, tm_ns, cr_base, ldT, outT, outK};
   p.bnt = bnt;
+  p.A2 = A2; p.gather2 = gather2; p.k2_start = k2_start; p.g2_n = g2_n;
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int tiles = ((M + r4tc::G_BM - 1) / r4tc::G_BM) * ((N + bnt - 1) / bnt);
   r4tc::k_gemm_tc<<<std::min(tiles, sms), r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
@@ -230,30 +235,42 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
 
 // Kernel-choice options (r4_set_option; the environment gives the initial values).
 struct AugruOpts {
-  int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel
+  int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel (one recurrence per pair), 3 ping-pong pair kernel
   int pair_impl = 1;      // 1 = k_augru_pair2<R4P2_RELAY, R4P2_TMAP>, 2..4 = <0,1> <1,0> <0,0>
-  int cost_single = 15, cost_pair = 8;  // per-wave cost ratio, measured: 1.19 ms (k_augru_tc) : 0.64 ms (k_augru_pair2<1,1>), tools/augru_probe.cu
+  // cost of one wave, measured (tools/augru_probe.cu, ms x 12.5): k_augru_tc 1.19 ms per 148 tile-sequences,
+  // k_augru_pair2 0.64 ms per 74, k_augru_pp 0.72 ms per 74 TILES (= 148 tile-sequences)
+  int cost_single = 15, cost_pair = 8, cost_pp = 9;
   AugruOpts() {
-    if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2;
+    if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
     if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
-    if (const char* e = getenv("R4_AUGRU_RULE")) { int a = 0, b = 0; if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { cost_single = a; cost_pair = b; } }
+    if (const char* e = getenv("R4_AUGRU_RULE")) {
+      int a = 0, b = 0, c = 0;
+      int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
+      if (n >= 2 && a > 0 && b > 0) { cost_single = a; cost_pair = b; if (n == 3 && c > 0) cost_pp = c; }
+    }
   }
 };
 AugruOpts& augru_opts() { static AugruOpts o; return o; }
 
-// Which AUGRU kernel runs `ctas` = 2 x row tiles of work.  The 2-CTA pair kernel finishes a 128-row tile faster than the
-// one-CTA kernel but occupies two SMs for it: compare cost_single * waves(ctas, sms) with cost_pair * waves(ctas, sms / 2).
-static bool augru_rule_single(int ctas, int sms) {
+// Which AUGRU kernel runs `ctas` = 2 x row tiles (tile-sequences) of work: 1 = k_augru_tc (one CTA per tile-sequence),
+// 2 = k_augru_pair2 (a CTA pair per tile-sequence), 3 = k_augru_pp (a CTA pair per TILE, both sequences in flight).
+// The pair kernels finish a tile sooner but occupy two SMs for it, the ping-pong kernel keeps the tensor pipe busier but
+// needs twice the tiles to fill the chip: compare wave counts x measured wave times.
+static int augru_rule(int ctas, int sms) {
   const AugruOpts& o = augru_opts();
-  const int w_single = (ctas + sms - 1) / sms, w_pair = (ctas + sms / 2 - 1) / (sms / 2);
-  return o.cost_single * w_single <= o.cost_pair * w_pair;
+  const int pairs = sms / 2;
+  const long c1 = (long)o.cost_single * ((ctas + sms - 1) / sms);
+  const long c2 = (long)o.cost_pair * ((ctas + pairs - 1) / pairs);
+  const long c3 = (long)o.cost_pp * (((ctas + 1) / 2 + pairs - 1) / pairs);
+  if (c3 <= c2 && c3 <= c1) return 3;
+  return c1 <= c2 ? 1 : 2;
 }
-static bool augru_use_single(int ctas) {
+static int augru_choice(int ctas) {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int force = augru_opts().force;
-  if (force) return force == 1;
-  return augru_rule_single(ctas, sms);
+  return force ? force : augru_rule(ctas, sms);
 }
+static bool augru_use_single(int ctas) { return augru_choice(ctas) == 1; }
 static int augru_pair_impl() { return augru_opts().pair_impl; }
 
 // One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
@@ -261,10 +278,37 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
                  const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
                  float* p1_out, float* probs_out, cudaStream_t st) {
   int rc;
+  if (e->sim == R4_SIM_DNN) {
+    // nets/dnn.py:31-37: all = [mean_t E_c[cat] | dense tower]; Dense(256, ELU); simulator_obs Dense(256, ELU); softmax head
+    if ((rc = reserve(e, e->ws_allf, (size_t)R * 2 * HU * 4))) return rc;
+    if ((rc = reserve(e, e->ws_tmp, (size_t)R * OBSD * 4))) return rc;
+    float* allf = reinterpret_cast<float*>(e->ws_allf.p);
+    float* tmp = reinterpret_cast<float*>(e->ws_tmp.p);
+    static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
+    { ProfScope ps(e, SL_CAT, st, (double)R * (NCAT * 4 + NCAT * EMB * 4));       // work = algorithmic gather bytes
+      const int blocks = std::max(1, std::min((R + POOL_WARPS - 1) / POOL_WARPS, 2 * sms));
+      k_cat_pool<<<blocks, POOL_WARPS * 32, POOL_SMEM, st>>>(R, cat, e->emb_cat, allf, 2 * HU); }
+    R4_LAUNCH_CHECK(e, "k_cat_pool");
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + HU, 2 * HU, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, OBSD, 2 * HU, allf, 2 * HU, nullptr, e->fc_img, e->fcb, tmp, OBSD, st))) return rc;
+    float* obs = obs_out;
+    if (!obs) {
+      if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
+      obs = reinterpret_cast<float*>(e->ws_obs.p);
+    }
+    if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, OBSD, tmp, OBSD, nullptr, e->wo_img, e->bo, obs, OBSD, st))) return rc;
+    if (p1_out || probs_out) {
+      { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
+        k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
+      R4_LAUNCH_CHECK(e, "k_reward_head");
+    }
+    return R4_OK;
+  }
   const int rtiles = (R + r4tc::TM - 1) / r4tc::TM;
   const size_t sc_per_seq = (size_t)rtiles * r4tc::TM * MAXLEN;
   if ((rc = reserve(e, e->ws_scores, 2 * sc_per_seq * 4))) return rc;
-  if ((rc = reserve(e, e->ws_allf, (size_t)R * ALLF * 4))) return rc;
+  if ((rc = reserve(e, e->ws_allf, (size_t)R * ALLF_LD * 4))) return rc;
   if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
   if ((rc = reserve(e, e->ws_q, (size_t)R * (r4tc::S_K + 2 * r4tc::S_N) * 4))) return rc;
   float* qbuf = reinterpret_cast<float*>(e->ws_q.p);
@@ -290,7 +334,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     q.out = allf + i * AUH; q.shared = sh[i];
   }
   sp.R = R; sp.row0 = row0; sp.div = div; sp.q = qbuf;
-  rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF;
+  rp.R = R; rp.row0 = row0; rp.div = div; rp.out_ld = ALLF_LD;
   // The side stream (lowest priority) does the AUGRU-independent half of the feature vector: category attention +
   // dense tower.  It forks AFTER k_scores_tc and is fed after the AUGRU launch, so the AUGRU pairs (1 CTA per SM,
   // 128 SMs at 4096 rows) are resident first and the side kernels fill the remaining SMs instead of delaying them.
@@ -307,7 +351,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     R4_LAUNCH_CHECK(e, "k_cat_attn");
     int rc2;
     if ((rc2 = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, ss))) return rc2;
-    if ((rc2 = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF, ss))) return rc2;
+    if ((rc2 = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * AUH, ALLF_LD, ss))) return rc2;
     if (!no_side) R4_CUDA(e, cudaEventRecord(e->ev_join, ss));
     return R4_OK;
   };
@@ -325,8 +369,14 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   if (!no_side && !side_early) R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
     const dim3 pgrid(rtiles * 2, 2);
-    if (augru_use_single(2 * rtiles)) r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp);
-    else {
+    const int which = augru_choice(2 * rtiles);
+    if (which == 1) r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp);
+    else if (which == 3) {
+      r4tc::AugruPairParams pp;
+      pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
+      if (augru_pair_impl() == 2 || augru_pair_impl() == 4) r4tc::k_augru_pp<0><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
+      else r4tc::k_augru_pp<R4P2_RELAY><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
+    } else {
       r4tc::AugruPairParams pp;
       pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
       switch (augru_pair_impl()) {
@@ -336,7 +386,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
         default: r4tc::k_augru_pair2<R4P2_RELAY, R4P2_TMAP><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
       }
     } }
-  R4_LAUNCH_CHECK(e, augru_use_single(2 * rtiles) ? "k_augru_tc" : "k_augru_pair");
+  R4_LAUNCH_CHECK(e, augru_choice(2 * rtiles) == 1 ? "k_augru_tc" : (augru_choice(2 * rtiles) == 3 ? "k_augru_pp" : "k_augru_pair2"));
   if (!no_side && !side_early && (rc = side_work())) return rc;
   if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
@@ -344,7 +394,9 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
     obs = reinterpret_cast<float*>(e->ws_obs.p);
   }
-  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr, nullptr, HEAD_BNT))) return rc;
+  // head: K = 768 materialised columns + 21 x 128 gathered from the category embedding table by `cat`
+  if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF_LD, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr, nullptr, HEAD_BNT,
+                 e->emb_cat, cat, ALLF_LD, NCAT))) return rc;
   if (p1_out || probs_out) {
     { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
     k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
@@ -443,7 +495,7 @@ const float* hw_get(r4_env* e, const std::string& name, size_t n) {
 
 extern "C" {
 
-int r4_abi_version(void) { return 1; }
+int r4_abi_version(void) { return 2; }
 
 const char* r4_last_error(const r4_env* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
 
@@ -464,6 +516,8 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
     return fail(nullptr, R4_ERR_ARG, "r4_create: SeqSlateRecEnv needs max_steps to be a multiple of page_items");
   if (cfg->category_hash_size < cfg->action_size)
     return fail(nullptr, R4_ERR_ARG, "r4_create: category_hash_size must cover the item ids");
+  if (cfg->simulator != R4_SIM_DIEN && cfg->simulator != R4_SIM_DNN)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: simulator must be R4_SIM_DIEN or R4_SIM_DNN (config['algo'] = 'dien' | 'dnn')");
   cudaError_t st = cudaSetDevice(device);
   if (st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(st));
   r4_env* e = new r4_env();
@@ -472,6 +526,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   e->A = cfg->action_size; e->words = (e->A + 31) / 32; e->T = cfg->max_steps; e->P = cfg->page_items;
   e->B = cfg->batch_size; e->seq = cfg->env_kind == R4_ENV_SEQSLATE; e->hash = cfg->category_hash_size;
   e->max_rows = cfg->max_rows_per_pass > 0 ? cfg->max_rows_per_pass : 36864;
+  e->sim = cfg->simulator;
   bool ok = cudaMalloc(&e->row_idx, (size_t)e->B * 4) == cudaSuccess &&
             cudaMalloc(&e->prev_actions, (size_t)e->B * e->T * 4) == cudaSuccess &&
             cudaMalloc(&e->amask, (size_t)e->B * e->words * 4) == cudaSuccess &&
@@ -479,6 +534,8 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
@@ -486,6 +543,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
+  cudaFuncSetAttribute(k_cat_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM);
   st = cudaGetLastError();
   if (st != cudaSuccess) { r4_destroy(e); return fail(nullptr, R4_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(st)); }
   int prio_lo = 0, prio_hi = 0;
@@ -561,6 +619,29 @@ int r4_finalize_weights(r4_env* e, void* stream) {
   R4_CUDA(e, cudaSetDevice(e->device));
   const size_t Hh = (size_t)e->hash;
   struct Need { const char* n; size_t sz; };
+  if (e->sim == R4_SIM_DNN) {
+    // W-table of nets/dnn.py:8-45: emb_cat [H,128], dense tower, fc [256,256] (the unnamed Dense of :34), simulator_obs
+    // [256,256], simulator_reward [256,2].  The graph's second Embedding (sequence_input_concat) feeds nothing.
+    std::vector<Need> need = {{"emb_cat", Hh * EMB}, {"dense_w1", (size_t)NDENSE * HU}, {"dense_b1", HU},
+                              {"dense_w2", (size_t)HU * HU}, {"dense_b2", HU}, {"fc_w", (size_t)2 * HU * OBSD}, {"fc_b", OBSD},
+                              {"obs_w", (size_t)OBSD * OBSD}, {"obs_b", OBSD}, {"rew_w", OBSD * 2}, {"rew_b", 2}};
+    for (auto& nd : need)
+      if (!hw_get(e, nd.n, nd.sz)) return fail(e, R4_ERR_ARG, std::string("r4_finalize_weights(dnn): missing or mis-shaped ") + nd.n);
+    for (void* p : e->owned) cudaFree(p);
+    e->owned.clear();
+    int rc;
+    if ((rc = upload(e, e->hw["emb_cat"], &e->emb_cat)) || (rc = upload(e, e->hw["dense_b1"], &e->b1)) ||
+        (rc = upload(e, e->hw["dense_b2"], &e->b2)) || (rc = upload(e, e->hw["fc_b"], &e->fcb)) ||
+        (rc = upload(e, e->hw["obs_b"], &e->bo)) || (rc = upload(e, e->hw["rew_w"], &e->wr)) ||
+        (rc = upload(e, e->hw["rew_b"], &e->br)) ||
+        (rc = upload_image(e, e->hw["dense_w1"].data(), NDENSE, HU, &e->w1_img)) ||
+        (rc = upload_image(e, e->hw["dense_w2"].data(), HU, HU, &e->w2_img)) ||
+        (rc = upload_image(e, e->hw["fc_w"].data(), 2 * HU, OBSD, &e->fc_img)) ||
+        (rc = upload_image(e, e->hw["obs_w"].data(), OBSD, OBSD, &e->wo_img))) return rc;
+    e->hw.clear();
+    e->weights_ready = true;
+    return R4_OK;
+  }
   std::vector<Need> need = {{"emb_cat", Hh * EMB}, {"emb_seq", Hh * EMB}, {"dense_w1", (size_t)NDENSE * HU},
                             {"dense_b1", HU}, {"dense_w2", (size_t)HU * HU}, {"dense_b2", HU},
                             {"obs_w", (size_t)ALLF * OBSD}, {"obs_b", OBSD}, {"rew_w", OBSD * 2}, {"rew_b", 2}};
@@ -697,8 +778,9 @@ int r4_reset(r4_env* e, const int32_t* row_idx, const r4_out* out, void* stream)
                                                        (int32_t*)e->ws_ids0.p, nullptr, out ? out->seq : nullptr);
   R4_LAUNCH_CHECK(e, "k_seq_ids");
   e->has_reset = true;
-  // user-history GRU-1 + input projections: once per episode (they do not depend on the actions)
-  if ((rc = build_cache(e, 0, (const int32_t*)e->ws_ids0.p, B, e->c0, st))) return rc;
+  // user-history GRU-1 + input projections: once per episode (they do not depend on the actions); the dnn simulator
+  // has no sequence branch
+  if (e->sim == R4_SIM_DIEN && (rc = build_cache(e, 0, (const int32_t*)e->ws_ids0.p, B, e->c0, st))) return rc;
   if ((rc = obs_pass(e, 0, 0, out, st))) return rc;
   if (out && out->reward) { k_fill_f64<<<(B + 255) / 256, 256, 0, st>>>(B, 0.0, out->reward); R4_LAUNCH_CHECK(e, "k_fill_f64"); }
   if (out && out->done) { k_fill_u8<<<(B + 255) / 256, 256, 0, st>>>(B, 0, out->done); R4_LAUNCH_CHECK(e, "k_fill_u8"); }
@@ -718,7 +800,7 @@ int r4_step(r4_env* e, const void* action, int action_is_f64, const r4_out* out,
   bool conti = (e->cfg.flags & R4_FLAG_CONTI) != 0;
   // SeqSlate: entering a new page, the second sequence becomes the items of all previous pages
   // (seqslate.py:109-110) -> rebuild its GRU-1 cache once per page.
-  if (e->seq && cur > 0 && cur % e->P == 0) {
+  if (e->sim == R4_SIM_DIEN && e->seq && cur > 0 && cur % e->P == 0) {
     if ((rc = reserve(e, e->ws_ids1, (size_t)B * MAXLEN * 4))) return rc;
     k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, cur, e->row_idx, e->log_seq, e->prev_actions,
                                                          nullptr, (int32_t*)e->ws_ids1.p, nullptr);
@@ -787,6 +869,27 @@ int r4_violation(r4_env* e, int32_t* out, void* stream) {
   return R4_OK;
 }
 
+int r4_features(r4_env* e, int32_t* cat, float* dense, int32_t* seq, void* stream) {
+  if (!e || (!cat && !dense && !seq)) return fail(e, R4_ERR_ARG, "r4_features: null argument");
+  if (!e->has_reset) return fail(e, R4_ERR_STATE, "r4_features: reset first");
+  R4_CUDA(e, cudaSetDevice(e->device));
+  cudaStream_t st = S(stream);
+  int rc;
+  const int B = e->B, cur = e->cur_steps;
+  if (cat || dense) {
+    int32_t* c = cat; float* d = dense;
+    if (!c) { if ((rc = reserve(e, e->ws_cat, (size_t)B * NCAT * 4))) return rc; c = (int32_t*)e->ws_cat.p; }
+    if (!d) { if ((rc = reserve(e, e->ws_dense, (size_t)B * NDENSE * 4))) return rc; d = (float*)e->ws_dense.p; }
+    if ((rc = assemble(e, cur == 0 ? 0 : 1, cur == 0 ? 0 : cur - 1, 1, 0, B, c, d, st))) return rc;
+  }
+  if (seq) {
+    const int p0 = (e->seq && cur > 0) ? (cur - 1) / e->P * e->P : 0;
+    k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, p0, e->row_idx, e->log_seq, e->prev_actions, nullptr, nullptr, seq);
+    R4_LAUNCH_CHECK(e, "k_seq_ids");
+  }
+  return R4_OK;
+}
+
 int r4_nearest_neighbor(r4_env* e, const void* action, int action_is_f64, int n, int32_t* out, void* stream) {
   if (!e || !action || !out || n < 1) return fail(e, R4_ERR_ARG, "r4_nearest_neighbor: bad argument");
   if (!e->items_ready) return fail(e, R4_ERR_STATE, "r4_nearest_neighbor: load items first");
@@ -804,15 +907,16 @@ int r4_set_option(const char* key, int value) {
   if (!key) return fail(nullptr, R4_ERR_ARG, "r4_set_option: null key");
   AugruOpts& o = augru_opts();
   const std::string k(key);
-  if (k == "augru_kernel" && value >= 0 && value <= 2) o.force = value;
+  if (k == "augru_kernel" && value >= 0 && value <= 3) o.force = value;
   else if (k == "augru_pair_impl" && value >= 1 && value <= 4) o.pair_impl = value;
   else if (k == "augru_cost_single" && value > 0) o.cost_single = value;
   else if (k == "augru_cost_pair" && value > 0) o.cost_pair = value;
+  else if (k == "augru_cost_pp" && value > 0) o.cost_pp = value;
   else return fail(nullptr, R4_ERR_ARG, "r4_set_option: unknown key or value out of range: " + k);
   return R4_OK;
 }
 
-int r4_augru_kernel_for(int ctas, int sms) { return (ctas < 1 || sms < 2) ? 0 : (augru_rule_single(ctas, sms) ? 1 : 2); }
+int r4_augru_kernel_for(int ctas, int sms) { return (ctas < 1 || sms < 2) ? 0 : augru_rule(ctas, sms); }
 
 int r4_profile(r4_env* e, int mode) {
   if (!e || mode < 0 || mode > 2) return fail(e, R4_ERR_ARG, "r4_profile: mode must be 0, 1 or 2");
@@ -1102,6 +1206,16 @@ int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int
   R4_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = S(stream);
   int rc;
+  if (e->sim == R4_SIM_DNN) {           // no sequence branch: straight through forward_rows
+    rc = R4_OK;
+    int chunk = std::min(n_rows, e->max_rows);
+    for (int r0 = 0; !rc && r0 < n_rows; r0 += chunk) {
+      int nr = std::min(chunk, n_rows - r0);
+      rc = forward_rows(e, nr, r0, 1, cat + (size_t)r0 * NCAT, dense + (size_t)r0 * NDENSE, e->c0, 0, e->c0, 0,
+                        obs ? obs + (size_t)r0 * OBSD : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
+    }
+    return rc;
+  }
   SeqCache t0, t1;
   DevBuf ids;
   if ((rc = reserve(e, ids, (size_t)2 * n_rows * MAXLEN * 4))) return rc;

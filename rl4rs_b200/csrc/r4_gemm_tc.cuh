@@ -86,6 +86,11 @@ struct GemmTcParams {
   // column the AUGRU epilogue spent 18 % of its cycles in lg_throttle, 192 LDGs per thread and step).
   int tm_ns, cr_base, ldT; float* outT; float* outK;
   int bnt = G_BNMAX;          // n-tile width of the weight image (build_gemm_image)
+  // Second, GATHERED part of the A operand (the observation head: K = 768 + 21 x 128): for k >= k2_start, A[m][k] is
+  // A2[gather2[m * g2_n + j] * 128 + (k - k2_start) % 128] with j = (k - k2_start) / 128 -- the Flatten() of the category
+  // embeddings (nets/utils.py:24) read straight from the embedding table (L2-resident, 51 MB) instead of from a
+  // 10.7 KB-per-row copy that k_cat_attn used to write and this kernel used to read back.  k2_start % 32 == 0.
+  const float* A2 = nullptr; const int32_t* gather2 = nullptr; int k2_start = 0, g2_n = 0;
   long long* dbg = nullptr;   // development probe (tools/gemm_probe.cu): per-role wait/busy cycles of CTA 0
 };
 
@@ -197,6 +202,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     // are in flight while one is converted (a register-staged single prefetch left the GEMMs latency-bound).
     const int kc = tid & 3, r8 = tid >> 2;      // 64 row slots x 2 passes
     const float* arow[2] = {p.A, p.A};
+    const int32_t* grow[2] = {p.gather2, p.gather2};
     int is_tile = blockIdx.x, is_kb = 0;
     auto issue = [&](int slot) {
       if (is_tile < ntiles) {
@@ -209,14 +215,18 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
             if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
             size_t src = p.gather ? (size_t)__ldg(p.gather + m) : (size_t)m;
             arow[it] = p.A + src * p.lda + kc * 8;
+            if (p.A2) grow[it] = p.gather2 + (size_t)m * p.g2_n;
           }
         }
+        const bool part2 = p.A2 && is_kb * G_BK >= p.k2_start;
+        const int k2 = is_kb * G_BK - p.k2_start;              // offset inside the gathered part (multiple of 32)
         const bool kok = is_kb * G_BK + kc * 8 + 8 <= p.K;   // K % 8 == 0 is required; beyond K: zero fill
         const uint32_t nb = kok ? 16u : 0u;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           uint8_t* dst = raw + slot * G_RAW_BYTES + (it * 64 + r8) * (G_BK * 4) + kc * 32;
           const float* src = kok ? arow[it] + is_kb * G_BK : arow[it];
+          if (part2 && kok) src = p.A2 + (size_t)__ldg(grow[it] + (k2 >> 7)) * 128 + (k2 & 127) + kc * 8;
           cp_async16(dst, src, nb);
           cp_async16(dst + 16, src + 4, nb);
         }

@@ -246,11 +246,13 @@ __global__ void k_seq_ids(int B, int T, int p0, const int32_t* __restrict__ row_
 // ------------------------------------------------------------------------------------------
 // K4 + K5 category features (nets/utils.py:16-25): E_c gather, tf.keras.layers.Attention()
 // (softmax(Q K^T) V, no scale, no mask), GlobalAveragePooling1D, and the flattened embeddings.
-// One warp per row; softmax rows are reduced with warp shuffles.  Writes straight into the
-// concatenated head input: allf[r, 640:768] = pooled attention, allf[r, 768:3456] = flatten.
+// One warp per row; softmax rows are reduced with warp shuffles.  Writes the pooled attention straight into the
+// head input: allf[r, 640:768] (row stride out_ld).  The Flatten() half of the category feature is NOT materialised:
+// the head GEMM gathers those 21 x 128 values from the embedding table itself (r4_gemm_tc.cuh: A2 / gather2).
 // mean_t(P emb) is evaluated as (mean_t P) emb -- same value up to fp32 rounding order.
 // ------------------------------------------------------------------------------------------
 constexpr int CAT_LD = 132;
+constexpr int ALLF_LD = 2 * AUH + HU + EMB;    // 768: [sequence 512 | dense 128 | pooled category attention 128]
 __global__ void __launch_bounds__(128) k_cat_attn(int R, const int32_t* __restrict__ cat,
                                                   const float* __restrict__ emb_cat, float* __restrict__ allf) {
   extern __shared__ __align__(16) float smem[];
@@ -260,11 +262,10 @@ __global__ void __launch_bounds__(128) k_cat_attn(int R, const int32_t* __restri
   float* Ssm = e + NCAT * CAT_LD;                         // [21][24]
   if (r >= R) return;
   const int32_t* crow = cat + (size_t)r * NCAT;
-  float* out = allf + (size_t)r * ALLF;
+  float* out = allf + (size_t)r * ALLF_LD;
   for (int j = 0; j < NCAT; ++j) {
     float4 v = ldg4(emb_cat + (size_t)crow[j] * EMB + lane * 4);
     *reinterpret_cast<float4*>(&e[j * CAT_LD + lane * 4]) = v;
-    *reinterpret_cast<float4*>(out + 2 * AUH + HU + EMB + j * EMB + lane * 4) = v;   // Flatten
   }
   __syncwarp();
   // S[t][j] = <e_t, e_j>, symmetric: 231 pairs spread over lanes
@@ -304,6 +305,65 @@ __global__ void __launch_bounds__(128) k_cat_attn(int R, const int32_t* __restri
     acc.z = fmaf(wj, v.z, acc.z); acc.w = fmaf(wj, v.w, acc.w);
   }
   *reinterpret_cast<float4*>(out + 2 * AUH + HU + lane * 4) = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// dnn simulator (nets/dnn.py:31, nets/utils.py:7-14): category_feature = GlobalAveragePooling1D(Embedding(cat)).
+// THE gather kernel of the path: per feature row 21 x 512 B embedding rows in, 512 B out (G_dnn).
+// One warp per row, persistent grid.  The 21 rows of a feature row are staged into shared memory by the bulk-copy
+// engine (cp.async.bulk, 1-D TMA): lanes 0..20 each issue ONE 512-byte copy for their id, all completing on the warp's
+// mbarrier, two rows in flight per warp (double buffer) -- the loads of row i+1 are in the memory system while row i is
+// reduced, with no registers tied up.  The reduction reads shared memory with 128-bit loads (lane = 4 columns) and
+// writes the pooled row with one coalesced 512-byte store.  Sum order j = 0..20 then * (1/21) (fp32; the reference's
+// reduce_mean is order-free up to rounding).
+// ------------------------------------------------------------------------------------------
+constexpr int POOL_WARPS = 4;
+constexpr int POOL_SMEM = POOL_WARPS * 2 * NCAT * EMB * 4;          // 86 016 B: 2 CTAs per SM
+__global__ void __launch_bounds__(POOL_WARPS * 32) k_cat_pool(int R, const int32_t* __restrict__ cat,
+                                                              const float* __restrict__ emb_cat, float* __restrict__ out,
+                                                              int out_ld) {
+  extern __shared__ __align__(128) float pool_s[];
+  __shared__ uint64_t bar[POOL_WARPS][2];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* buf = pool_s + (size_t)w * 2 * NCAT * EMB;
+  const int gw = blockIdx.x * POOL_WARPS + w, nw = gridDim.x * POOL_WARPS;
+  if (lane == 0) {
+    for (int i = 0; i < 2; ++i)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bar[w][i])), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  auto issue = [&](int r, int b) {
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&bar[w][b]);
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(NCAT * EMB * 4) : "memory");
+    __syncwarp();
+    if (lane < NCAT) {
+      const float* src = emb_cat + (size_t)__ldg(cat + (size_t)r * NCAT + lane) * EMB;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf + ((size_t)b * NCAT + lane) * EMB);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"(dst), "l"(src), "r"(EMB * 4), "r"(mb) : "memory");
+    }
+  };
+  int it = 0;
+  if (gw < R) issue(gw, 0);
+  for (int r = gw; r < R; r += nw, ++it) {
+    const int b = it & 1;
+    if (r + nw < R) issue(r + nw, b ^ 1);                       // buffer b^1 was consumed one iteration ago (program order)
+    const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&bar[w][b]);
+    const uint32_t par = (uint32_t)((it >> 1) & 1);
+    asm volatile("{\n\t.reg .pred p;\n\tPOOL_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra POOL_DONE;\n\tbra POOL_WAIT;\n\tPOOL_DONE:\n\t}\n"
+                 :: "r"(mb), "r"(par) : "memory");
+    const float* e = buf + (size_t)b * NCAT * EMB + lane * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < NCAT; ++j) {
+      const float4 v = *reinterpret_cast<const float4*>(e + j * EMB);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float n = (float)NCAT;                                 // sum / count, like Eigen's MeanReducer / numpy.mean
+    *reinterpret_cast<float4*>(out + (size_t)r * out_ld + lane * 4) = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+    __syncwarp();                                                // every lane has read buffer b before it is refilled
+  }
 }
 
 // ------------------------------------------------------------------------------------------

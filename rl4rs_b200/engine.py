@@ -54,7 +54,8 @@ class Engine(object):
             category_feature_num=int(config.get("category_feature_num", 21)),
             category_hash_size=int(config.get("category_hash_size", 100000)),
             emb_size=int(config.get("emb_size", 128)), hidden_units=int(config.get("hidden_units", 128)),
-            max_rows_per_pass=int(config.get("max_rows_per_pass", 0)))
+            max_rows_per_pass=int(config.get("max_rows_per_pass", 0)),
+            simulator=_capi.SIMULATORS[config.get("algo", "dien")])
         h = C.c_void_p()
         rc = self.lib.r4_create(C.byref(cfg), self.device.index, C.byref(h))
         _capi.check(self.lib, None, rc, "r4_create")
@@ -235,6 +236,28 @@ class Engine(object):
         rc = self.lib.r4_violation(self.h, _ptr(out), self._sp())
         _capi.check(self.lib, self.h, rc, "r4_violation")
         return out
+
+    def log_row_of(self, record):
+        """Row index of a record string in the resident log (text-ingested logs only)."""
+        idx = getattr(self, "_line_index", None)
+        if idx is None:
+            lines = getattr(self.log, "lines", None)
+            if lines is None:
+                raise ValueError("the log was not ingested from text: pass row indices as records")
+            idx = self._line_index = {}
+            for i, ln in enumerate(lines):
+                idx.setdefault(ln, i)
+        return idx[record]
+
+    def features(self):
+        """(cat i32[B,21], dense f32[B,432], seq i32[B,2,64]) of the current state, device tensors (r4_features)."""
+        c = self.config
+        cat = torch.empty((self.B, int(c.get("category_feature_num", 21))), dtype=torch.int32, device=self.device)
+        dense = torch.empty((self.B, int(c.get("dense_feature_num", 432))), dtype=torch.float32, device=self.device)
+        seq = torch.empty((self.B, int(c.get("seq_num", 2)), int(c.get("maxlen", 64))), dtype=torch.int32, device=self.device)
+        rc = self.lib.r4_features(self.h, _ptr(cat), _ptr(dense), _ptr(seq), self._sp())
+        _capi.check(self.lib, self.h, rc, "r4_features")
+        return cat, dense, seq
 
     def nearest_neighbor(self, actions):
         a = torch.as_tensor(np.ascontiguousarray(actions, dtype=np.float64)).to(self.device)

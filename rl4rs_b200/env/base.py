@@ -124,7 +124,17 @@ class RecDataBase(object):
         else:
             idx = np.random.randint(0, len(self.sample_list), batch_size)
             rows = np.asarray(self.sample_list, dtype=np.int64)[idx]
-        return self.state_cls(self.config, rows, self.engine)
+        # The reference hands the RECORD STRINGS to the state plug-in (base.py:92-100: state_cls(config, records)).  When
+        # the log was ingested from text they are still available and are passed as such; the row indices travel beside
+        # them so the device-backed state classes need no string look-up.  Logs that exist only as arrays (synthetic /
+        # .npz) have no record text: `records` are then the row indices themselves.
+        lines = getattr(self.engine.log, "lines", None)
+        records = [lines[i] for i in rows] if lines is not None else rows
+        self.config["__engine__"], self.config["__rows__"] = self.engine, rows
+        try:
+            return self.state_cls(self.config, records)
+        finally:
+            self.config.pop("__rows__", None)
 
     def reset(self, reset_file=False):
         self.sample_list = []

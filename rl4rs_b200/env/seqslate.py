@@ -10,7 +10,7 @@ from .slate import SlateRecEnv, SlateState
 class SeqSlateState(SlateState):
     seq = True
 
-    def __init__(self, config, records, engine):
+    def __init__(self, config, records, engine=None):
         super().__init__(config, records, engine)
         self.page_items = config.get("page_items", 9)
 

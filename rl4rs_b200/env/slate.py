@@ -10,15 +10,81 @@ from .base import RecSimBase, RecState
 from ..synth import Catalog
 
 
+class StateView(object):
+    """What ``RecState.state`` hands to ``obs_fn`` (slate.py:90-106), materialised on demand from the device.
+
+    The reference returns the raw 6-field state rows ``[role_id, [seq0, seq1], dense, category, slate_label, label]``
+    (slate.py:67-83,203-213), wrapped in ``{'state', 'action_mask'}`` / ``{'state', 'masked_actions', 'cur_steps'}`` in
+    the two mask modes.  The built-in ``SlateRecEnv.obs_fn`` never looks at it (the simulator pass of a step is fused
+    behind ``act``), so nothing is copied unless a custom ``obs_fn`` plug-in reads it.  Rows arrive already padded the
+    way ``FeatureUtil.feature_extraction`` pads them (datautil.py:43-65; padding is idempotent): dense f32[432],
+    category i32[21], sequences i32[64] x 2."""
+
+    def __init__(self, st):
+        self._st, self._rows, self._cache = st, None, {}
+
+    def rows(self):
+        if self._rows is None:
+            eng = self._st.engine
+            cat, dense, seq = eng.features()
+            h = eng.to_host(cat=cat, dense=dense, seq=seq)
+            self._rows = [[0, [h["seq"][i, 0], h["seq"][i, 1]], h["dense"][i], h["cat"][i], [0] * 9, 0]
+                          for i in range(eng.B)]
+        return self._rows
+
+    def keys(self):
+        eng = self._st.engine
+        if eng.rllib:
+            return ["state", "action_mask"]
+        if eng.d3rl:
+            return ["state", "masked_actions", "cur_steps"]
+        return []
+
+    def __contains__(self, k):
+        return k in self.keys()
+
+    def __getitem__(self, k):
+        st = self._st
+        if isinstance(k, (int, np.integer, slice)):
+            if self.keys():
+                raise KeyError(k)
+            return self.rows()[k]
+        if k not in self.keys():
+            raise KeyError(k)
+        if k == "state":
+            return self.rows()
+        if k == "action_mask":
+            return st.action_mask
+        if k == "masked_actions":
+            return st.prev_actions
+        return np.full((st.batch_size, 1), st.cur_steps)
+
+    def __len__(self):
+        return len(self.keys()) or self._st.batch_size
+
+    def __iter__(self):
+        return iter(self.keys() or self.rows())
+
+
 class SlateState(RecState):
-    """slate.py:8-217.  ``records`` are row indices into the resident log."""
+    """slate.py:8-217.  Constructed like the reference's, ``state_cls(config, records)`` (base.py:68-71,92-100);
+    ``records`` are the record strings when the log was ingested from text, else row indices into the resident log."""
 
     seq = False
 
-    def __init__(self, config, records, engine):
+    def __init__(self, config, records, engine=None):
         super().__init__(config, records)
+        engine = engine if engine is not None else config.get("__engine__")
+        if engine is None:
+            raise ValueError("SlateState needs the simulator's engine (construct it through RecSimBase.sample)")
         self.engine = engine
-        self.rows = np.asarray(records, dtype=np.int64)
+        rows = config.get("__rows__")
+        if rows is None or len(rows) != len(records):
+            if len(records) and isinstance(records[0], str):         # a caller-made record list: resolve against the log
+                rows = [engine.log_row_of(r) for r in records]
+            else:
+                rows = records
+        self.rows = np.asarray(rows, dtype=np.int64)
         self.batch_size = config["batch_size"]
         self.action_size = config["action_size"]
         self.action_emb_size = engine.emb_dim
@@ -84,8 +150,12 @@ class SlateState(RecState):
 
     @property
     def state(self):
-        """slate.py:90-106: a handle to the device-resident state (what obs_fn consumes)."""
-        return self
+        """slate.py:90-106, materialised lazily (see StateView)."""
+        return StateView(self)
+
+    @property
+    def _state(self):
+        return StateView(self).rows()
 
     @property
     def user(self):
@@ -127,9 +197,8 @@ class SlateState(RecState):
         self.engine.step(actions)
 
     def to_string(self):
-        lines = getattr(self.engine.log, "lines", None)
-        if lines is not None:
-            return "\n".join(lines[i] for i in self.rows)
+        if len(self.records) and isinstance(self.records[0], str):
+            return "\n".join(self.records)                                  # slate.py:216-217
         return "\n".join("log row %d (user %s)" % (r, u) for r, u in zip(self.rows, self.user))
 
 
@@ -149,9 +218,10 @@ class SlateRecEnv(RecSimBase):
             self.obs_dim = 256 + (self.engine.P if self.seq else self.max_steps) + 1   # slate.py:274-277
 
     def get_model(self, config):
-        algo = config.get("algo", "dien")                              # slate.py:239-242
-        if algo != "dien":
-            raise NotImplementedError("only the 'dien' simulator is built (SURVEY.md section 8f n4)")
+        algo = config.get("algo", "dien")                              # slate.py:239-242: rl4rs/nets/<algo>.py
+        if algo not in ("dien", "dnn"):
+            raise NotImplementedError("simulator %r is not built: 'dien' (nets/dien.py) and 'dnn' (nets/dnn.py) are "
+                                      "(SURVEY.md section 8f n4)" % (algo,))
         w = config.get("weights")
         if w is None:
             w = self.load_model_file(config["model_file"], config)
@@ -163,7 +233,8 @@ class SlateRecEnv(RecSimBase):
         ``<prefix>.index`` + ``<prefix>.data-*``, README.md:124-137), or an .npz of the W-table."""
         from ..utils import tf_checkpoint
         if tf_checkpoint.is_saver_prefix(model_file):
-            return tf_checkpoint.load_dien_checkpoint(model_file, config, name_map=config.get("variable_name_map"))
+            load = tf_checkpoint.load_dnn_checkpoint if config.get("algo", "dien") == "dnn" else tf_checkpoint.load_dien_checkpoint
+            return load(model_file, config, name_map=config.get("variable_name_map"))
         return dict(np.load(model_file))
 
     # slate.py:244-279

@@ -249,6 +249,33 @@ def weight_shapes(cfg=None):
     return shapes
 
 
+def dnn_weight_shapes(cfg=None):
+    """W-table of the `dnn` simulator (rl4rs/nets/dnn.py:8-45): the graph's second Embedding feeds nothing and is
+    not part of the table."""
+    cfg = cfg or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D = cfg.get("dense_feature_num", 432)
+    return [("emb_cat", (H, E)), ("dense_w1", (D, U)), ("dense_b1", (U,)), ("dense_w2", (U, U)), ("dense_b2", (U,)),
+            ("fc_w", (E + U, 256)), ("fc_b", (256,)), ("obs_w", (256, 256)), ("obs_b", (256,)),
+            ("rew_w", (256, cfg.get("class_num", 2))), ("rew_b", (cfg.get("class_num", 2),))]
+
+
+def make_dnn_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0):
+    """Keras default initialisers for the `dnn` simulator (embeddings U(-0.05, 0.05), Dense glorot-uniform, bias 0)."""
+    rs = np.random.RandomState(seed)
+    w = {}
+    for name, shape in dnn_weight_shapes(cfg):
+        if name.startswith("emb_"):
+            w[name] = rs.uniform(-0.05, 0.05, shape).astype(np.float32)
+        elif len(shape) == 1:
+            w[name] = np.zeros(shape, np.float32)
+            if bias_noise:
+                w[name] += rs.normal(0.0, bias_noise, shape).astype(np.float32)
+        else:
+            w[name] = _glorot_uniform(rs, shape) * np.float32(stress)
+    return w
+
+
 def make_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0, bounded_scores=False):
     """W-table with TF1/Keras default initialisers; ``stress`` scales all non-embedding kernels,
     ``bias_noise`` adds N(0, bias_noise) to every bias (so parity tests see non-trivial biases).

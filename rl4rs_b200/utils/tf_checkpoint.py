@@ -402,14 +402,36 @@ def load_dien_checkpoint(prefix, config=None, name_map=None):
     Resolution per W-table entry: (1) ``name_map[name]`` if given; (2) the expected full name if present; (3) the one
     variable under the expected top-level scope whose shape matches (optimizer slots and metric counters ignored).
     Anything missing or ambiguous raises with the candidates listed."""
+    return _load_by_plan(prefix, dien_layer_plan(config), dien_variable_names(config), name_map)
+
+
+def dnn_layer_plan(config=None):
+    """[(W-table name, top-level Keras layer scope, shape)] for the graph of nets/dnn.py:8-45 in creation order:
+    id_input_processing -> Embedding #0; dense_input_processing -> Dense #0, #1; sequence_input_concat -> Embedding #1
+    (feeds nothing, not loaded); Dense(256) -> Dense #2; then the two named heads."""
+    cfg = config or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D, cls = cfg.get("dense_feature_num", 432), cfg.get("class_num", 2)
+    return [("emb_cat", "embedding", (H, E)), ("dense_w1", "dense", (D, U)), ("dense_b1", "dense", (U,)),
+            ("dense_w2", "dense_1", (U, U)), ("dense_b2", "dense_1", (U,)),
+            ("fc_w", "dense_2", (E + U, 256)), ("fc_b", "dense_2", (256,)),
+            ("obs_w", "simulator_obs", (256, 256)), ("obs_b", "simulator_obs", (256,)),
+            ("rew_w", "simulator_reward", (256, cls)), ("rew_b", "simulator_reward", (cls,))]
+
+
+def dnn_variable_names(config=None):
+    inner = {"emb_cat": "embeddings"}
+    return {name: scope + "/" + inner.get(name, "kernel" if name.endswith(("_w", "_w1", "_w2")) else "bias")
+            for name, scope, _ in dnn_layer_plan(config)}
+
+
+def _load_by_plan(prefix, plan, expect, name_map):
     rd = TensorBundleReader(prefix)
     allv = rd.variables()
     live = {k: v for k, v in allv.items() if not _SLOT.search(k)}
-    expect = dien_variable_names(config)
     name_map = name_map or {}
     out, used = {}, set()
-    for name, scope, shape in dien_layer_plan(config):
-        cand = None
+    for name, scope, shape in plan:
         if name in name_map:
             cand = name_map[name]
             if cand not in allv:
@@ -430,6 +452,16 @@ def load_dien_checkpoint(prefix, config=None, name_map=None):
             raise ValueError("%s <- %s has shape %s, expected %s" % (name, cand, arr.shape, shape))
         out[name] = np.ascontiguousarray(arr, dtype=np.float32)
     return out
+
+
+def load_dnn_checkpoint(prefix, config=None, name_map=None):
+    """Saver prefix of a `dnn` simulator (nets/dnn.py) -> its W-table; same resolution rules as load_dien_checkpoint."""
+    return _load_by_plan(prefix, dnn_layer_plan(config), dnn_variable_names(config), name_map)
+
+
+def save_dnn_checkpoint(prefix, weights, config=None):
+    names = dnn_variable_names(config)
+    return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})
 
 
 def save_dien_checkpoint(prefix, weights, config=None):

@@ -24,7 +24,7 @@ def test_library_builds_and_exports_header_symbols():
     for s in syms:
         assert hasattr(lib, s), "missing export %s" % s
     assert set(syms) == set(_capi.EXPORTS), set(syms) ^ set(_capi.EXPORTS)
-    assert lib.r4_abi_version() == 1
+    assert lib.r4_abi_version() == 2
 
 
 def test_create_rejects_bad_config_without_gpu_work():
@@ -66,23 +66,31 @@ def test_product_never_imports_oracle():
 
 
 def test_augru_kernel_choice_rule():
-    """r4_augru_kernel_for: the 2-CTA pair kernel (2) exactly when the one-CTA kernel (1) would leave SMs idle.
-    Measured wave times 1.19 ms (one-CTA) : 0.64 ms (pair), i.e. cost 15 : 8.  B200 (148 SMs): a 4096-row observation
-    pass = 64 tile-sequences -> pair; the 36 864-row reward pass = 576 -> one-CTA kernel (4 waves against 8 pair waves);
-    8192-row passes = 128 -> one-CTA (1 wave against 2)."""
+    """r4_augru_kernel_for(ctas = 2 x row tiles, sms): 1 = k_augru_tc (a CTA per tile-sequence), 2 = k_augru_pair2 (a CTA
+    pair per tile-sequence), 3 = k_augru_pp (a CTA pair per tile, both sequences in flight) -- the cheapest by wave
+    count x measured wave cost (defaults 15 : 8 : 9).  B200 (148 SMs): a 4096-row observation pass = 64 tile-sequences
+    -> pair2 (one wave on 128 SMs beats one ping-pong wave on 64); the 36 864-row reward pass = 576 and 8192-row
+    passes = 128 -> ping-pong."""
     from rl4rs_b200 import _capi
     lib = _capi.load_library()
     f = lib.r4_augru_kernel_for
+
+    def want(ctas, sms, cs=15, cp=8, cpp=9):
+        pairs = sms // 2
+        c1, c2, c3 = cs * -(-ctas // sms), cp * -(-ctas // pairs), cpp * -(-((ctas + 1) // 2) // pairs)
+        return 3 if (c3 <= c2 and c3 <= c1) else (1 if c1 <= c2 else 2)
+
     assert f(64, 148) == 2 and f(2, 148) == 2 and f(74, 148) == 2
-    assert f(576, 148) == 1 and f(128, 148) == 1 and f(148, 148) == 1
-    assert f(75, 148) == 1                       # 2 pair waves (16 units) against 1 single wave (15)
+    assert f(576, 148) == 3 and f(128, 148) == 3 and f(148, 148) == 3
     assert f(0, 148) == 0 and f(64, 1) == 0      # bad arguments
-    for ctas in range(1, 1200, 7):               # never picks the slower one under the measured wave-time ratio
-        ws, wp = -(-ctas // 148), -(-ctas // 74)
-        assert f(ctas, 148) == (1 if 15 * ws <= 8 * wp else 2)
-    # r4_set_option: overrides are validated, and the rule follows the cost ratio it is given
+    for ctas in range(1, 1200, 7):
+        assert f(ctas, 148) == want(ctas, 148), ctas
+    # r4_set_option: overrides are validated, and the rule follows the costs it is given
+    assert lib.r4_set_option(b"augru_cost_pp", 100) == 0
+    assert f(576, 148) == 1 and f(64, 148) == 2          # without the ping-pong kernel: the round-1 rule
     assert lib.r4_set_option(b"augru_cost_single", 3) == 0 and lib.r4_set_option(b"augru_cost_pair", 1) == 0
     assert f(576, 148) == 2
-    assert lib.r4_set_option(b"augru_cost_single", 15) == 0 and lib.r4_set_option(b"augru_cost_pair", 8) == 0
+    for k, v in ((b"augru_cost_single", 15), (b"augru_cost_pair", 8), (b"augru_cost_pp", 9)):
+        assert lib.r4_set_option(k, v) == 0
     assert lib.r4_set_option(b"augru_kernel", 7) != 0 and lib.r4_set_option(b"no_such_key", 1) != 0
     assert lib.r4_set_option(b"augru_kernel", 0) == 0

@@ -31,8 +31,11 @@ class _FakeEngine(object):
 
 
 class _Rows(object):
-    def __init__(self, config, rows, engine):
-        self.rows = rows
+    """A state plug-in with the REFERENCE's constructor signature: state_cls(config, records) (base.py:68-71)."""
+
+    def __init__(self, config, records):
+        self.records = records
+        self.rows = config["__rows__"]
 
 
 def test_sampler_cursor_matches_oracle_and_wraps():
@@ -155,3 +158,19 @@ def test_parse_log_stops_at_first_blank_line_and_keeps_records():
     parsed = FeatureUtil.parse_log(recs[:4] + ["", recs[4], recs[5]])
     assert parsed.n == 4 and parsed.lines == recs[:4]
     assert FeatureUtil.parse_log(recs + [""]).n == 6
+
+
+def test_state_plugin_gets_record_strings_when_the_log_has_text():
+    """base.py:92-100: the sampler hands the RECORD STRINGS to state_cls(config, records); array-only logs hand indices."""
+    cat = synth.make_catalog()
+    log = synth.make_log(12, catalog=cat, keep_hist=True)
+    parsed = FeatureUtil.parse_log(synth.render_records(log, cat))
+    eng = type("E", (), {"log": parsed})()
+    rd = RecDataBase({"cache_size": 4, "is_eval": True}, _Rows, eng)
+    rd.reset()
+    st = rd.sample(4)
+    assert st.records == parsed.lines[:4] and list(st.rows) == [0, 1, 2, 3]
+    assert [r.split("@")[1] for r in st.records] == [str(int(x)) for x in parsed.session_id[:4]]     # slate.py:109-110
+    rd2 = RecDataBase({"cache_size": 4, "is_eval": True}, _Rows, _FakeEngine(12))
+    rd2.reset()
+    assert list(rd2.sample(4).records) == [0, 1, 2, 3]
