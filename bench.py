@@ -47,11 +47,13 @@ if ROOT not in sys.path:
 
 METRIC = "env transitions/sec (SlateRecEnv-v0, batch x steps)"
 UNIT = "transitions/s"
-BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}
+BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}     # SURVEY.md section 8(d), dien: 83 732 B per row-forward
+G_DNN = 12564                                                   # dnn: algorithmic bytes per row-forward (section 8d)
+ROW_FORWARDS_PER_TRANSITION = {9: 19.0 / 9, 27: 55.0 / 27, 36: 73.0 / 36}
 CPU_THREADS = 16                                                # BLAS threads of the CPU arm (fixed: run-to-run spread)
 
 
-def base_config(B, seq=False, max_steps=None, conti=False):
+def base_config(B, seq=False, max_steps=None, conti=False, simulator="dien"):
     cfg = {"epoch": 1, "maxlen": 64, "batch_size": B, "action_size": 284, "class_num": 2,
            "dense_feature_num": 432, "category_feature_num": 21, "category_hash_size": 100000,
            "seq_num": 2, "emb_size": 128, "hidden_units": 128, "page_items": 9,
@@ -59,6 +61,8 @@ def base_config(B, seq=False, max_steps=None, conti=False):
            "is_eval": False, "cache_size": 2048, "support_rllib_mask": True}
     if conti:
         cfg["support_conti_env"] = True
+    if simulator != "dien":
+        cfg["algo"] = simulator                      # slate.py:239-242: rl4rs/nets/<algo>.py
     return cfg
 
 
@@ -138,10 +142,11 @@ class _TimedDien(object):
         return self._t(self.d.reward_layer, feat)
 
 
-def cpu_reference_episodes(B, seq, log, catalog, weights, episodes, warmup, threads=CPU_THREADS):
+def cpu_reference_episodes(B, seq, log, catalog, weights, episodes, warmup, threads=CPU_THREADS, simulator="dien"):
     """The reference's CPU path (oracle port; NumPy/OpenBLAS pinned to `threads` threads): offline-action replay
     episodes of B rows.  -> dict(value tr/s from the MEDIAN episode, per-episode times, NN share, threads)."""
     from oracle.dien_np import DienOracle
+    from oracle.dnn_np import DnnOracle
     from oracle.env_np import OracleEnv
     try:
         from threadpoolctl import threadpool_limits
@@ -153,7 +158,7 @@ def cpu_reference_episodes(B, seq, log, catalog, weights, episodes, warmup, thre
 
     def run():
         np.random.seed(0)
-        net = _TimedDien(DienOracle(weights, np.float32))
+        net = _TimedDien((DnnOracle if simulator == "dnn" else DienOracle)(weights, np.float32))
         env = OracleEnv(cfg, log, catalog, net, seq=seq)
         times, nn = [], []
         for ep in range(warmup + episodes):
@@ -190,9 +195,9 @@ def run_reference(args):
     Bs = args.cpu_sample_rows
     cat = synth.make_catalog()
     log = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=cat)
-    w = synth.make_weights(base_config(Bs, seq))
-    r = cpu_reference_episodes(Bs, seq, log, cat, w, max(args.steps, 1), max(args.warmup, 1))
-    c1 = cpu_reference_episodes(32, seq, log, cat, w, 3, 1)
+    w = synth.make_dnn_weights(base_config(Bs, seq)) if args.simulator == "dnn" else synth.make_weights(base_config(Bs, seq))
+    r = cpu_reference_episodes(Bs, seq, log, cat, w, max(args.steps, 1), max(args.warmup, 1), simulator=args.simulator)
+    c1 = cpu_reference_episodes(32, seq, log, cat, w, 3, 1, simulator=args.simulator)
     T = base_config(Bs, seq)["max_steps"]
     sample = ("%d of %d env rows per step (one offline-action replay episode = %d transitions); median of %d episodes, "
               "spread (max-min)/median %.2f, NN share of the time %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"
@@ -219,10 +224,10 @@ def workload_config(args, seq):
     else:
         learner = ("PPO discrete (MyMaskActionsModel, SoftQ T=1 rollout + one SGD epoch, sgd_minibatch_size %d TOTAL = %d per GPU)"
                    % (args.sgd_minibatch, args.sgd_minibatch // max(args.gpus, 1)))
-    return {"workload": "%s batch=%d/GPU x max_steps=%d, %s, DIEN simulator, synthetic 283-item catalog + synthetic log "
-                        "(seed 1234) + synthetic weights (seed 4321)" % (env, args.batch_per_gpu, T, learner),
+    return {"workload": "%s batch=%d/GPU x max_steps=%d, %s, %s simulator, synthetic 283-item catalog + synthetic log "
+                        "(seed 1234) + synthetic weights (seed 4321)" % (env, args.batch_per_gpu, T, learner, args.simulator.upper()),
             "batch_per_gpu": args.batch_per_gpu, "global_batch": args.batch_per_gpu * args.gpus,
-            "max_steps": T, "simulator": "dien", "algo": "none" if args.conti else args.algo,
+            "max_steps": T, "simulator": args.simulator, "algo": "none" if args.conti else args.algo,
             "sgd_minibatch_size_total": None if (args.conti or args.algo != "ppo") else args.sgd_minibatch,
             "category_hash_size": 100000,
             "parallelism": "env rows sharded by contiguous blocks, dp%d, no data-path collective" % args.gpus,
@@ -251,6 +256,8 @@ def main():
     ap.add_argument("--env", default="slate", choices=["slate", "seqslate"])
     ap.add_argument("--algo", default="ppo", choices=["ppo", "a2c"])
     ap.add_argument("--conti", action="store_true", help="continuous actions + masked kNN (BASELINE configs[3]); no learner")
+    ap.add_argument("--simulator", default="dien", choices=["dien", "dnn"],
+                    help="config['algo']: dien (BASELINE configs, tensor-bound) or dnn (nets/dnn.py, the gather-bound simulator)")
     ap.add_argument("--batch-per-gpu", type=int, default=None, help="default: 4096 at N=1, 8192 at N>1")
     ap.add_argument("--sgd-minibatch", type=int, default=None, help="PPO sgd_minibatch_size, TOTAL over GPUs (default 256 x N)")
     ap.add_argument("--cpu-sample-rows", type=int, default=128)
@@ -287,13 +294,13 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     seq = args.env == "seqslate"
     B = args.batch_per_gpu
-    cfg = base_config(B, seq, conti=args.conti)
+    cfg = base_config(B, seq, conti=args.conti, simulator=args.simulator)
     T = cfg["max_steps"]
     catalog = synth.make_catalog()
     # the log is generated once from the single seed; rank r samples from its own slice of it
     n_log = max(4 * B, 8192)
     log = synth.make_log(n_log, pages=4 if seq else 1, catalog=catalog, seed=synth.LOG_SEED + rank)
-    weights = synth.make_weights(cfg)
+    weights = synth.make_dnn_weights(cfg) if args.simulator == "dnn" else synth.make_weights(cfg)
 
     def make(fmt):
         c = dict(cfg, catalog=catalog, log=log, weights=weights, output_format=fmt, device=local_rank)
@@ -418,6 +425,25 @@ def main():
                     "share_of_step": au["ms"] / ms}
     bpt = BYTES_PER_TRANSITION.get(T, 176768)
     hbm = peaks["hbm_gbs"]
+    if args.simulator == "dnn":
+        bpt = int(round(G_DNN * ROW_FORWARDS_PER_TRANSITION.get(T, 19.0 / 9)))
+        gk = [p for p in prof if p["name"].startswith("k_cat")]
+        if gk:
+            gk = gk[0]
+            gbs = gk["work"] / (gk["ms"] / 1e3) / 1e9
+            traffic, traffic_src = None, None
+            tp = os.path.join(ROOT, "profiles", "dnn_gather_traffic.json")
+            if os.path.exists(tp):
+                tj = json.load(open(tp))
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+            roofline = {"kernel": "k_cat_pool: Embedding gather + GlobalAveragePooling1D of the dnn simulator, 21 x 512 B rows per "
+                                  "feature row staged by cp.async.bulk (1-D TMA) into shared memory, 128-bit reduction reads",
+                        "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": traffic,
+                        "traffic_source": traffic_src or "profiles/dnn_gather_traffic.json (ncu capture; the 51 MB table is L2-resident, "
+                                                          "so DRAM traffic is far below the algorithmic bytes)",
+                        "algorithmic_bytes_per_row": 21 * 4 + 21 * 512, "launches": gk["launches"],
+                        "avg_launch_ms": gk["ms"] / gk["launches"], "share_of_step": gk["ms"] / ms,
+                        "peak_source": "%s HBM copy bandwidth" % peaks["source"]}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -430,7 +456,8 @@ def main():
                        "achieved_value": value * bpt / 1e9, "frac_value": value * bpt / 1e9 / (world * hbm),
                        "achieved_env_only": env_only * bpt / 1e9, "frac_env_only": env_only * bpt / 1e9 / (world * hbm),
                        "note": "SURVEY.md 8(d): transitions/s x algorithmic bytes per transition / (N x measured HBM peak); the DIEN "
-                               "simulator is tensor-bound (111.5 MFLOP per row-forward), so this fraction is small by construction"},
+                               "simulator is tensor-bound (111.5 MFLOP per row-forward), so its fraction is small by construction; the "
+                               "dnn simulator (12 564 B per row-forward) is the gather-bound configuration"},
             "env_only": {"value": env_only, "unit": UNIT, "ms_per_step": ms_env / args.steps,
                          "note": "same rollout without the learner pass (policy sampling still on the GPU)"}}
     if exchange:
@@ -442,7 +469,7 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         Bs = args.cpu_sample_rows
         clog = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=catalog)
-        r = cpu_reference_episodes(Bs, seq, clog, catalog, weights, episodes=3, warmup=1)
+        r = cpu_reference_episodes(Bs, seq, clog, catalog, weights, episodes=3, warmup=1, simulator=args.simulator)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                 "sample": "median of 3 offline-replay episodes of %d env rows (%d transitions each) after 1 warm-up, "
                                           "%.1f s, spread %.2f, NN share %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"

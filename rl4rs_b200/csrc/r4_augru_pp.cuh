@@ -282,7 +282,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
             if (ch + PP_XD < PP_NCH) load_x8(x[(ch + PP_XD) % (PP_XD + 1)], xs, hc0 + (ch + PP_XD) * PP_CH, L[s].ln4);
 #pragma unroll
             for (int j = 0; j < PP_CH; ++j)
-              a[cur][j] = rcp_approx(1.0f + ex2_approx(P2_NL2E * (a[cur][j] + x[ch % (PP_XD + 1)][j]))) * h[s][ch * PP_CH + j];
+              a[cur][j] = rcp_sel(1.0f + ex2_approx(fminf(P2_NL2E * (a[cur][j] + x[ch % (PP_XD + 1)][j]), 60.0f)), j) * h[s][ch * PP_CH + j];
             split_store8(a[cur], L[s].aHi, L[s].aLo, a_row_off + (uint32_t)((hc0 + ch * PP_CH) / 8) * LBO);
           }
         }
@@ -339,7 +339,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
             for (int j = 0; j < PP_CH; ++j) {
               const float F = 1.0f + ex2_approx(fminf(P2_2L2E * (a[cur][j] + x[xi][j]), 60.0f));
               const float E = u[cur][j];
-              const float rc = rcp_approx(E * F);
+              const float rc = rcp_sel(E * F, j);
               const float c = fmaf(-2.0f, rc * E, 1.0f);
               const float up = oms[s] * (rc * F);
               const float hn = fmaf(up, h[s][ch * PP_CH + j] - c, c);

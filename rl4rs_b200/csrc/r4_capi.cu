@@ -118,7 +118,7 @@ int fail(r4_env* e, int code, const std::string& msg) {
 enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
        SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_XT, SL_MISC, SL_COUNT };
 const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm_tc[gru1 input proj + E_s gather]",
-    "k_gru_tc[GRU-1 tcgen05]", "k_gemm_tc[augru/att input proj]", "k_scores_tc", "k_augru_tc[AUGRU tcgen05]", "k_cat_attn",
+    "k_gru_tc[GRU-1 tcgen05]", "k_gemm_tc[augru/att input proj]", "k_scores_tc", "k_augru[AUGRU tcgen05: pair2 / pp / tc]", "k_cat_attn | k_cat_pool",
     "k_gemm_tc[dense tower]", "k_gemm_tc[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "k_query"};
 
 // Brackets one launch with CUDA events on the launching stream when profiling is on.
@@ -129,7 +129,8 @@ struct ProfScope {
     cudaEvent_t x; cudaEventCreate(&x); return x;
   }
   ProfScope(r4_env* e_, int slot_, cudaStream_t st_, double work_) : e(e_), slot(slot_), st(st_), work(work_) {
-    on = e->prof_mode == 2 || (e->prof_mode == 1 && slot == SL_AUGRU);
+    // mode 1 = the dominant kernel only: the AUGRU recurrence (dien) / the embedding gather (dnn)
+    on = e->prof_mode == 2 || (e->prof_mode == 1 && slot == (e->sim == R4_SIM_DNN ? SL_CAT : SL_AUGRU));
     if (on) { a = get(e); b = get(e); cudaEventRecord(a, st); }
   }
   ~ProfScope() {

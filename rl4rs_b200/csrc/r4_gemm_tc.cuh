@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     const int kc = tid & 3, r8 = tid >> 2;      // 64 row slots x 2 passes
     const float* arow[2] = {p.A, p.A};
     const int32_t* grow[2] = {p.gather2, p.gather2};
+    int id_cur[2] = {0, 0}, id_next[2] = {0, 0};   // gathered part: table row of the current / next 128-wide slot of each row
     int is_tile = blockIdx.x, is_kb = 0;
     auto issue = [&](int slot) {
       if (is_tile < ntiles) {
@@ -215,18 +216,26 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
             if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
             size_t src = p.gather ? (size_t)__ldg(p.gather + m) : (size_t)m;
             arow[it] = p.A + src * p.lda + kc * 8;
-            if (p.A2) grow[it] = p.gather2 + (size_t)m * p.g2_n;
+            if (p.A2) { grow[it] = p.gather2 + (size_t)m * p.g2_n; id_next[it] = __ldg(grow[it]); }   // slot 0: needed k2_start / 32 K blocks later
           }
         }
         const bool part2 = p.A2 && is_kb * G_BK >= p.k2_start;
         const int k2 = is_kb * G_BK - p.k2_start;              // offset inside the gathered part (multiple of 32)
+        if (part2 && (k2 & 127) == 0) {                        // entering slot j: its id was requested 4 K blocks ago; request j + 1
+          const int j = k2 >> 7;
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            id_cur[it] = id_next[it];
+            if (j + 1 < p.g2_n) id_next[it] = __ldg(grow[it] + j + 1);
+          }
+        }
         const bool kok = is_kb * G_BK + kc * 8 + 8 <= p.K;   // K % 8 == 0 is required; beyond K: zero fill
         const uint32_t nb = kok ? 16u : 0u;
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
           uint8_t* dst = raw + slot * G_RAW_BYTES + (it * 64 + r8) * (G_BK * 4) + kc * 32;
           const float* src = kok ? arow[it] + is_kb * G_BK : arow[it];
-          if (part2 && kok) src = p.A2 + (size_t)__ldg(grow[it] + (k2 >> 7)) * 128 + (k2 & 127) + kc * 8;
+          if (part2 && kok) src = p.A2 + (size_t)id_cur[it] * 128 + (k2 & 127) + kc * 8;
           cp_async16(dst, src, nb);
           cp_async16(dst + 16, src + 4, nb);
         }

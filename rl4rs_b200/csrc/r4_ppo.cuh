@@ -208,10 +208,23 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
   float* gout = partial + (size_t)blockIdx.x * L.n;
   const float* w1p = prm + L.o_w1;
   const float* w2p = prm + L.o_w2;
+  __shared__ uint64_t wbar;
   if (SINGLE) {
-    for (int i = tid; i < OBS * HID / 4; i += NT) reinterpret_cast<float4*>(g_s)[i] = __ldg(reinterpret_cast<const float4*>(prm + L.o_w1) + i);
+    // Both weight matrices (64 KB + 71 KB) come in through the bulk-copy engine: ONE thread issues two cp.async.bulk and
+    // everybody waits on the mbarrier right before the first use.  (ncu, round 2: the per-thread ld -> st.shared copy
+    // loop this replaces was 38 % of the kernel's 36 us -- 71 dependent L2 round trips per thread.)
     float* w2s = g_s + OBS * HID;
-    for (int i = tid; i < HID * L.A; i += NT) w2s[i] = __ldg(prm + L.o_w2 + i);
+    if (tid == 0) {
+      const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&wbar);
+      const uint32_t b1 = OBS * HID * 4, b2 = (uint32_t)(HID * L.A * 4);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(mb) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mb), "r"(b1 + b2) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((uint32_t)__cvta_generic_to_shared(g_s)), "l"(prm + L.o_w1), "r"(b1), "r"(mb) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   :: "r"((uint32_t)__cvta_generic_to_shared(w2s)), "l"(prm + L.o_w2), "r"(b2), "r"(mb) : "memory");
+    }
     w1p = g_s; w2p = w2s;
   } else {
     for (int i = tid; i < L.n; i += NT) g_s[i] = 0.f;
@@ -224,6 +237,11 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
     __syncthreads();
     if (tid < TS) { int i = min(s0 + tid, n - 1); src[tid] = idx ? idx[i] : (int64_t)i; }
     __syncthreads();
+    if (SINGLE) {                                  // the weights have landed (the barrier was initialised before the __syncthreads)
+      const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&wbar);
+      asm volatile("{\n\t.reg .pred p;\n\tPG_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra PG_DONE;\n\tbra PG_WAIT;\n\tPG_DONE:\n\t}\n"
+                   :: "r"(mb) : "memory");
+    }
     forward_tile<SINGLE>(L, prm, w1p, w2p, obs, mask, src, nvalid, obs_s, h_s, lg_s, val_s);
     // ---- per-sample loss derivatives: one warp per sample ----
     for (int s = warp; s < TS; s += NT / 32) {

@@ -112,6 +112,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float W2_s[S_N * 16];
   __shared__ float b2_s[16], kv_s[16];
+  __shared__ __align__(16) float qa_s[2][2 * S_N];      // q (Wq+Wd) + b1 of the tile's two feature rows, double buffered
   const ScoreTcSeq& S = p.s[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (p.R + 1) / 2;
@@ -216,6 +217,16 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       const int r = tile * 2 + rr;
       const int rc = min(r, p.R - 1);
       const size_t ci = S.shared ? 0 : (size_t)((p.row0 + rc) / p.div);
+      // Everything this thread needs from global memory is requested BEFORE it waits for the accumulators: its key's
+      // cached half k_t (Wk - Wd) (16 x 128-bit, one 256-byte line per lane) and, through shared memory, the tile's two
+      // query rows.  (ncu, round 1: with the loads inside the j loop the 64 x 16 FMA tail sat on the long scoreboard --
+      // 16 dependent L2 round trips per tile -- and the kernel ran at 20 % issue utilisation, 5 % of DRAM bandwidth.)
+      const float* kp = S.Kp + (ci * S_KEYS + key) * S_KP_LD;
+      float4 kk[S_N / 4];
+#pragma unroll
+      for (int j = 0; j < S_N / 4; ++j) kk[j] = __ldg(reinterpret_cast<const float4*>(kp) + j);
+      qa_s[s][e] = __ldg(S.qa + (size_t)rc * S_N + key);
+      named_bar_sync(2, 128);                      // epilogue warps only; buffer s is rewritten two tiles later
       mbar_wait(&bar_tfull[s], ph);
       tc_fence_after();
       float z[S_N];
@@ -225,16 +236,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&bar_tempty[s]);               // accumulators are free again
-      const float* kp = S.Kp + (ci * S_KEYS + key) * S_KP_LD;
-      const float* qap = S.qa + (size_t)rc * S_N;
+      const float* qap = qa_s[s] + rr * S_N;
       float o[16];
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) o[jj] = b2_s[jj];
 #pragma unroll
       for (int j = 0; j < S_N; j += 4) {
-        float4 kk = __ldg(reinterpret_cast<const float4*>(kp + j));
-        float4 qq = __ldg(reinterpret_cast<const float4*>(qap + j));
-        float zz[4] = {z[j] + qq.x + kk.x, z[j + 1] + qq.y + kk.y, z[j + 2] + qq.z + kk.z, z[j + 3] + qq.w + kk.w};
+        const float4 kq = kk[j / 4];
+        const float4 qq = *reinterpret_cast<const float4*>(qap + j);
+        float zz[4] = {z[j] + qq.x + kq.x, z[j + 1] + qq.y + kq.y, z[j + 2] + qq.z + kq.z, z[j + 3] + qq.w + kq.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           float a1 = fast_sigmoid(zz[u]);        // ex2.approx + rcp.approx (2^-22 / 1 ulp), as in the AUGRU gates

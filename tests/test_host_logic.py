@@ -1,5 +1,6 @@
 """CPU: host-side logic -- log ingest, the file-cursor sampler, synthetic data, gym shim."""
 import numpy as np
+import pytest
 
 from golden_util import Golden
 from rl4rs_b200 import synth, gymshim
@@ -174,3 +175,24 @@ def test_state_plugin_gets_record_strings_when_the_log_has_text():
     rd2 = RecDataBase({"cache_size": 4, "is_eval": True}, _Rows, _FakeEngine(12))
     rd2.reset()
     assert list(rd2.sample(4).records) == [0, 1, 2, 3]
+
+
+def test_ingest_matches_the_reference_preprocessing_fixture():
+    """slate2trajectory / data_augment (script/data_preprocess.py:6-88) against what the reference's own script wrote for
+    the same page records (tests/golden/ingest_pages.json, made by tests/golden/make_ingest_golden.py), incl. the
+    dropped last session and the global-RNG page padding; then the text -> SoA ingest of the trajectories."""
+    import json
+    import os
+    from golden_util import GOLDEN_DIR
+    from rl4rs_b200.utils import ingest
+    g = json.load(open(os.path.join(GOLDEN_DIR, "ingest_pages.json")))
+    traj = ingest.slate2trajectory(g["pages"])
+    assert traj == [x for x in g["trajectories"] if x] and len(traj) == 6          # 7 sessions in, the last one dropped
+    np.random.seed(5)
+    assert ingest.data_augment(g["short"]) == [x for x in g["augmented"] if x]
+    with pytest.raises(AssertionError):
+        ingest.slate2trajectory(g["short"])
+    log = ingest.ingest(g["pages"], trajectories=True)
+    assert log.n == 6 and log.items.shape == (6, 36) and log.feedback.shape == (6, 36) and log.lines == traj
+    first = [int(x) for p in g["pages"][1:5] for x in p.split("@")[3].split(",")]
+    np.testing.assert_array_equal(log.items[0], first)
