@@ -64,6 +64,19 @@ __device__ __forceinline__ void tma_box_cg2(uint32_t dst_smem, const CUtensorMap
                :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar_cluster) : "memory");
 }
 
+// the same, MULTICAST: one L2 read delivers the box to the same shared-memory offset of every CTA in `mask`; with
+// cta_group::2 each destination's completion bytes go to the barrier of ITS pair's even CTA (the operand names the
+// even-CTA position of the issuer's pair).  This is what lets several CTA pairs of a cluster share one weight stream.
+__device__ __forceinline__ void tma_box_cg2_mc(uint32_t dst_smem, const CUtensorMap* tm, int c0, int c1, uint32_t mbar_cluster, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+               :: "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(mbar_cluster), "h"(mask) : "memory");
+}
+// tcgen05.commit -> one arrival on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void commit2_mask(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               :: "r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+
 constexpr int P2_TM_ROW_BYTES = 1024;                             // tensor-map row = 256 x u32
 constexpr int P2_TM_BOX_ROWS = P_STAGE_BYTES / P2_TM_ROW_BYTES;   // 16 rows per ring stage
 
@@ -73,7 +86,8 @@ constexpr int P2_TM_BOX_ROWS = P_STAGE_BYTES / P2_TM_ROW_BYTES;   // 16 rows per
 // No tcgen05 fence per stage: the weights come from TMA.
 template <int GATE>
 __device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo,
-                                            uint64_t* bar_full, uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par) {
+                                            uint64_t* bar_full, uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par,
+                                            uint16_t empty_mask = 3) {
   constexpr uint32_t idesc = make_idesc(TM, HID);
   constexpr uint32_t dcol = GATE == 0 ? P_TC_R : (GATE == 1 ? P_TC_U : P_TC_C);
   constexpr uint32_t a_hi = desc_hi(A_SBO), b_hi = desc_hi(B_SBO);
@@ -96,7 +110,7 @@ __device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uin
         mma2_bf16(tbase + dcol, dal, dbh, idesc, 1u);
         mma2_bf16(tbase + dcol, dah, dbl, idesc, 1u);
       }
-      commit2(&bar_empty[stage]);
+      commit2_mask(&bar_empty[stage], empty_mask);
     }
     __syncwarp();
   }
@@ -162,8 +176,15 @@ __device__ __forceinline__ float p2_ex2(float x) { return ex2_approx(x); }
 __device__ __forceinline__ float p2_rcp(float x, int j) { return rcp_sel(x, j); }
 #endif
 
-template <int RELAY, int TMAP>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_constant__ AugruPairParams pp) {
+// CS = CTAs per cluster (2, 4 or 8; set at launch with cudaLaunchAttributeClusterDimension): CS / 2 CTA pairs working on
+// consecutive row tiles of the SAME sequence share ONE weight stream -- pair 0's producers multicast every ring stage to
+// all pairs.  Why: chip-wide the recurrence is bound by L2 throughput, not by the tensor pipe (ablation probes, round 2:
+// 128 CTAs x (393 KB weights + 196 KB inputs) per step = 75 MB against ~6300 B/clk of L2 -> 12 k cycles; without the
+// input loads 13.6 k, without any epilogue work 11.4 k of the 17.3 k-cycle step).  Sharing the stream between 2 (4)
+// pairs cuts the weight traffic to 1/2 (1/4).  Requires TMAP.
+template <int RELAY, int TMAP, int CS = 2>
+__global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_constant__ AugruPairParams pp) {
+  static_assert(CS == 2 || TMAP, "weight-stream sharing needs the tensor-map ring");
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h0, bar_h1, bar_rh, bar_r, bar_u, bar_c;
   __shared__ uint32_t tmem_base_s;
@@ -176,13 +197,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   uint8_t* sB = smem + 4 * P_A_BYTES;
   const AugruTcSeq& S = p.s[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int m0 = (blockIdx.x >> 1) * TM;      // the pair's 128-row tile
+  const uint32_t crank = cluster_ctarank();    // rank in the cluster: pair = crank >> 1
+  const uint32_t rank = crank & 1;             // rank inside the CTA pair: 0 = leader (issues the MMAs)
+  const uint32_t lead = crank & ~1u;           // cluster rank of this pair's leader
+  const int n_tiles = (p.R + TM - 1) / TM;
+  const int tile = min((int)(blockIdx.x >> 1), n_tiles - 1);   // padding pairs of the last cluster redo the last tile, unseen
+  const bool pad_pair = (int)(blockIdx.x >> 1) >= n_tiles;
+  const int m0 = tile * TM;                    // the pair's 128-row tile
+  constexpr uint16_t ALL_MASK = (uint16_t)((1u << CS) - 1);
+  const uint16_t pair_mask = (uint16_t)(3u << lead);
 
   if (tid == 0) {
     // "full": TMAP -> only the leader's barrier is used: one expect_tx arrival covering both CTAs' bytes;
     //         else the leader's collects its own TMA (expect_tx arrival) and the peer's relay arrival.
-    for (int i = 0; i < P_NST; ++i) { mbar_init(&bar_full[i], (rank == 0 && !TMAP) ? 2 : 1); mbar_init(&bar_empty[i], 1); }
+    for (int i = 0; i < P_NST; ++i) { mbar_init(&bar_full[i], (rank == 0 && !TMAP) ? 2 : 1); mbar_init(&bar_empty[i], CS / 2); }
     // hand-over barriers: RELAY -> 8 local warps (+ 1 relay arrival on the leader); else 8 warps x 2 CTAs on the leader
     const int nh = RELAY ? (rank == 0 ? 9 : 8) : 16;
     mbar_init(&bar_h0, nh); mbar_init(&bar_h1, nh); mbar_init(&bar_rh, nh);
@@ -198,8 +226,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
   cluster_sync_all();                         // the peer's barriers exist before anyone arrives remotely
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
-  const uint32_t bar_h0_leader = mapa_rank(smem_u32(&bar_h0), 0), bar_h1_leader = mapa_rank(smem_u32(&bar_h1), 0),
-                 bar_rh_leader = mapa_rank(smem_u32(&bar_rh), 0);
+  const uint32_t bar_h0_leader = mapa_rank(smem_u32(&bar_h0), lead), bar_h1_leader = mapa_rank(smem_u32(&bar_h1), lead),
+                 bar_rh_leader = mapa_rank(smem_u32(&bar_rh), lead);
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // frees 128 x 128 registers = what 232 for the 256 epilogue threads takes
@@ -209,14 +237,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         int stage = 0; uint32_t phase = 0;
         if (TMAP) {
           const CUtensorMap* tm = &pp.tmap[blockIdx.y];
-          const uint32_t full0_leader = mapa_rank(smem_u32(&bar_full[0]), 0);
+          const uint32_t full0_leader = mapa_rank(smem_u32(&bar_full[0]), lead);
           const uint32_t sB_u = smem_u32(sB);
+          // CS > 2: the two CTAs of pair 0 each multicast THEIR column half to the same-parity CTA of every pair
+          uint16_t mc_mask = 0;
+          for (int c = (int)rank; c < CS; c += 2) mc_mask |= (uint16_t)(1u << c);
           for (int t = 0; t < STEPS; ++t) {
             int row = (int)rank * P_STAGES_PER_STEP * P2_TM_BOX_ROWS;
             for (int i = 0; i < P_STAGES_PER_STEP; ++i, row += P2_TM_BOX_ROWS) {
-              mbar_wait(&bar_empty[stage], phase ^ 1);
+              mbar_wait(&bar_empty[stage], phase ^ 1);          // every pair of the cluster has released the stage
               if (rank == 0) mbar_expect_tx(&bar_full[stage], 2 * P_STAGE_BYTES);
-              tma_box_cg2(sB_u + stage * P_STAGE_BYTES, tm, 0, row, full0_leader + stage * 8);
+              if (CS == 2) tma_box_cg2(sB_u + stage * P_STAGE_BYTES, tm, 0, row, full0_leader + stage * 8);
+              else if (crank < 2) tma_box_cg2_mc(sB_u + stage * P_STAGE_BYTES, tm, 0, row, full0_leader + stage * 8, mc_mask);
               if (++stage == P_NST) { stage = 0; phase ^= 1; }
             }
           }
@@ -236,7 +268,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
     } else if (warp == 8 && rank == 1) {
       // ===== ring relay (only without the tensor map): tell the leader that this CTA's copy of stage s has landed =====
       if (!TMAP && lane == 0) {
-        const uint32_t remote0 = mapa_rank(smem_u32(&bar_full[0]), 0);
+        const uint32_t remote0 = mapa_rank(smem_u32(&bar_full[0]), lead);
         int stage = 0; uint32_t phase = 0;
         for (int i = 0; i < STEPS * P_STAGES_PER_STEP; ++i) {
           mbar_wait(&bar_full[stage], phase);
@@ -259,17 +291,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         mbar_wait_cl(&bar_h0, par);     // both CTAs' even K blocks of h (hi/lo) are in shared memory
         tc_fence_after();
         if (dbg) dbg[1] = clock64();
-        issue_gate2<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par);   // ... the odd ones by its second half
-        if (leader) commit2(&bar_r);
+        issue_gate2<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par, ALL_MASK);   // ... the odd ones by its second half
+        if (leader) commit2_mask(&bar_r, pair_mask);
         if (dbg) dbg[2] = clock64();
-        issue_gate2<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0);
-        if (leader) commit2(&bar_u);
+        issue_gate2<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0, ALL_MASK);
+        if (leader) commit2_mask(&bar_u, pair_mask);
         if (dbg) dbg[3] = clock64();
         mbar_wait_cl(&bar_rh, par);     // both CTAs' r*h written
         tc_fence_after();
         if (dbg) dbg[4] = clock64();
-        issue_gate2<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0);
-        if (leader) commit2(&bar_c);
+        issue_gate2<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0, ALL_MASK);
+        if (leader) commit2_mask(&bar_c, pair_mask);
         if (dbg) { dbg[5] = clock64(); dbg[6] = 0; dbg[7] = 0; }
       }
     } else if (RELAY && rank == 1 && lane == 0) {
@@ -295,8 +327,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
     const int hc0 = (q >> 1) * 128 + sub * 64;             // first hidden column of this thread
     const uint32_t tcol = (uint32_t)sub * 64;              // TMEM column offset inside a gate
     int r = m0 + prow;
-    const bool valid = r < p.R;
-    if (!valid) r = p.R - 1;
+    const bool valid = r < p.R && !pad_pair;
+    if (r >= p.R) r = p.R - 1;
     const int ci = S.shared ? 0 : (p.row0 + r) / p.div;
     const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM;
     const int ln4 = (ci % TM) * 4;

@@ -239,11 +239,13 @@ struct AugruOpts {
   int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel (one recurrence per pair), 3 ping-pong pair kernel
   int pair_impl = 1;      // 1 = k_augru_pair2<R4P2_RELAY, R4P2_TMAP>, 2..4 = <0,1> <1,0> <0,0>
   // cost of one wave, measured (tools/augru_probe.cu, ms x 12.5): k_augru_tc 1.19 ms per 148 tile-sequences,
-  // k_augru_pair2 0.64 ms per 74, k_augru_pp 0.72 ms per 74 TILES (= 148 tile-sequences)
-  int cost_single = 15, cost_pair = 8, cost_pp = 9;
+  // k_augru_pair2 0.64 ms per 74, k_augru_pp 1.0 ms per 74 TILES (= 148 tile-sequences)
+  int cost_single = 15, cost_pair = 8, cost_pp = 13;
+  int cluster = 2;        // CTAs per cluster of the pair kernel: 2, or 4 / 8 = weight stream shared by 2 / 4 pairs (multicast)
   AugruOpts() {
     if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
     if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
+    if (const char* e = getenv("R4_AUGRU_CLUSTER")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) cluster = v; }
     if (const char* e = getenv("R4_AUGRU_RULE")) {
       int a = 0, b = 0, c = 0;
       int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
@@ -380,12 +382,24 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     } else {
       r4tc::AugruPairParams pp;
       pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
-      switch (augru_pair_impl()) {
-        case 2: r4tc::k_augru_pair2<0, 1><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
-        case 3: r4tc::k_augru_pair2<1, 0><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
-        case 4: r4tc::k_augru_pair2<0, 0><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
-        default: r4tc::k_augru_pair2<R4P2_RELAY, R4P2_TMAP><<<pgrid, r4tc::NTHREADS, r4tc::P_SMEM_BYTES, st>>>(pp); break;
+      // cluster size = CTAs sharing one weight stream (2 = one pair, 4 / 8 = 2 / 4 pairs: multicast ring)
+      const int cs = augru_opts().cluster;
+      cudaLaunchConfig_t lc = {};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      lc.gridDim = dim3((pgrid.x + cs - 1) / cs * cs, 2); lc.blockDim = dim3(r4tc::NTHREADS);
+      lc.dynamicSmemBytes = r4tc::P_SMEM_BYTES; lc.stream = st; lc.attrs = at; lc.numAttrs = 1;
+      cudaError_t le;
+      if (cs == 4) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, 1, 4>, pp);
+      else if (cs == 8) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, 1, 8>, pp);
+      else switch (augru_pair_impl()) {
+        case 2: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 1, 2>, pp); break;
+        case 3: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<1, 0, 2>, pp); break;
+        case 4: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 0, 2>, pp); break;
+        default: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, R4P2_TMAP, 2>, pp); break;
       }
+      (void)le;
     } }
   R4_LAUNCH_CHECK(e, augru_choice(2 * rtiles) == 1 ? "k_augru_tc" : (augru_choice(2 * rtiles) == 3 ? "k_augru_pp" : "k_augru_pair2"));
   if (!no_side && !side_early && (rc = side_work())) return rc;
@@ -535,12 +549,14 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<R4P2_RELAY, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<R4P2_RELAY, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
@@ -913,6 +929,7 @@ int r4_set_option(const char* key, int value) {
   else if (k == "augru_cost_single" && value > 0) o.cost_single = value;
   else if (k == "augru_cost_pair" && value > 0) o.cost_pair = value;
   else if (k == "augru_cost_pp" && value > 0) o.cost_pp = value;
+  else if (k == "augru_cluster" && (value == 2 || value == 4 || value == 8)) o.cluster = value;
   else return fail(nullptr, R4_ERR_ARG, "r4_set_option: unknown key or value out of range: " + k);
   return R4_OK;
 }

@@ -55,6 +55,7 @@ def test_dnn_env_matches_oracle(seq):
         o, r = env.reset(), ref.reset()
         assert_close_rel(o["obs"], r["obs"], what="dnn env reset obs")
         np.testing.assert_array_equal(o["action_mask"], r["action_mask"])
+        paid = 0
         for t in range(cfg["max_steps"]):
             a = np.where(rs.rand(B) < 0.8, ref.offline_action, rs.randint(0, 284, B))
             o, rew, done, info = env.step(a)
@@ -64,7 +65,8 @@ def test_dnn_env_matches_oracle(seq):
             np.testing.assert_array_equal(env.samples.get_violation(), ref.samples.get_violation())
             assert_close_rel(o["obs"], r["obs"], what="dnn env obs step %d" % t)
             assert_close_rel(rew, rrew, what="dnn env reward step %d" % t)
-        assert (np.asarray(rrew) != 0).any()
+            paid += int((np.asarray(rrew) != 0).any())
+        assert paid >= 1          # (SeqSlate: one early violation zeroes every later page, so only the first pages pay)
 
 
 def test_dnn_big_batch_oracle_sample():

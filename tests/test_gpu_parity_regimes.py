@@ -44,7 +44,7 @@ def augru_option():
     from rl4rs_b200 import _capi
 
     def force(mode):
-        _capi.set_option("augru_kernel", {"auto": 0, "single": 1, "pair": 2}[mode])
+        _capi.set_option("augru_kernel", {"auto": 0, "single": 1, "pair": 2, "pp": 3}[mode])
     yield force
     _capi.set_option("augru_kernel", 0)
 
@@ -131,7 +131,7 @@ def _random_feature_rows(R, seed, hash_size):
 
 
 @pytest.mark.parametrize("regime", ["default", "stress"])
-@pytest.mark.parametrize("kernel", ["single", "pair"])
+@pytest.mark.parametrize("kernel", ["single", "pair", "pp"])
 def test_dien_forward_each_augru_kernel(kernel, regime, augru_option):
     """The simulator alone on 200 random feature rows through EACH AUGRU kernel, both weight regimes."""
     from oracle.dien_np import DienOracle
@@ -152,7 +152,7 @@ def test_dien_forward_each_augru_kernel(kernel, regime, augru_option):
     assert_close_rel(probs.cpu().numpy(), p_ref, what="dien probs [%s, %s]" % (kernel, regime))
 
 
-@pytest.mark.parametrize("kernel", ["single", "pair"])
+@pytest.mark.parametrize("kernel", ["single", "pair", "pp"])
 @pytest.mark.parametrize("name", ["slate_rllib_replay", "seqslate27_plain_mixed"])
 def test_env_fixture_each_augru_kernel(name, kernel, augru_option):
     """Two reference-made fixtures end to end with the AUGRU kernel forced (obs + reward passes)."""

@@ -18,7 +18,11 @@
 #include "../rl4rs_b200/csrc/r4_augru_pp.cuh"
 #define KERNEL (k_augru_pp<P2RELAY>)
 #else
-#define KERNEL (k_augru_pair2<P2RELAY, P2TMAP>)
+#ifndef P2CS
+#define P2CS 2
+#endif
+#define KERNEL (k_augru_pair2<P2RELAY, P2TMAP, P2CS>)
+#define CLUSTER P2CS
 #endif
 #endif
 #ifdef PP
@@ -110,7 +114,15 @@ int main(int argc, char** argv) {
 #ifdef PAIR2
   CUtensorMap tmap;
   { int trc = make_pair_tensor_map(dimg, &tmap); if (trc) { printf("make_pair_tensor_map failed: %d\n", trc); return 1; } }
+#ifdef CLUSTER
+#define LAUNCH(grid, prm) do { AugruPairParams pp_; pp_.b = (prm); pp_.tmap[0] = tmap; pp_.tmap[1] = tmap; \
+    cudaLaunchConfig_t lc_ = {}; dim3 g_ = (grid); g_.x = (g_.x + CLUSTER - 1) / CLUSTER * CLUSTER; lc_.gridDim = g_; lc_.blockDim = dim3(KTHREADS); \
+    lc_.dynamicSmemBytes = KSMEM; cudaLaunchAttribute at_[1]; at_[0].id = cudaLaunchAttributeClusterDimension; \
+    at_[0].val.clusterDim.x = CLUSTER; at_[0].val.clusterDim.y = 1; at_[0].val.clusterDim.z = 1; lc_.attrs = at_; lc_.numAttrs = 1; \
+    CK(cudaLaunchKernelEx(&lc_, KERNEL, pp_)); } while (0)
+#else
 #define LAUNCH(grid, prm) do { AugruPairParams pp_; pp_.b = (prm); pp_.tmap[0] = tmap; pp_.tmap[1] = tmap; KERNEL<<<grid, KTHREADS, KSMEM>>>(pp_); } while (0)
+#endif
 #else
 #define LAUNCH(grid, prm) KERNEL<<<grid, KTHREADS, KSMEM>>>(prm)
 #endif
