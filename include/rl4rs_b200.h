@@ -48,8 +48,12 @@ enum { R4_ENV_SLATE = 0, R4_ENV_SEQSLATE = 1 };   /* rl4rs/__init__.py:10-18 */
 /* config['algo'] (slate.py:239-242): which rl4rs/nets/<algo>.py graph the simulator is.
  *   DIEN  nets/dien.py:8-45   (sequence GRU/attention/AUGRU + dense tower + category attention; tensor-bound)
  *   DNN   nets/dnn.py:8-45    (mean-pooled category embeddings + dense tower + FC 256 + simulator_obs; gather-bound:
- *                              the sequence branch of that graph does not reach the output and is not evaluated) */
-enum { R4_SIM_DIEN = 0, R4_SIM_DNN = 1 };
+ *                              the sequence branch of that graph does not reach the output and is not evaluated)
+ *   WIDEDEEP  nets/widedeep.py:8-45 (mean-pooled sequence embeddings -> Dense 256 | dense tower | flattened category
+ *                              embeddings; 'simulator_obs' IS that 3072-wide concat, so obs buffers are f32 [B,3072]) */
+enum { R4_SIM_DIEN = 0, R4_SIM_DNN = 1, R4_SIM_WIDEDEEP = 2 };
+/* width of the observation a simulator produces (256, or 3072 for widedeep) */
+int r4_obs_dim(int simulator);
 
 /* The config dict of the reference scripts (simulator_eval.py:9-12, modelfree_train.py:32-37). */
 typedef struct {
@@ -68,14 +72,14 @@ typedef struct {
   int32_t emb_size;             /* 128 */
   int32_t hidden_units;         /* 128 */
   int32_t max_rows_per_pass;    /* 0 = default; bound on simulator rows per launch group */
-  int32_t simulator;            /* R4_SIM_DIEN | R4_SIM_DNN (ABI version >= 2) */
+  int32_t simulator;            /* R4_SIM_DIEN | R4_SIM_DNN | R4_SIM_WIDEDEEP (ABI version >= 2) */
 } r4_config;
 
 /* Per-call output buffers (device, caller-owned).  NULL = not wanted.
  * Replaces the return values of RecSimBase._step / sample (base.py:157-175) and
  * SlateRecEnv.obs_fn (slate.py:244-279). */
 typedef struct {
-  float*   obs;          /* f32 [B,256]   simulator_obs layer (dien.py:35); NULL with RAWSTATE */
+  float*   obs;          /* f32 [B,256]   simulator_obs layer (dien.py:35; [B,3072] for widedeep); NULL with RAWSTATE */
   uint8_t* action_mask;  /* u8  [B,A]     action_mask & location_mask & special_mask (slate.py:93-97) */
   double*  reward;       /* f64 [B]       slate.py:281-308 / seqslate.py:136-160 */
   uint8_t* done;         /* u8  [B]       base.py:165-168 */

@@ -35,6 +35,19 @@ def dnn_forward(w, dense, cat):
     return obs.numpy(), F.softmax(F.linear(obs, _t(w, "rew_w").T, _t(w, "rew_b")), dim=-1).numpy()
 
 
+def widedeep_forward(w, seq, dense, cat):
+    seq = torch.as_tensor(seq, dtype=torch.long)
+    cat = torch.as_tensor(cat, dtype=torch.long)
+    es = _t(w, "emb_seq")
+    pooled = torch.cat([F.embedding(seq[:, i], es).sum(dim=1) / seq.shape[2] for i in range(seq.shape[1])], dim=1)
+    s = F.elu(F.linear(pooled, _t(w, "fc_w").T, _t(w, "fc_b")))
+    x = torch.as_tensor(dense, dtype=torch.float64)
+    for i in (1, 2):
+        x = F.elu(F.linear(x, _t(w, "dense_w%d" % i).T, _t(w, "dense_b%d" % i)))
+    obs = torch.cat([s, x, F.embedding(cat, _t(w, "emb_cat")).flatten(1)], dim=1)
+    return obs.numpy(), F.softmax(F.linear(obs, _t(w, "rew_w").T, _t(w, "rew_b")), dim=-1).numpy()
+
+
 def _gru_step(x, h, wg, bg, wc, bc, att=None):
     """One step of TF1 GRUCell / deepctr VecAttGRUCell with the fused kernels split per gate and per input half."""
     nx, nh = x.shape[1], h.shape[1]

@@ -11,8 +11,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr
 
 FLAG_RLLIB_MASK, FLAG_D3RL_MASK, FLAG_CONTI, FLAG_ONEHOT, FLAG_RAWSTATE, FLAG_INFO_FETCH = 1, 2, 4, 8, 16, 32
 ENV_SLATE, ENV_SEQSLATE = 0, 1
-SIM_DIEN, SIM_DNN = 0, 1
-SIMULATORS = {"dien": SIM_DIEN, "dnn": SIM_DNN}
+SIM_DIEN, SIM_DNN, SIM_WIDEDEEP = 0, 1, 2
+SIMULATORS = {"dien": SIM_DIEN, "dnn": SIM_DNN, "widedeep": SIM_WIDEDEEP}
 
 
 class R4Config(C.Structure):
@@ -52,6 +52,7 @@ EXPORTS = {
     "r4_profile_read": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int64), C.POINTER(C.c_double)]),
     "r4_abi_version": (C.c_int, []),
+    "r4_obs_dim": (C.c_int, [C.c_int]),
     "r4_augru_kernel_for": (C.c_int, [C.c_int, C.c_int]),
     "r4_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "r4_policy_num_params": (C.c_int, [C.c_int]),

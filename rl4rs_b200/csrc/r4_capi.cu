@@ -71,7 +71,9 @@ struct r4_env {
   float *wo = nullptr, *bo = nullptr, *wr = nullptr, *br = nullptr;
   uint8_t *w1_img = nullptr, *w2_img = nullptr, *wo_img = nullptr;   // tensor-core images (r4_gemm_tc.cuh)
   int sim = R4_SIM_DIEN;                                             // config['algo']: which simulator graph
-  float* fcb = nullptr; uint8_t *fc_img = nullptr;                   // dnn: the unnamed Dense(256, ELU) of nets/dnn.py:34
+  float* fcb = nullptr; uint8_t *fc_img = nullptr;                   // dnn: the unnamed Dense(256, ELU) of nets/dnn.py:34; widedeep: nets/widedeep.py:34
+  int obs_dim = OBSD;                                                // 256, or 3072 for widedeep
+  DevBuf ws_seq;                                                     // widedeep: sequence ids of a pass, i32 [R,2,64]
   PerSeq ps[2];
   bool weights_ready = false;
   std::vector<void*> owned;
@@ -281,6 +283,33 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
                  const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
                  float* p1_out, float* probs_out, cudaStream_t st) {
   int rc;
+  if (e->sim == R4_SIM_WIDEDEEP) {
+    // nets/widedeep.py:31-38: simulator_obs = [Dense256(ELU)(seq mean-pools) | dense tower | Flatten(E_c[cat])]; softmax head on it.
+    // The sequence ids of the pass rows are in e->ws_seq (obs / reward passes: k_seq_ids_rows; r4_dien_forward: the caller's).
+    if ((rc = reserve(e, e->ws_allf, (size_t)R * 2 * EMB * 4))) return rc;
+    if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
+    float* pooled = reinterpret_cast<float*>(e->ws_allf.p);
+    float* tmp = reinterpret_cast<float*>(e->ws_tmp.p);
+    float* obs = obs_out;
+    if (!obs) {
+      if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD_WD * 4))) return rc;
+      obs = reinterpret_cast<float*>(e->ws_obs.p);
+    }
+    { ProfScope ps(e, SL_CAT, st, (double)R * (2 * MAXLEN * EMB * 4 + NCAT * EMB * 4));
+      k_seq_pool<<<(R + 3) / 4, 128, 0, st>>>(R, reinterpret_cast<const int32_t*>(e->ws_seq.p), e->emb_seq, pooled);
+      k_cat_flatten<<<(R + 3) / 4, 128, 0, st>>>(R, cat, e->emb_cat, obs + 2 * EMB + HU, OBSD_WD); }
+    R4_LAUNCH_CHECK(e, "k_seq_pool / k_cat_flatten");
+    e->launches++;
+    if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, 2 * EMB, 2 * EMB, pooled, 2 * EMB, nullptr, e->fc_img, e->fcb, obs, OBSD_WD, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, obs + 2 * EMB, OBSD_WD, st))) return rc;
+    if (p1_out || probs_out) {
+      { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD_WD * 2);
+        k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out, OBSD_WD); }
+      R4_LAUNCH_CHECK(e, "k_reward_head");
+    }
+    return R4_OK;
+  }
   if (e->sim == R4_SIM_DNN) {
     // nets/dnn.py:31-37: all = [mean_t E_c[cat] | dense tower]; Dense(256, ELU); simulator_obs Dense(256, ELU); softmax head
     if ((rc = reserve(e, e->ws_allf, (size_t)R * 2 * HU * 4))) return rc;
@@ -432,6 +461,17 @@ int assemble(r4_env* e, int mode, int step, int rpe, int row0, int nrows, int32_
 
 const SeqCache& seq1_cache(const r4_env* e) { return e->c1_is_page ? e->c1page : e->c1const; }
 
+// widedeep reads the raw sequence ids of its pass rows (no sequence cache): stage them in e->ws_seq
+int stage_seq_rows(r4_env* e, int R, int row0, int div, int p0, cudaStream_t st) {
+  if (e->sim != R4_SIM_WIDEDEEP) return R4_OK;
+  int rc;
+  if ((rc = reserve(e, e->ws_seq, (size_t)R * 2 * MAXLEN * 4))) return rc;
+  k_seq_rows<<<(R * MAXLEN + 255) / 256, 256, 0, st>>>(R, row0, div, e->T, p0, e->row_idx, e->log_seq, e->prev_actions,
+                                                      reinterpret_cast<int32_t*>(e->ws_seq.p));
+  R4_LAUNCH_CHECK(e, "k_seq_rows");
+  return R4_OK;
+}
+
 // obs pass for the current state (mode 0 after reset, mode 1 after act at `step`)
 int obs_pass(r4_env* e, int mode, int step, const r4_out* out, cudaStream_t st) {
   int rc;
@@ -450,8 +490,9 @@ int obs_pass(r4_env* e, int mode, int step, const r4_out* out, cudaStream_t st) 
     if ((rc = assemble(e, mode, step, 1, r0, nr, cat, dense, st))) return rc;
     if (need_obs) {
       const SeqCache& c1 = seq1_cache(e);
+      if ((rc = stage_seq_rows(e, nr, r0, 1, (mode == 1 && e->seq) ? step / e->P * e->P : 0, st))) return rc;
       if ((rc = forward_rows(e, nr, r0, 1, cat, dense, e->c0, 0, c1, e->c1_is_page ? 0 : 1,
-                             out->obs + (size_t)r0 * OBSD, nullptr, nullptr, st))) return rc;
+                             out->obs + (size_t)r0 * e->obs_dim, nullptr, nullptr, st))) return rc;
     }
   }
   return R4_OK;
@@ -473,6 +514,7 @@ int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st) {
     int32_t* cat = (int32_t*)e->ws_cat.p;
     float* dense = (float*)e->ws_dense.p;
     if ((rc = assemble(e, 2, cur_after, rpe, b0 * rpe, nr, cat, dense, st))) return rc;
+    if ((rc = stage_seq_rows(e, nr, b0 * rpe, rpe, e->seq ? cur_after - e->P : 0, st))) return rc;
     const SeqCache& c1 = seq1_cache(e);
     if ((rc = forward_rows(e, nr, b0 * rpe, rpe, cat, dense, e->c0, 0, c1, e->c1_is_page ? 0 : 1, nullptr,
                            p1 + (size_t)b0 * rpe, nullptr, st))) return rc;
@@ -511,6 +553,7 @@ const float* hw_get(r4_env* e, const std::string& name, size_t n) {
 extern "C" {
 
 int r4_abi_version(void) { return 2; }
+int r4_obs_dim(int simulator) { return simulator == R4_SIM_WIDEDEEP ? OBSD_WD : OBSD; }
 
 const char* r4_last_error(const r4_env* env) { return env ? env->err.c_str() : g_create_error.c_str(); }
 
@@ -531,8 +574,8 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
     return fail(nullptr, R4_ERR_ARG, "r4_create: SeqSlateRecEnv needs max_steps to be a multiple of page_items");
   if (cfg->category_hash_size < cfg->action_size)
     return fail(nullptr, R4_ERR_ARG, "r4_create: category_hash_size must cover the item ids");
-  if (cfg->simulator != R4_SIM_DIEN && cfg->simulator != R4_SIM_DNN)
-    return fail(nullptr, R4_ERR_ARG, "r4_create: simulator must be R4_SIM_DIEN or R4_SIM_DNN (config['algo'] = 'dien' | 'dnn')");
+  if (cfg->simulator < R4_SIM_DIEN || cfg->simulator > R4_SIM_WIDEDEEP)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: simulator must be R4_SIM_DIEN, R4_SIM_DNN or R4_SIM_WIDEDEEP (config['algo'] = 'dien' | 'dnn' | 'widedeep')");
   cudaError_t st = cudaSetDevice(device);
   if (st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(st));
   r4_env* e = new r4_env();
@@ -542,6 +585,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   e->B = cfg->batch_size; e->seq = cfg->env_kind == R4_ENV_SEQSLATE; e->hash = cfg->category_hash_size;
   e->max_rows = cfg->max_rows_per_pass > 0 ? cfg->max_rows_per_pass : 36864;
   e->sim = cfg->simulator;
+  e->obs_dim = cfg->simulator == R4_SIM_WIDEDEEP ? OBSD_WD : OBSD;
   bool ok = cudaMalloc(&e->row_idx, (size_t)e->B * 4) == cudaSuccess &&
             cudaMalloc(&e->prev_actions, (size_t)e->B * e->T * 4) == cudaSuccess &&
             cudaMalloc(&e->amask, (size_t)e->B * e->words * 4) == cudaSuccess &&
@@ -583,7 +627,7 @@ void r4_destroy(r4_env* e) {
   DevBuf* bufs[] = {&e->c0.H, &e->c0.Kp, &e->c1const.H, &e->c1const.Kp, &e->c1page.H, &e->c1page.Kp,
                     &e->c0.XT, &e->c1const.XT, &e->c1page.XT,
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
-                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q};
+                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q, &e->ws_seq};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
@@ -636,6 +680,28 @@ int r4_finalize_weights(r4_env* e, void* stream) {
   R4_CUDA(e, cudaSetDevice(e->device));
   const size_t Hh = (size_t)e->hash;
   struct Need { const char* n; size_t sz; };
+  if (e->sim == R4_SIM_WIDEDEEP) {
+    // W-table of nets/widedeep.py:8-45: emb_cat, dense tower, emb_seq (ONE table for both sequences), fc [256,256] (the
+    // Dense on the pooled sequences, :34), simulator_reward [3072,2]; 'simulator_obs' is a Concatenate (no weights)
+    std::vector<Need> need = {{"emb_cat", Hh * EMB}, {"emb_seq", Hh * EMB}, {"dense_w1", (size_t)NDENSE * HU}, {"dense_b1", HU},
+                              {"dense_w2", (size_t)HU * HU}, {"dense_b2", HU}, {"fc_w", (size_t)2 * EMB * 2 * EMB}, {"fc_b", 2 * EMB},
+                              {"rew_w", (size_t)OBSD_WD * 2}, {"rew_b", 2}};
+    for (auto& nd : need)
+      if (!hw_get(e, nd.n, nd.sz)) return fail(e, R4_ERR_ARG, std::string("r4_finalize_weights(widedeep): missing or mis-shaped ") + nd.n);
+    for (void* p : e->owned) cudaFree(p);
+    e->owned.clear();
+    int rc;
+    if ((rc = upload(e, e->hw["emb_cat"], &e->emb_cat)) || (rc = upload(e, e->hw["emb_seq"], &e->emb_seq)) ||
+        (rc = upload(e, e->hw["dense_b1"], &e->b1)) || (rc = upload(e, e->hw["dense_b2"], &e->b2)) ||
+        (rc = upload(e, e->hw["fc_b"], &e->fcb)) || (rc = upload(e, e->hw["rew_w"], &e->wr)) ||
+        (rc = upload(e, e->hw["rew_b"], &e->br)) ||
+        (rc = upload_image(e, e->hw["dense_w1"].data(), NDENSE, HU, &e->w1_img)) ||
+        (rc = upload_image(e, e->hw["dense_w2"].data(), HU, HU, &e->w2_img)) ||
+        (rc = upload_image(e, e->hw["fc_w"].data(), 2 * EMB, 2 * EMB, &e->fc_img))) return rc;
+    e->hw.clear();
+    e->weights_ready = true;
+    return R4_OK;
+  }
   if (e->sim == R4_SIM_DNN) {
     // W-table of nets/dnn.py:8-45: emb_cat [H,128], dense tower, fc [256,256] (the unnamed Dense of :34), simulator_obs
     // [256,256], simulator_reward [256,2].  The graph's second Embedding (sequence_input_concat) feeds nothing.
@@ -1210,7 +1276,8 @@ int r4_ppo_epoch_dist(r4_comm* c, float* params, const float* obs, const uint8_t
                               action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, inv, scratch, G, scratch, nullptr, 0.f,
                               stream, false);
     if (rc) return rc;
-    rc = exchange_launch(c, scratch, G, np, flat_grad, stats_accum, inv, 1, params, m, v, step0 + steps + 1, lr, beta1, beta2,
+    // statistics stay per-rank means over this rank's mb samples (the trainer averages them over the ranks)
+    rc = exchange_launch(c, scratch, G, np, flat_grad, stats_accum, 1.0f / (float)mb, 1, params, m, v, step0 + steps + 1, lr, beta1, beta2,
                          eps, stream);
     if (rc) return rc;
   }
@@ -1224,13 +1291,17 @@ int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int
   R4_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = S(stream);
   int rc;
-  if (e->sim == R4_SIM_DNN) {           // no sequence branch: straight through forward_rows
+  if (e->sim != R4_SIM_DIEN) {          // dnn: no sequence branch; widedeep: raw ids, no sequence cache
     rc = R4_OK;
     int chunk = std::min(n_rows, e->max_rows);
     for (int r0 = 0; !rc && r0 < n_rows; r0 += chunk) {
       int nr = std::min(chunk, n_rows - r0);
+      if (e->sim == R4_SIM_WIDEDEEP) {
+        if ((rc = reserve(e, e->ws_seq, (size_t)nr * 2 * MAXLEN * 4))) return rc;
+        R4_CUDA(e, cudaMemcpyAsync(e->ws_seq.p, seq + (size_t)r0 * 2 * MAXLEN, (size_t)nr * 2 * MAXLEN * 4, cudaMemcpyDeviceToDevice, st));
+      }
       rc = forward_rows(e, nr, r0, 1, cat + (size_t)r0 * NCAT, dense + (size_t)r0 * NDENSE, e->c0, 0, e->c0, 0,
-                        obs ? obs + (size_t)r0 * OBSD : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
+                        obs ? obs + (size_t)r0 * e->obs_dim : nullptr, nullptr, probs ? probs + (size_t)r0 * 2 : nullptr, st);
     }
     return rc;
   }

@@ -23,7 +23,8 @@ constexpr int HU = 128;         // hidden_units (dense tower)
 constexpr int AH1 = 64;         // attention MLP hidden 1
 constexpr int AH2 = 16;         // attention MLP hidden 2
 constexpr int AUH = 256;        // AUGRU hidden (emb_size * 2, nets/utils.py:123)
-constexpr int OBSD = 256;       // simulator_obs width (dien.py:35)
+constexpr int OBSD = 256;       // simulator_obs width (dien.py:35, dnn.py:35)
+constexpr int OBSD_WD = 2 * EMB + HU + NCAT * EMB;   // 3072: widedeep's simulator_obs is the concat itself (widedeep.py:35-37)
 constexpr int ALLF = 2 * AUH + HU + EMB + NCAT * EMB;   // 3456, dien.py:34
 constexpr int XIN_LD = 3 * EMB;                          // GRU-1 input projection: [r|u|c] = 384
 constexpr int XK_LD = 2 * AUH + AUH + AH1;               // AUGRU input proj [r|u (512) | c (256) | key (64)] = 832
@@ -367,12 +368,65 @@ __global__ void __launch_bounds__(POOL_WARPS * 32) k_cat_pool(int R, const int32
 }
 
 // ------------------------------------------------------------------------------------------
+// widedeep simulator (nets/widedeep.py:31-38): the two gather halves of its 3072-wide 'simulator_obs' concat.
+//   k_seq_pool     sequence_input_concat (nets/utils.py:56-77): per sequence GlobalAveragePooling1D over the 64
+//                  embedded positions (ONE shared table; pad id 0 is embedded and averaged like any id) -> [R, 2 x 128]
+//   k_cat_flatten  id_input_processing_concat (nets/utils.py:38-45): Flatten(Embedding(cat)) -> obs[r, 384:3072]
+// One warp per feature row, 128-bit loads, coalesced 512-byte stores.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_seq_pool(int R, const int32_t* __restrict__ seq /*[R,2,64]*/,
+                                                  const float* __restrict__ emb_seq, float* __restrict__ out /*[R,256]*/) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int32_t* ids = seq + ((size_t)r * 2 + s) * MAXLEN;
+    const int id0 = __ldg(ids + lane), id1 = __ldg(ids + 32 + lane);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+    for (int t = 0; t < MAXLEN; ++t) {
+      const int id = __shfl_sync(0xffffffffu, t < 32 ? id0 : id1, t & 31);
+      const float4 v = ldg4(emb_seq + (size_t)id * EMB + lane * 4);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    const float n = (float)MAXLEN;
+    *reinterpret_cast<float4*>(out + (size_t)r * 2 * EMB + s * EMB + lane * 4) = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
+  }
+}
+// sequence ids of the rows of one simulator pass (pass row i -> env row (row0 + i) / div): seq0 = user history, seq1 = the
+// items of the previous pages (seqslate.py:36-37,109-110) or zeros, as k_seq_ids
+__global__ void k_seq_rows(int R, int row0, int div, int T, int p0, const int32_t* __restrict__ row_idx,
+                           const int32_t* __restrict__ log_seq, const int32_t* __restrict__ prev_actions,
+                           int32_t* __restrict__ out /*[R,2,64]*/) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= R * MAXLEN) return;
+  const int rr = i / MAXLEN, t = i % MAXLEN;
+  const int b = (row0 + rr) / div;
+  const int n = p0 < MAXLEN ? p0 : MAXLEN;
+  int v1 = 0;
+  if (t >= MAXLEN - n) v1 = prev_actions[(size_t)b * T + (p0 - n) + (t - (MAXLEN - n))];
+  out[(size_t)rr * 2 * MAXLEN + t] = log_seq[(size_t)row_idx[b] * MAXLEN + t];
+  out[(size_t)rr * 2 * MAXLEN + MAXLEN + t] = v1;
+}
+__global__ void __launch_bounds__(128) k_cat_flatten(int R, const int32_t* __restrict__ cat, const float* __restrict__ emb_cat,
+                                                     float* __restrict__ out, int out_ld) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int id = lane < NCAT ? __ldg(cat + (size_t)r * NCAT + lane) : 0;
+#pragma unroll 7
+  for (int j = 0; j < NCAT; ++j) {
+    const int idj = __shfl_sync(0xffffffffu, id, j);
+    *reinterpret_cast<float4*>(out + (size_t)r * out_ld + j * EMB + lane * 4) = ldg4(emb_cat + (size_t)idj * EMB + lane * 4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // K10 tail: probs = softmax(obs Wr + br) (dien.py:36); click prob = probs[:,1] (slate.py:298).
-// One warp per row, warp-shuffle reduction of the two 256-long dots.
+// One warp per row, warp-shuffle reduction of the two OBSD-long dots (OBSD = 256; 3072 for widedeep).
 // ------------------------------------------------------------------------------------------
 __global__ void k_reward_head(int R, const float* __restrict__ obs, const float* __restrict__ Wr,
                               const float* __restrict__ br, float* __restrict__ p1 /*[R] or null*/,
-                              float* __restrict__ probs /*[R,2] or null*/) {
+                              float* __restrict__ probs /*[R,2] or null*/, int OBSD = 256) {
   int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (r >= R) return;

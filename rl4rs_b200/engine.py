@@ -60,6 +60,7 @@ class Engine(object):
         rc = self.lib.r4_create(C.byref(cfg), self.device.index, C.byref(h))
         _capi.check(self.lib, None, rc, "r4_create")
         self.h = h
+        self.obs_dim = int(self.lib.r4_obs_dim(_capi.SIMULATORS[config.get("algo", "dien")]))
         self.stream = torch.cuda.current_stream(self.device)
         self._load_items(catalog)
         self._load_weights(weights)
@@ -122,7 +123,7 @@ class Engine(object):
         dev, B = self.device, self.B
         z = lambda shape, dt: torch.zeros(shape, dtype=dt, device=dev)
         self.rows = z((B,), torch.int32)
-        self.obs = None if self.raw else z((B, OBS_DIM), torch.float32)
+        self.obs = None if self.raw else z((B, self.obs_dim), torch.float32)
         self.mask = z((B, self.A), torch.uint8) if self.rllib else None
         self.reward = z((B,), torch.float64)
         self.chosen = z((B,), torch.int32)
@@ -273,7 +274,7 @@ class Engine(object):
         dense = torch.as_tensor(np.ascontiguousarray(dense, dtype=np.float32)).to(dev)
         cat = torch.as_tensor(np.ascontiguousarray(cat, dtype=np.int32)).to(dev)
         n = seq.shape[0]
-        obs = torch.empty((n, OBS_DIM), dtype=torch.float32, device=dev)
+        obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=dev)
         probs = torch.empty((n, 2), dtype=torch.float32, device=dev)
         rc = self.lib.r4_dien_forward(self.h, _ptr(seq), _ptr(dense), _ptr(cat), n, _ptr(obs), _ptr(probs), self._sp())
         _capi.check(self.lib, self.h, rc, "r4_dien_forward")

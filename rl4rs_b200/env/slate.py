@@ -213,15 +213,16 @@ class SlateRecEnv(RecSimBase):
         self.max_steps = config["max_steps"]
         self.batch_size = config["batch_size"]
         super().__init__(config, state_cls)
+        self.obs_dim = self.engine.obs_dim                   # 256; 3072 for widedeep ('simulator_obs' is its concat layer)
         if config.get("support_d3rl_mask", False) and not config.get("support_rllib_mask", False) \
                 and not config.get("rawstate_as_obs", False):
-            self.obs_dim = 256 + (self.engine.P if self.seq else self.max_steps) + 1   # slate.py:274-277
+            self.obs_dim = self.engine.obs_dim + (self.engine.P if self.seq else self.max_steps) + 1   # slate.py:274-277
 
     def get_model(self, config):
         algo = config.get("algo", "dien")                              # slate.py:239-242: rl4rs/nets/<algo>.py
-        if algo not in ("dien", "dnn"):
-            raise NotImplementedError("simulator %r is not built: 'dien' (nets/dien.py) and 'dnn' (nets/dnn.py) are "
-                                      "(SURVEY.md section 8f n4)" % (algo,))
+        if algo not in ("dien", "dnn", "widedeep"):
+            raise NotImplementedError("simulator %r is not built: 'dien' (nets/dien.py), 'dnn' (nets/dnn.py) and 'widedeep' "
+                                      "(nets/widedeep.py) are (SURVEY.md section 8f n4)" % (algo,))
         w = config.get("weights")
         if w is None:
             w = self.load_model_file(config["model_file"], config)
@@ -233,7 +234,8 @@ class SlateRecEnv(RecSimBase):
         ``<prefix>.index`` + ``<prefix>.data-*``, README.md:124-137), or an .npz of the W-table."""
         from ..utils import tf_checkpoint
         if tf_checkpoint.is_saver_prefix(model_file):
-            load = tf_checkpoint.load_dnn_checkpoint if config.get("algo", "dien") == "dnn" else tf_checkpoint.load_dien_checkpoint
+            load = {"dnn": tf_checkpoint.load_dnn_checkpoint, "widedeep": tf_checkpoint.load_widedeep_checkpoint}.get(
+                config.get("algo", "dien"), tf_checkpoint.load_dien_checkpoint)
             return load(model_file, config, name_map=config.get("variable_name_map"))
         return dict(np.load(model_file))
 

@@ -276,6 +276,36 @@ def make_dnn_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0):
     return w
 
 
+def widedeep_weight_shapes(cfg=None):
+    """W-table of the `widedeep` simulator (rl4rs/nets/widedeep.py:8-45); 'simulator_obs' is a Concatenate (no weights)."""
+    cfg = cfg or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D, C, S = cfg.get("dense_feature_num", 432), cfg.get("category_feature_num", 21), cfg.get("seq_num", 2)
+    return [("emb_cat", (H, E)), ("dense_w1", (D, U)), ("dense_b1", (U,)), ("dense_w2", (U, U)), ("dense_b2", (U,)),
+            ("emb_seq", (H, E)), ("fc_w", (S * E, 256)), ("fc_b", (256,)),
+            ("rew_w", (256 + U + C * E, cfg.get("class_num", 2))), ("rew_b", (cfg.get("class_num", 2),))]
+
+
+def _make_plain(shapes, seed, stress, bias_noise):
+    rs = np.random.RandomState(seed)
+    w = {}
+    for name, shape in shapes:
+        if name.startswith("emb_"):
+            w[name] = rs.uniform(-0.05, 0.05, shape).astype(np.float32)
+        elif len(shape) == 1:
+            w[name] = np.zeros(shape, np.float32)
+            if bias_noise:
+                w[name] += rs.normal(0.0, bias_noise, shape).astype(np.float32)
+        else:
+            w[name] = _glorot_uniform(rs, shape) * np.float32(stress)
+    return w
+
+
+def make_widedeep_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0):
+    """Keras default initialisers for the `widedeep` simulator."""
+    return _make_plain(widedeep_weight_shapes(cfg), seed, stress, bias_noise)
+
+
 def make_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0, bounded_scores=False):
     """W-table with TF1/Keras default initialisers; ``stress`` scales all non-embedding kernels,
     ``bias_noise`` adds N(0, bias_noise) to every bias (so parity tests see non-trivial biases).

@@ -459,6 +459,34 @@ def load_dnn_checkpoint(prefix, config=None, name_map=None):
     return _load_by_plan(prefix, dnn_layer_plan(config), dnn_variable_names(config), name_map)
 
 
+def widedeep_layer_plan(config=None):
+    """nets/widedeep.py:8-45 in creation order: id_input_processing_concat -> Embedding #0; dense tower -> Dense #0, #1;
+    sequence_input_concat -> Embedding #1; Dense(256) on the pooled sequences -> Dense #2; simulator_obs is a Concatenate;
+    simulator_reward."""
+    cfg = config or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D, C, S, cls = cfg.get("dense_feature_num", 432), cfg.get("category_feature_num", 21), cfg.get("seq_num", 2), cfg.get("class_num", 2)
+    return [("emb_cat", "embedding", (H, E)), ("dense_w1", "dense", (D, U)), ("dense_b1", "dense", (U,)),
+            ("dense_w2", "dense_1", (U, U)), ("dense_b2", "dense_1", (U,)), ("emb_seq", "embedding_1", (H, E)),
+            ("fc_w", "dense_2", (S * E, 256)), ("fc_b", "dense_2", (256,)),
+            ("rew_w", "simulator_reward", (256 + U + C * E, cls)), ("rew_b", "simulator_reward", (cls,))]
+
+
+def widedeep_variable_names(config=None):
+    inner = {"emb_cat": "embeddings", "emb_seq": "embeddings"}
+    return {name: scope + "/" + inner.get(name, "kernel" if name.endswith(("_w", "_w1", "_w2")) else "bias")
+            for name, scope, _ in widedeep_layer_plan(config)}
+
+
+def load_widedeep_checkpoint(prefix, config=None, name_map=None):
+    return _load_by_plan(prefix, widedeep_layer_plan(config), widedeep_variable_names(config), name_map)
+
+
+def save_widedeep_checkpoint(prefix, weights, config=None):
+    names = widedeep_variable_names(config)
+    return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})
+
+
 def save_dnn_checkpoint(prefix, weights, config=None):
     names = dnn_variable_names(config)
     return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})

@@ -88,3 +88,51 @@ def test_dnn_big_batch_oracle_sample():
         np.testing.assert_array_equal(o["action_mask"][idx], r["action_mask"])
         assert_close_rel(o["obs"][idx], r["obs"], what="dnn B=16384 sample obs step %d" % t)
         assert_close_rel(np.asarray(rew)[idx], rrew, what="dnn B=16384 sample reward step %d" % t)
+
+
+# ---- widedeep (config['algo'] = 'widedeep'; rl4rs/nets/widedeep.py:8-45): 'simulator_obs' is the 3072-wide concat --------
+def _wd_setup(B, seq, stress=1.0, bias_noise=0.0, **flags):
+    from rl4rs_b200 import synth
+    cfg = dict(_cfg(B, seq, **flags), algo="widedeep")
+    cat = synth.make_catalog()
+    log = synth.make_log(4 * B, pages=4 if seq else 1, catalog=cat, hash_size=100000, corrupt_frac=0.1)
+    return cfg, cat, log, synth.make_widedeep_weights(cfg, stress=stress, bias_noise=bias_noise)
+
+
+def test_widedeep_forward_alone_matches_oracle():
+    from oracle.widedeep_np import WideDeepOracle
+    from test_gpu_parity_regimes import _random_feature_rows
+    cfg, cat, log, w = _wd_setup(8, False, stress=2.0, bias_noise=0.1)
+    env = make_env(cfg, False, cat, log, w, output_format="numpy")
+    seq, dense, catf = _random_feature_rows(700, 8, 100000)
+    obs, probs = env.sim.engine.dien_forward(seq, dense, catf)
+    o_ref, p_ref = WideDeepOracle(w, np.float32).forward(seq, dense, catf)
+    assert obs.shape == (700, 3072)
+    np.testing.assert_array_equal(obs.cpu().numpy()[:, 384:], o_ref[:, 384:])          # the Flatten() half is a pure gather
+    assert_close_rel(obs.cpu().numpy()[:, :384], o_ref[:, :384], what="widedeep obs (dense halves)")
+    assert_close_rel(probs.cpu().numpy(), p_ref, what="widedeep probs")
+
+
+@pytest.mark.parametrize("seq", [False, True])
+def test_widedeep_env_matches_oracle(seq):
+    from oracle.widedeep_np import WideDeepOracle
+    from oracle.env_np import OracleEnv
+    B = 40
+    cfg, cat, log, w = _wd_setup(B, seq, stress=1.0, bias_noise=0.1, support_rllib_mask=True)
+    env = make_env(cfg, seq, cat, log, w, output_format="numpy")
+    assert env.observation_space["obs"].shape == (3072,)
+    ref = OracleEnv(cfg, log, cat, WideDeepOracle(w, np.float32), seq=seq)
+    rs = np.random.RandomState(7)
+    o, r = env.reset(), ref.reset()
+    assert_close_rel(o["obs"][:, :384], r["obs"][:, :384], what="widedeep env reset obs")
+    paid = 0
+    for t in range(cfg["max_steps"]):
+        a = np.where(rs.rand(B) < 0.85, ref.offline_action, rs.randint(0, 284, B))
+        o, rew, done, info = env.step(a)
+        r, rrew, rdone, _ = ref.step(a)
+        np.testing.assert_array_equal(o["action_mask"], r["action_mask"], err_msg="mask %d" % t)
+        np.testing.assert_array_equal(o["obs"][:, 384:], r["obs"][:, 384:], err_msg="flatten half %d" % t)
+        assert_close_rel(o["obs"][:, :384], r["obs"][:, :384], what="widedeep env obs step %d" % t)
+        assert_close_rel(rew, rrew, what="widedeep env reward step %d" % t)
+        paid += int((np.asarray(rrew) != 0).any())
+    assert paid >= 1

@@ -47,6 +47,22 @@ def test_dnn_numpy_oracle_matches_independent_torch_restatement():
     assert np.abs(o32 - o_t).max() < 1e-4 * max(1.0, np.abs(o_t).max())
 
 
+def test_widedeep_numpy_oracle_matches_independent_torch_restatement(tmp_path):
+    from oracle.widedeep_np import WideDeepOracle
+    from rl4rs_b200.utils import tf_checkpoint as tfc
+    w = synth.make_widedeep_weights(SMALL, stress=2.0, bias_noise=0.2)
+    seq, dense, cat = _rows(48, 3, 600)
+    o_np, p_np = WideDeepOracle(w, np.float64).forward(seq, dense, cat)
+    o_t, p_t = torch_ref.widedeep_forward(w, seq, dense, cat)
+    assert o_np.shape == (48, 3072)
+    np.testing.assert_allclose(o_np, o_t, rtol=0, atol=1e-12 * max(1.0, np.abs(o_t).max()))
+    np.testing.assert_allclose(p_np, p_t, rtol=0, atol=1e-13)
+    p = tfc.save_widedeep_checkpoint(str(tmp_path / "wd"), w, SMALL)
+    got = tfc.load_widedeep_checkpoint(p, SMALL)
+    assert set(got) == set(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    assert tfc.widedeep_variable_names(SMALL)["fc_w"] == "dense_2/kernel"
+
+
 def test_dnn_checkpoint_round_trip(tmp_path):
     from rl4rs_b200.utils import tf_checkpoint as tfc
     w = synth.make_dnn_weights(SMALL, bias_noise=0.1)

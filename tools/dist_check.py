@@ -116,6 +116,7 @@ def main():
     out["trainer"] = {k: {kk: vv for kk, vv in v.items() if kk != "flat"} for k, v in res.items()}
     out["peer_vs_nccl_max_abs_param_diff"] = d
     ok = ok and res["peer"]["replicas_bit_identical"] and res["nccl"]["replicas_bit_identical"] and d < 5e-5
+    ok = ok and abs(res["peer"]["total_loss"] - res["nccl"]["total_loss"]) <= 1e-3 * abs(res["nccl"]["total_loss"])
     if comm.ok:
         ok = ok and res["peer"]["uses_peer"] and not res["nccl"]["uses_peer"]
     out["ok"] = bool(ok)
