@@ -60,6 +60,15 @@ except Exception:  # ImportError or a broken install
         def contains(self, x):
             return all(k in x and s.contains(x[k]) for k, s in self.spaces.items())
 
+        def __getitem__(self, key):
+            return self.spaces[key]
+
+        def __iter__(self):
+            return iter(self.spaces)
+
+        def __len__(self):
+            return len(self.spaces)
+
         def __repr__(self):
             return "Dict(%s)" % ", ".join("%s:%r" % kv for kv in self.spaces.items())
 
