@@ -50,8 +50,10 @@ enum { R4_ENV_SLATE = 0, R4_ENV_SEQSLATE = 1 };   /* rl4rs/__init__.py:10-18 */
  *   DNN   nets/dnn.py:8-45    (mean-pooled category embeddings + dense tower + FC 256 + simulator_obs; gather-bound:
  *                              the sequence branch of that graph does not reach the output and is not evaluated)
  *   WIDEDEEP  nets/widedeep.py:8-45 (mean-pooled sequence embeddings -> Dense 256 | dense tower | flattened category
- *                              embeddings; 'simulator_obs' IS that 3072-wide concat, so obs buffers are f32 [B,3072]) */
-enum { R4_SIM_DIEN = 0, R4_SIM_DNN = 1, R4_SIM_WIDEDEEP = 2 };
+ *                              embeddings; 'simulator_obs' IS that 3072-wide concat, so obs buffers are f32 [B,3072])
+ *   LSTM  nets/lstm.py:8-45   (Keras GRU -- hard sigmoid, reset_after False -- over each behaviour sequence and over the 21
+ *                              category embeddings | dense tower | flattened category embeddings -> simulator_obs 256) */
+enum { R4_SIM_DIEN = 0, R4_SIM_DNN = 1, R4_SIM_WIDEDEEP = 2, R4_SIM_LSTM = 3 };
 /* width of the observation a simulator produces (256, or 3072 for widedeep) */
 int r4_obs_dim(int simulator);
 
@@ -72,7 +74,7 @@ typedef struct {
   int32_t emb_size;             /* 128 */
   int32_t hidden_units;         /* 128 */
   int32_t max_rows_per_pass;    /* 0 = default; bound on simulator rows per launch group */
-  int32_t simulator;            /* R4_SIM_DIEN | R4_SIM_DNN | R4_SIM_WIDEDEEP (ABI version >= 2) */
+  int32_t simulator;            /* R4_SIM_DIEN | R4_SIM_DNN | R4_SIM_WIDEDEEP | R4_SIM_LSTM (ABI version >= 2) */
 } r4_config;
 
 /* Per-call output buffers (device, caller-owned).  NULL = not wanted.

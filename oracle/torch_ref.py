@@ -48,6 +48,36 @@ def widedeep_forward(w, seq, dense, cat):
     return obs.numpy(), F.softmax(F.linear(obs, _t(w, "rew_w").T, _t(w, "rew_b")), dim=-1).numpy()
 
 
+def _keras_gru_last(x, k, rk, b):
+    """Keras v1 GRU (hard sigmoid, reset_after False, gates [z | r | h]) written per gate from the layer definition."""
+    U = rk.shape[0]
+    h = torch.zeros(x.shape[0], U, dtype=torch.float64)
+    hs = lambda v: torch.clamp(0.2 * v + 0.5, 0.0, 1.0)
+    for t in range(x.shape[1]):
+        xt = x[:, t]
+        z = hs(xt @ k[:, :U] + b[:U] + h @ rk[:, :U])
+        r = hs(xt @ k[:, U:2 * U] + b[U:2 * U] + h @ rk[:, U:2 * U])
+        hh = torch.tanh(xt @ k[:, 2 * U:] + b[2 * U:] + (r * h) @ rk[:, 2 * U:])
+        h = z * h + hh - z * hh
+    return h
+
+
+def lstm_forward(w, seq, dense, cat):
+    seq = torch.as_tensor(seq, dtype=torch.long)
+    cat = torch.as_tensor(cat, dtype=torch.long)
+    ec = F.embedding(cat, _t(w, "emb_cat"))
+    cg = _keras_gru_last(ec, _t(w, "cgru_k"), _t(w, "cgru_rk"), _t(w, "cgru_b"))
+    x = torch.as_tensor(dense, dtype=torch.float64)
+    for i in (1, 2):
+        x = F.elu(F.linear(x, _t(w, "dense_w%d" % i).T, _t(w, "dense_b%d" % i)))
+    es = _t(w, "emb_seq")
+    sg = [_keras_gru_last(F.embedding(seq[:, i], es), _t(w, "sgru%d_k" % i), _t(w, "sgru%d_rk" % i), _t(w, "sgru%d_b" % i))
+          for i in range(seq.shape[1])]
+    allf = torch.cat(sg + [x, cg, ec.flatten(1)], dim=1)
+    obs = F.elu(F.linear(allf, _t(w, "obs_w").T, _t(w, "obs_b")))
+    return obs.numpy(), F.softmax(F.linear(obs, _t(w, "rew_w").T, _t(w, "rew_b")), dim=-1).numpy()
+
+
 def _gru_step(x, h, wg, bg, wc, bc, att=None):
     """One step of TF1 GRUCell / deepctr VecAttGRUCell with the fused kernels split per gate and per input half."""
     nx, nh = x.shape[1], h.shape[1]

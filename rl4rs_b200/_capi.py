@@ -11,8 +11,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libr
 
 FLAG_RLLIB_MASK, FLAG_D3RL_MASK, FLAG_CONTI, FLAG_ONEHOT, FLAG_RAWSTATE, FLAG_INFO_FETCH = 1, 2, 4, 8, 16, 32
 ENV_SLATE, ENV_SEQSLATE = 0, 1
-SIM_DIEN, SIM_DNN, SIM_WIDEDEEP = 0, 1, 2
-SIMULATORS = {"dien": SIM_DIEN, "dnn": SIM_DNN, "widedeep": SIM_WIDEDEEP}
+SIM_DIEN, SIM_DNN, SIM_WIDEDEEP, SIM_LSTM = 0, 1, 2, 3
+SIMULATORS = {"dien": SIM_DIEN, "dnn": SIM_DNN, "widedeep": SIM_WIDEDEEP, "lstm": SIM_LSTM}
 
 
 class R4Config(C.Structure):

@@ -31,7 +31,10 @@ constexpr int P_NB = 128;                             // weight columns (B rows)
 constexpr int P_HALF_BYTES = P_NB * KB * 2;           // 8192: one split of one 32-deep K block of the CTA's 128 columns
 constexpr int P_STAGE_BYTES = 2 * P_HALF_BYTES;       // 16384: ring stage = [hi | lo] of one K block (6 MMAs, 384 cycles)
 constexpr int P_STAGES_PER_STEP = 3 * NKB;            // 24
-constexpr int P_NST = 6;
+#ifndef R4P_NST
+#define R4P_NST 6
+#endif
+constexpr int P_NST = R4P_NST;                        // ring depth; 24 % (2 * P_NST) == 0 keeps stage and parity compile-time
 #ifndef R4P_COMMIT_GROUP
 #define R4P_COMMIT_GROUP 1
 #endif
@@ -79,6 +82,10 @@ __device__ __forceinline__ void cluster_sync_all() {
 // The kernel itself lives in r4_augru_pair2.cuh (k_augru_pair2); this header keeps the shared constants, the PTX
 // wrappers of the 2-CTA instructions and the host-side weight image.
 
+// Ring stage s8 (0..7) of every gate holds K block 0,4,1,5,2,6,3,7: the epilogue of k_augru_pair2 completes the blocks
+// {q, 4 + q} of an A operand with its q-th column chunk, and the MMAs follow it in that order.
+__host__ __device__ constexpr int pair_kb(int s8) { return (s8 & 1) * 4 + (s8 >> 1); }
+
 // host: fp32 recurrent weights -> [rank 2][mat r,u,c][8 K blocks][hi, lo] stages of 128 columns x 32 K (8 KB).
 // Wg: [256][512] rows = h index, columns [r | u];  Wc: [256][256].
 inline void build_pair_image(const float* Wg, const float* Wc, uint8_t* img) {
@@ -86,8 +93,7 @@ inline void build_pair_image(const float* Wg, const float* Wc, uint8_t* img) {
     for (int mat = 0; mat < 3; ++mat)
       for (int kb = 0; kb < NKB; ++kb)
         for (int sp = 0; sp < 2; ++sp) {
-          // stage s8 of the r and u gates holds K block (s8 & 3) * 2 + (s8 >> 2): 0,2,4,6,1,3,5,7 (see gemm() in the kernel)
-          const int kbsrc = mat < 2 ? ((kb & 3) * 2 + (kb >> 2)) : kb;
+          const int kbsrc = pair_kb(kb);               // the order in which the kernels walk the K blocks of a gate
           uint8_t* st = img + (size_t)rank * P_RANK_IMAGE_BYTES + (size_t)((mat * NKB + kb) * 2 + sp) * P_HALF_BYTES;
           for (int nl = 0; nl < P_NB; ++nl)
             for (int kk = 0; kk < KB; ++kk) {

@@ -80,14 +80,15 @@ __device__ __forceinline__ void commit2_mask(uint64_t* bar, uint16_t mask) {
 constexpr int P2_TM_ROW_BYTES = 1024;                             // tensor-map row = 256 x u32
 constexpr int P2_TM_BOX_ROWS = P_STAGE_BYTES / P2_TM_ROW_BYTES;   // 16 rows per ring stage
 
-// One gate of one step: 8 ring stages x 2 K16 slices x (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo).  The r and u gates walk
-// the K blocks of h in the order 0,2,4,6,1,3,5,7 -- the order in which the epilogue finishes them -- and the r gate
-// waits for `half_bar` (the odd blocks) before its second half; build_pair_image lays the weights out in the same order.
-// No tcgen05 fence per stage: the weights come from TMA.
+// One gate of one step: 8 ring stages x 2 K16 slices x (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo).  Every gate walks the K
+// blocks of its A operand in the order pair_kb() = 0,4,1,5,2,6,3,7: the epilogue finishes blocks {q, 4 + q} with its
+// q-th column chunk and publishes them on quarter barrier q, so the gate's MMAs chase the epilogue that produces their
+// operand, 12 MMAs behind it (`qbar` = the 4 quarter barriers of the A operand, nullptr when it is already complete).
+// build_pair_image lays the weights out in the same order.  No tcgen05 fence per stage: the weights come from TMA.
 template <int GATE>
 __device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo,
-                                            uint64_t* bar_full, uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par,
-                                            uint16_t empty_mask = 3) {
+                                            uint64_t* bar_full, uint64_t* bar_empty, uint64_t* qbar, uint32_t qpar,
+                                            uint16_t empty_mask = 3, long long* wait_acc = nullptr) {
   constexpr uint32_t idesc = make_idesc(TM, HID);
   constexpr uint32_t dcol = GATE == 0 ? P_TC_R : (GATE == 1 ? P_TC_U : P_TC_C);
   constexpr uint32_t a_hi = desc_hi(A_SBO), b_hi = desc_hi(B_SBO);
@@ -96,9 +97,13 @@ __device__ __forceinline__ void issue_gate2(uint32_t leader, uint32_t tbase, uin
     const int u = GATE * NKB + s8;
     const int stage = u % P_NST;
     const uint32_t par = (uint32_t)((u / P_NST) & 1);
-    const int kb = GATE < 2 ? ((s8 & 3) * 2 + (s8 >> 2)) : s8;
-    if (GATE == 0 && s8 == NKB / 2) { mbar_wait_cl(half_bar, half_par); tc_fence_after(); }
+    const int kb = pair_kb(s8);
+    // wait_acc (probe builds only): [0] cycles waiting for operand quarters, [1] cycles waiting for ring stages
+    long long w0 = wait_acc ? clock64() : 0;
+    if (qbar != nullptr && (s8 & 1) == 0) { mbar_wait_cl(&qbar[s8 >> 1], qpar); tc_fence_after(); }
+    long long w1 = wait_acc ? clock64() : 0;
     mbar_wait(&bar_full[stage], par);
+    if (wait_acc) { wait_acc[0] += w1 - w0; wait_acc[1] += clock64() - w1; }
     if (leader) {
 #pragma unroll
       for (int j = 0; j < KB / 16; ++j) {
@@ -186,7 +191,7 @@ template <int RELAY, int TMAP, int CS = 2>
 __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_constant__ AugruPairParams pp) {
   static_assert(CS == 2 || TMAP, "weight-stream sharing needs the tensor-map ring");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h0, bar_h1, bar_rh, bar_r, bar_u, bar_c;
+  __shared__ uint64_t bar_full[P_NST], bar_empty[P_NST], bar_h[4], bar_rh[4], bar_r, bar_u, bar_c;
   __shared__ uint32_t tmem_base_s;
   const AugruTcParams& p = pp.b;
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -213,7 +218,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
     for (int i = 0; i < P_NST; ++i) { mbar_init(&bar_full[i], (rank == 0 && !TMAP) ? 2 : 1); mbar_init(&bar_empty[i], CS / 2); }
     // hand-over barriers: RELAY -> 8 local warps (+ 1 relay arrival on the leader); else 8 warps x 2 CTAs on the leader
     const int nh = RELAY ? (rank == 0 ? 9 : 8) : 16;
-    mbar_init(&bar_h0, nh); mbar_init(&bar_h1, nh); mbar_init(&bar_rh, nh);
+    for (int i = 0; i < 4; ++i) { mbar_init(&bar_h[i], nh); mbar_init(&bar_rh[i], nh); }
     mbar_init(&bar_r, 1); mbar_init(&bar_u, 1); mbar_init(&bar_c, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -226,8 +231,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
   cluster_sync_all();                         // the peer's barriers exist before anyone arrives remotely
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
-  const uint32_t bar_h0_leader = mapa_rank(smem_u32(&bar_h0), lead), bar_h1_leader = mapa_rank(smem_u32(&bar_h1), lead),
-                 bar_rh_leader = mapa_rank(smem_u32(&bar_rh), lead);
+  const uint32_t bar_h_leader = mapa_rank(smem_u32(&bar_h[0]), lead), bar_rh_leader = mapa_rank(smem_u32(&bar_rh[0]), lead);
 
   if (warp >= 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // frees 128 x 128 registers = what 232 for the 256 epilogue threads takes
@@ -288,44 +292,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
         // keep the 144 descriptors of a step OUT of the loop-invariant set: hoisted, they live in local memory (this warp
         // has 40 registers) and every MMA pays a local load; rebuilt from these five words each costs one add
         asm volatile("" : "+r"(hHi_d), "+r"(hLo_d), "+r"(rHi_d), "+r"(rLo_d), "+r"(b_d));
-        mbar_wait_cl(&bar_h0, par);     // both CTAs' even K blocks of h (hi/lo) are in shared memory
-        tc_fence_after();
+        long long wacc[2] = {0, 0};
+        long long* wa = dbg ? wacc : nullptr;
         if (dbg) dbg[1] = clock64();
-        issue_gate2<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, &bar_h1, par, ALL_MASK);   // ... the odd ones by its second half
+        issue_gate2<0>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, bar_h, par, ALL_MASK, wa);   // chases phase C of step t-1
         if (leader) commit2_mask(&bar_r, pair_mask);
         if (dbg) dbg[2] = clock64();
-        issue_gate2<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0, ALL_MASK);
+        issue_gate2<1>(leader, tbase, hHi_d, hLo_d, b_d, bar_full, bar_empty, nullptr, 0, ALL_MASK, wa);
         if (leader) commit2_mask(&bar_u, pair_mask);
         if (dbg) dbg[3] = clock64();
-        mbar_wait_cl(&bar_rh, par);     // both CTAs' r*h written
-        tc_fence_after();
         if (dbg) dbg[4] = clock64();
-        issue_gate2<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, nullptr, 0, ALL_MASK);
+        issue_gate2<2>(leader, tbase, rHi_d, rLo_d, b_d, bar_full, bar_empty, bar_rh, par, ALL_MASK, wa);  // chases phase R of this step
         if (leader) commit2_mask(&bar_c, pair_mask);
-        if (dbg) { dbg[5] = clock64(); dbg[6] = 0; dbg[7] = 0; }
+        if (dbg) { dbg[5] = clock64(); dbg[6] = wacc[0]; dbg[7] = wacc[1]; }
       }
     } else if (RELAY && rank == 1 && lane == 0) {
       // ===== hand-over relays (peer CTA): forward each completed local phase with a cluster-scope release =====
-      // A local phase k+1 cannot complete before phase k has been forwarded: it needs the leader's next MMAs, which wait
-      // for this very arrival.  warp 11: h0 (the latency-critical one); warp 10: r*h and h1, in their order in time.
+      // A barrier cannot complete its next phase before this one has been forwarded: that needs the leader's next gate on
+      // the same operand, which waits for this very arrival.  warp 11: the quarters of h; warp 10: the quarters of r*h.
       if (warp == 11) {
-        for (int k = 0; k <= STEPS; ++k) { mbar_wait(&bar_h0, k & 1); arrive_cl(bar_h0_leader); }
+        for (int k = 0; k <= STEPS; ++k)
+          for (int i = 0; i < 4; ++i) { mbar_wait(&bar_h[i], k & 1); arrive_cl(bar_h_leader + i * 8); }
       } else {
-        mbar_wait(&bar_h1, 0); arrive_cl(bar_h1_leader);
-        for (int t = 0; t < STEPS; ++t) {
-          mbar_wait(&bar_rh, t & 1); arrive_cl(bar_rh_leader);
-          mbar_wait(&bar_h1, (t + 1) & 1); arrive_cl(bar_h1_leader);
-        }
+        for (int t = 0; t < STEPS; ++t)
+          for (int i = 0; i < 4; ++i) { mbar_wait(&bar_rh[i], t & 1); arrive_cl(bar_rh_leader + i * 8); }
       }
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ===== epilogue warps: thread = (row of this CTA, 64 hidden columns) =====
+    // ===== epilogue warps: thread = (row of this CTA, 4 chunks of 16 hidden columns) =====
+    // Chunk ch of a thread covers hidden columns half * 128 + ch * 32 + sub * 16 .. + 15: the two warps (sub = 0, 1) of a
+    // lane quarter together finish the 32-wide K block half * 4 + ch with their ch-th chunk, so over the CTA pair chunk ch
+    // completes K blocks {ch, 4 + ch} of the A operand -- quarter barrier ch, the unit the MMA warp chases.
     const int q = warp & 3, sub = warp >> 2;
     const int rl = (q & 1) * 32 + lane;                    // row inside this CTA
     const int prow = (int)rank * P_RC + rl;                // row inside the pair's 128-row tile
-    const int hc0 = (q >> 1) * 128 + sub * 64;             // first hidden column of this thread
-    const uint32_t tcol = (uint32_t)sub * 64;              // TMEM column offset inside a gate
+    const int hcb = (q >> 1) * 128 + sub * 16;             // hidden column of chunk ch: hcb + ch * 32
+    const uint32_t tcb = (uint32_t)sub * 16;               // TMEM column inside a gate of chunk ch: tcb + ch * 32
     int r = m0 + prow;
     const bool valid = r < p.R && !pad_pair;
     if (r >= p.R) r = p.R - 1;
@@ -334,23 +337,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
     const int ln4 = (ci % TM) * 4;
     const float* st = S.scoresT + ((size_t)(m0 / TM) * STEPS) * TM + prow;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const uint32_t a_row_off = (uint32_t)(rl / 8) * A_SBO + (uint32_t)(rl % 8) * 16;
+    const uint32_t a_row_off = (uint32_t)(rl / 8) * A_SBO + (uint32_t)(rl % 8) * 16 + (uint32_t)(hcb / 8) * LBO;
     const bool local_arrive = RELAY || rank == 0;          // arrive on this CTA's own barrier (else: relaxed, on the leader's)
+    // publish quarter `i` of an A operand: this thread's stores -> async proxy, then one arrival per warp
+    auto publish = [&](uint64_t* bars, uint32_t bars_leader, int i) {
+      tc_fence_before();
+      proxy_fence();
+      __syncwarp();
+      if (lane == 0) { if (local_arrive) mbar_arrive(&bars[i]); else arrive_cl_relaxed(bars_leader + i * 8); }
+    };
     float h[64], x[4][16];
 #pragma unroll
     for (int i = 0; i < 64; ++i) h[i] = 0.f;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {                          // h0 = 0 into the A operand
-      uint32_t off = a_row_off + (uint32_t)((hc0 + g * 8) / 8) * LBO;
-      *reinterpret_cast<uint4*>(sHhi + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sHlo + off) = make_uint4(0, 0, 0, 0);
+    for (int ch = 0; ch < 4; ++ch) {                       // h0 = 0 into the A operand
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {
+        const uint32_t off = a_row_off + (uint32_t)(ch * 4 + g) * LBO;
+        *reinterpret_cast<uint4*>(sHhi + off) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sHlo + off) = make_uint4(0, 0, 0, 0);
+      }
     }
-    proxy_fence();
-    __syncwarp();
-    if (lane == 0) {
-      if (local_arrive) { mbar_arrive(&bar_h0); mbar_arrive(&bar_h1); }
-      else { arrive_cl_relaxed(bar_h0_leader); arrive_cl_relaxed(bar_h1_leader); }
-    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) publish(bar_h, bar_h_leader, i);
 #if R4_ABL & 4
 #define R4P2_LOADX(dst, base, colbase) do { _Pragma("unroll") for (int q_ = 0; q_ < 16; ++q_) (dst)[q_] = 0.125f * (float)(ln4 & 3); } while (0)
 #else
@@ -358,7 +367,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
 #endif
     // rolling input buffer: x[ch] always holds chunk ch of the NEXT phase to run (here: the r gate of step 0)
 #pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) { R4P2_LOADX(x[c4], xt, hc0 + c4 * 16); }
+    for (int c4 = 0; c4 < 4; ++c4) { R4P2_LOADX(x[c4], xt, hcb + c4 * 32); }
     float one_minus_s = 1.0f - __ldg(st);
 
     for (int t = 0; t < STEPS; ++t) {
@@ -377,41 +386,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
           asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(id >> 3) * 4 * TM + rank * (P_RC * 4) + (id & 7) * 32));
         }
       }
-      // ---- phase R (overlaps the u MMAs): r*h -> its own A operand; x[] <- the u gate's inputs ----
+      // ---- phase R (overlaps the u MMAs; the c MMAs chase it quarter by quarter): r*h -> its own A operand;
+      //      x[] <- the u gate's inputs ----
       {
-        float a[R4P2_SWPIPE ? 3 : 2][16];
-        constexpr int NA = R4P2_SWPIPE ? 3 : 2;
+        float a[2][16];
         if (dbg) dbg[8] = clock64();
         mbar_wait(&bar_r, par);
         if (dbg) dbg[9] = clock64();
         tc_fence_after();
-        P2_TMEM_LD16(tlane + P_TC_R + tcol, a[0]);
+        P2_TMEM_LD16(tlane + P_TC_R + tcb, a[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int cur = ch % NA, nxt = (ch + 1) % NA;
+          const int cur = ch & 1, nxt = cur ^ 1;
           P2_TMEM_WAIT_LD();
-          if (ch < 3) P2_TMEM_LD16(tlane + P_TC_R + tcol + (ch + 1) * 16, a[nxt]);
+          if (ch < 3) P2_TMEM_LD16(tlane + P_TC_R + tcb + (ch + 1) * 32, a[nxt]);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             a[cur][j] = p2_rcp(1.0f + p2_ex2(fminf(preact2(a[cur][j], x[ch][j], P2_NL2E), 60.0f)), j) * h[ch * 16 + j];
-          R4P2_LOADX(x[ch], xs, HID + hc0 + ch * 16);
-          const int sc = R4P2_SWPIPE ? ch - 1 : ch;      // chunk whose operand rows are written now
-          if (sc >= 0) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-              split_store8(a[sc % NA] + g * 8, sRhi, sRlo, a_row_off + (uint32_t)((hc0 + sc * 16 + g * 8) / 8) * LBO);
-          }
-        }
-        if (R4P2_SWPIPE) {
+          R4P2_LOADX(x[ch], xs, HID + hcb + ch * 32);
 #pragma unroll
           for (int g = 0; g < 2; ++g)
-            split_store8(a[3 % NA] + g * 8, sRhi, sRlo, a_row_off + (uint32_t)((hc0 + 3 * 16 + g * 8) / 8) * LBO);
+            split_store8(a[cur] + g * 8, sRhi, sRlo, a_row_off + (uint32_t)(ch * 4 + g) * LBO);
+          publish(bar_rh, bar_rh_leader, ch);
         }
       }
-      tc_fence_before();
-      proxy_fence();
-      __syncwarp();
-      if (lane == 0) { if (local_arrive) mbar_arrive(&bar_rh); else arrive_cl_relaxed(bar_rh_leader); }
       if (dbg) dbg[10] = clock64();
       // ---- phase U (overlaps the c MMAs): E = 1 + exp(-(acc_u + Xu)) back into TMEM; x[] <- the c gate's inputs ----
       {
@@ -419,42 +417,42 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
         mbar_wait(&bar_u, par);
         if (dbg) dbg[11] = clock64();
         tc_fence_after();
-        P2_TMEM_LD16(tlane + P_TC_U + tcol, a[0]);
+        P2_TMEM_LD16(tlane + P_TC_U + tcb, a[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
           const int cur = ch & 1, nxt = cur ^ 1;
           P2_TMEM_WAIT_LD();
-          if (ch < 3) P2_TMEM_LD16(tlane + P_TC_U + tcol + (ch + 1) * 16, a[nxt]);
+          if (ch < 3) P2_TMEM_LD16(tlane + P_TC_U + tcb + (ch + 1) * 32, a[nxt]);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             a[cur][j] = 1.0f + p2_ex2(fminf(preact2(a[cur][j], x[ch][j], P2_NL2E), 60.0f));
-          R4P2_LOADX(x[ch], xs, 2 * HID + hc0 + ch * 16);
-          P2_TMEM_ST16(tlane + P_TC_U + tcol + ch * 16, a[cur]);
+          R4P2_LOADX(x[ch], xs, 2 * HID + hcb + ch * 32);
+          P2_TMEM_ST16(tlane + P_TC_U + tcb + ch * 32, a[cur]);
         }
         P2_TMEM_WAIT_ST();
       }
       if (dbg) dbg[12] = clock64();
-      // ---- phase C: c = tanh(acc_c + Xc) = 1 - 2/(1 + F), u = 1/E with ONE reciprocal of E*F; x[] <- next step's r inputs ----
+      // ---- phase C (the next step's r MMAs chase it quarter by quarter): c = tanh(acc_c + Xc) = 1 - 2/(1 + F), u = 1/E
+      //      with ONE reciprocal of E*F; x[] <- next step's r inputs ----
       {
-        float a[R4P2_SWPIPE ? 3 : 2][16], u[2][16];
-        constexpr int NA = R4P2_SWPIPE ? 3 : 2;
+        float a[2][16], u[2][16];
         mbar_wait(&bar_c, par);
         if (dbg) dbg[13] = clock64();
         tc_fence_after();
-        P2_TMEM_LD16(tlane + P_TC_C + tcol, a[0]);
-        P2_TMEM_LD16(tlane + P_TC_U + tcol, u[0]);
+        P2_TMEM_LD16(tlane + P_TC_C + tcb, a[0]);
+        P2_TMEM_LD16(tlane + P_TC_U + tcb, u[0]);
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          const int cur = ch % NA, nxt = (ch + 1) % NA, ucur = ch & 1, unxt = ucur ^ 1;
+          const int cur = ch & 1, nxt = cur ^ 1;
           P2_TMEM_WAIT_LD();
           if (ch < 3) {
-            P2_TMEM_LD16(tlane + P_TC_C + tcol + (ch + 1) * 16, a[nxt]);
-            P2_TMEM_LD16(tlane + P_TC_U + tcol + (ch + 1) * 16, u[unxt]);
+            P2_TMEM_LD16(tlane + P_TC_C + tcb + (ch + 1) * 32, a[nxt]);
+            P2_TMEM_LD16(tlane + P_TC_U + tcb + (ch + 1) * 32, u[nxt]);
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float F = 1.0f + p2_ex2(fminf(preact2(a[cur][j], x[ch][j], P2_2L2E), 60.0f));
-            const float E = u[ucur][j];
+            const float E = u[cur][j];
             const float rc = p2_rcp(E * F, j);                      // E, F <= 1 + 2^60: the product is finite
             const float c = fmaf(-2.0f, rc * E, 1.0f);               // tanh
             const float up = one_minus_s * (rc * F);                 // (1 - s) sigmoid
@@ -462,37 +460,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
             h[ch * 16 + j] = hn;
             a[cur][j] = hn;
           }
-          R4P2_LOADX(x[ch], xs_next, hc0 + ch * 16);      // (last step: a harmless re-read of this step's lines)
-          const int sc = R4P2_SWPIPE ? ch - 1 : ch;
-          if (sc >= 0) {
-#pragma unroll
-            for (int g = 0; g < 2; ++g)
-              split_store8(a[sc % NA] + g * 8, sHhi, sHlo, a_row_off + (uint32_t)((hc0 + sc * 16 + g * 8) / 8) * LBO);
-          }
-          if (sc == 1) {              // this thread's even K block of h' is complete: release the first half of the next r gate
-            proxy_fence();
-            __syncwarp();
-            if (lane == 0) { if (local_arrive) mbar_arrive(&bar_h0); else arrive_cl_relaxed(bar_h0_leader); }
-          }
-        }
-        if (R4P2_SWPIPE) {
+          R4P2_LOADX(x[ch], xs_next, hcb + ch * 32);      // (last step: a harmless re-read of this step's lines)
 #pragma unroll
           for (int g = 0; g < 2; ++g)
-            split_store8(a[3 % NA] + g * 8, sHhi, sHlo, a_row_off + (uint32_t)((hc0 + 3 * 16 + g * 8) / 8) * LBO);
+            split_store8(a[cur] + g * 8, sHhi, sHlo, a_row_off + (uint32_t)(ch * 4 + g) * LBO);
+          publish(bar_h, bar_h_leader, ch);
         }
       }
-      tc_fence_before();
-      proxy_fence();
-      __syncwarp();
       if (dbg) dbg[14] = clock64();
-      if (lane == 0) { if (local_arrive) mbar_arrive(&bar_h1); else arrive_cl_relaxed(bar_h1_leader); }
       one_minus_s = oms_next;
     }
 #undef R4P2_LOADX
     if (valid) {
-      float* o = S.out + (size_t)(m0 + prow) * p.out_ld + hc0;
+      float* o = S.out + (size_t)(m0 + prow) * p.out_ld + hcb;
 #pragma unroll
-      for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
+      for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(o + ch * 32 + i) = make_float4(h[ch * 16 + i], h[ch * 16 + i + 1], h[ch * 16 + i + 2], h[ch * 16 + i + 3]);
     }
   }
   tc_fence_before();

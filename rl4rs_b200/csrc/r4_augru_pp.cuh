@@ -56,7 +56,7 @@ __device__ __forceinline__ void load_x8(float* dst, const float* ts, int colbase
 }
 
 // One gate (8 ring stages) of the leader's issue stream; U0 = index of its first ring use inside the step.
-template <int U0, bool PERM>
+template <int U0>
 __device__ __forceinline__ void issue_gate_pp(uint32_t leader, uint32_t d_tmem, uint32_t aHi_lo, uint32_t aLo_lo, uint32_t b_lo,
                                               uint64_t* bar_full, uint64_t* bar_empty, uint64_t* half_bar, uint32_t half_par) {
   constexpr uint32_t idesc = make_idesc(TM, HID);
@@ -66,7 +66,7 @@ __device__ __forceinline__ void issue_gate_pp(uint32_t leader, uint32_t d_tmem, 
     const int u = U0 + s8;
     const int stage = u % P_NST;
     const uint32_t par = (uint32_t)((u / P_NST) & 1);
-    const int kb = PERM ? ((s8 & 3) * 2 + (s8 >> 2)) : s8;
+    const int kb = pair_kb(s8);                     // the weight image's order (r4_augru_pair.cuh), every gate
     if (half_bar != nullptr && s8 == NKB / 2) { mbar_wait_cl(half_bar, half_par); tc_fence_after(); }
     mbar_wait(&bar_full[stage], par);
     if (leader) {
@@ -159,24 +159,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
         if (dbg) dbg[0] = clock64();
         mbar_wait_cl(&bar_h[0], par); tc_fence_after();
         if (dbg) dbg[1] = clock64();
-        issue_gate_pp<0, true>(leader, tbase + 0, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
-        issue_gate_pp<8, true>(leader, tbase + 128, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<0>(leader, tbase + 0, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<8>(leader, tbase + 128, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
         if (leader) commit2(&bar_u[0]);
         if (dbg) dbg[2] = clock64();
         mbar_wait_cl(&bar_h[1], par); tc_fence_after();
         if (dbg) dbg[3] = clock64();
-        issue_gate_pp<16, true>(leader, tbase + 256, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
-        issue_gate_pp<24, true>(leader, tbase + 384, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<16>(leader, tbase + 256, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<24>(leader, tbase + 384, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
         if (leader) commit2(&bar_u[1]);
         if (dbg) dbg[4] = clock64();
         mbar_wait_cl(&bar_rh[0], par); tc_fence_after();
         if (dbg) dbg[5] = clock64();
-        issue_gate_pp<32, false>(leader, tbase + 0, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<32>(leader, tbase + 0, a0h, a0l, b_d, bar_full, bar_empty, nullptr, 0);
         if (leader) commit2(&bar_c[0]);
         if (dbg) dbg[6] = clock64();
         mbar_wait_cl(&bar_rh[1], par); tc_fence_after();
         if (dbg) dbg[7] = clock64();
-        issue_gate_pp<40, false>(leader, tbase + 256, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
+        issue_gate_pp<40>(leader, tbase + 256, a1h, a1l, b_d, bar_full, bar_empty, nullptr, 0);
         if (leader) commit2(&bar_c[1]);
         if (dbg) dbg[8] = clock64();
       }

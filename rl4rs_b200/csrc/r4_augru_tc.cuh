@@ -125,10 +125,22 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 
 // 16 consecutive columns (colbase % 16 == 0) of one lane of a lane-major tile-step in the quad layout
 // [col / 4][lane][col % 4] (r4_gemm_tc.cuh: xt_index): four 128-bit loads.  `ts` = tile-step base, `ln4` = lane * 4.
+#ifndef R4_LDG_NOALLOC
+#define R4_LDG_NOALLOC 0     // 1: the input halves are read once per CTA -> ld.global.nc.L1::no_allocate (probe switch)
+#endif
+__device__ __forceinline__ float4 ldg_x4(const float* p) {
+#if R4_LDG_NOALLOC
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(reinterpret_cast<const float4*>(p));
+#endif
+}
 __device__ __forceinline__ void load_x16(float* dst, const float* ts, int colbase, int ln4) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(ts + (size_t)(colbase + 4 * g) * TM + ln4));
+    const float4 v = ldg_x4(ts + (size_t)(colbase + 4 * g) * TM + ln4);
     dst[4 * g] = v.x; dst[4 * g + 1] = v.y; dst[4 * g + 2] = v.z; dst[4 * g + 3] = v.w;
   }
 }

@@ -74,6 +74,10 @@ struct r4_env {
   float* fcb = nullptr; uint8_t *fc_img = nullptr;                   // dnn: the unnamed Dense(256, ELU) of nets/dnn.py:34; widedeep: nets/widedeep.py:34
   int obs_dim = OBSD;                                                // 256, or 3072 for widedeep
   DevBuf ws_seq;                                                     // widedeep: sequence ids of a pass, i32 [R,2,64]
+  // lstm (nets/lstm.py): the category GRU (Keras GRU over the 21 category embeddings, utils.py:34); the two sequence GRUs
+  // (utils.py:92) reuse ps[i].gru_wx_img / gru_bx / gru_img, their LAST states are cached per sequence in SeqCache.H [n,128]
+  uint8_t *cg_wx_img = nullptr, *cg_img = nullptr; float* cg_bx = nullptr;
+  DevBuf ws_cgx;                                                     // lstm: category-GRU input halves of a pass, lane-major tiles
   PerSeq ps[2];
   bool weights_ready = false;
   std::vector<void*> owned;
@@ -183,13 +187,14 @@ constexpr int HEAD_BNT = 128;
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
          int ldT = 0, float* outT = nullptr, float* outK = nullptr, int bnt = r4tc::G_BNMAX,
-         const float* A2 = nullptr, const int32_t* gather2 = nullptr, int k2_start = 0, int g2_n = 0) {
+         const float* A2 = nullptr, const int32_t* gather2 = nullptr, int k2_start = 0, int g2_n = 0, int tm_steps = MAXLEN) {
   if (M <= 0) return R4_OK;
   if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
   r4tc::GemmTcParams p{A, lda, gather, Wimg, bias, C, ldc, M, N, K, act, tm_ns, cr_base, ldT, outT, outK};
   p.bnt = bnt;
   p.A2 = A2; p.gather2 = gather2; p.k2_start = k2_start; p.g2_n = g2_n;
+  p.tm_steps = tm_steps;
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int tiles = ((M + r4tc::G_BM - 1) / r4tc::G_BM) * ((N + bnt - 1) / bnt);
   r4tc::k_gemm_tc<<<std::min(tiles, sms), r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
@@ -210,6 +215,27 @@ constexpr int SMEM_CAT = 4 * (NCAT * CAT_LD + NCAT * 24) * 4;
 int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaStream_t st) {
   int rc;
   const int TM = r4tc::TM;
+  if (e->sim == R4_SIM_LSTM) {
+    // nets/utils.py:90-92: Keras GRU over Embedding(seq_i), only the LAST state is used -> c.H is [n, 128]
+    if ((rc = reserve(e, c.H, (size_t)n * EMB * 4))) return rc;
+    c.n = n;
+    const PerSeq& w = e->ps[si];
+    const int chunk = 8192;
+    const int nsmax = std::min(n, chunk);
+    if ((rc = reserve(e, e->ws_xin, (size_t)((nsmax + TM - 1) / TM) * MAXLEN * r4tc::G1_XT_COLS * TM * 4))) return rc;
+    float* xinT = reinterpret_cast<float*>(e->ws_xin.p);
+    for (int s0 = 0; s0 < n; s0 += chunk) {
+      const int ns = std::min(chunk, n - s0);
+      if ((rc = gemm(e, SL_GEMM_XIN, 0, ns * MAXLEN, XIN_LD, EMB, e->emb_seq, EMB, ids + (size_t)s0 * MAXLEN, w.gru_wx_img,
+                     w.gru_bx, nullptr, XIN_LD, st, ns, 0, XIN_LD, xinT, nullptr))) return rc;
+      { ProfScope ps(e, SL_GRU1, st, (double)ns * MAXLEN * 2.0 * (EMB * 2 * EMB + EMB * EMB));
+        r4tc::GruTcParams gp{xinT, w.gru_img, nullptr, ns};
+        gp.hard = 1; gp.Hlast = reinterpret_cast<float*>(c.H.p) + (size_t)s0 * EMB; gp.ld_last = EMB;
+        r4tc::k_gru_tc<<<(ns + TM - 1) / TM, r4tc::NTHREADS, r4tc::G1_SMEM_BYTES, st>>>(gp); }
+      R4_LAUNCH_CHECK(e, "k_gru_tc");
+    }
+    return R4_OK;
+  }
   if ((rc = reserve(e, c.H, (size_t)n * MAXLEN * EMB * 4))) return rc;
   if ((rc = reserve(e, c.Kp, (size_t)n * MAXLEN * AH1 * 4))) return rc;
   if ((rc = reserve(e, c.XT, (size_t)((n + TM - 1) / TM) * MAXLEN * r4tc::XT_COLS * TM * 4))) return rc;
@@ -283,6 +309,46 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
                  const SeqCache& c0, int shared0, const SeqCache& c1, int shared1, float* obs_out,
                  float* p1_out, float* probs_out, cudaStream_t st) {
   int rc;
+  if (e->sim == R4_SIM_LSTM) {
+    // nets/lstm.py:29-36: all = [GRU(seq0) | GRU(seq1) | dense tower | GRU(E_c[cat]) | Flatten(E_c[cat])] -> Dense(256, ELU) =
+    // simulator_obs -> softmax head.  The sequence GRUs' last states come from the caches; the category GRU (21 steps)
+    // runs per pass: E_c gather fused into its input projection, then the tcgen05 recurrence writes its last state
+    // straight into the feature slab; the Flatten() part is gathered by the head GEMM's A staging (as in the dien head).
+    const int TM = r4tc::TM, LD = 4 * EMB;                  // materialised part of the feature vector: 512 columns
+    const int rtiles = (R + TM - 1) / TM;
+    if ((rc = reserve(e, e->ws_allf, (size_t)R * LD * 4))) return rc;
+    if ((rc = reserve(e, e->ws_tmp, (size_t)R * HU * 4))) return rc;
+    if ((rc = reserve(e, e->ws_cgx, (size_t)rtiles * NCAT * r4tc::G1_XT_COLS * TM * 4))) return rc;
+    float* allf = reinterpret_cast<float*>(e->ws_allf.p);
+    float* tmp = reinterpret_cast<float*>(e->ws_tmp.p);
+    float* cgx = reinterpret_cast<float*>(e->ws_cgx.p);
+    { ProfScope ps(e, SL_MISC, st, (double)R);
+      k_seq_last_rows<<<(R * 64 + 255) / 256, 256, 0, st>>>(R, row0, div, reinterpret_cast<const float*>(c0.H.p), shared0,
+                                                          reinterpret_cast<const float*>(c1.H.p), shared1, allf, LD); }
+    R4_LAUNCH_CHECK(e, "k_seq_last_rows");
+    if ((rc = gemm(e, SL_GEMM_XK, 0, R * NCAT, XIN_LD, EMB, e->emb_cat, EMB, cat, e->cg_wx_img, e->cg_bx, nullptr, XIN_LD, st,
+                   R, 0, XIN_LD, cgx, nullptr, r4tc::G_BNMAX, nullptr, nullptr, 0, 0, NCAT))) return rc;
+    { ProfScope ps(e, SL_GRU1, st, (double)R * NCAT * 2.0 * (EMB * 2 * EMB + EMB * EMB));
+      r4tc::GruTcParams gp{cgx, e->cg_img, nullptr, R};
+      gp.steps = NCAT; gp.hard = 1; gp.Hlast = allf + 3 * EMB; gp.ld_last = LD;
+      r4tc::k_gru_tc<<<rtiles, r4tc::NTHREADS, r4tc::G1_SMEM_BYTES, st>>>(gp); }
+    R4_LAUNCH_CHECK(e, "k_gru_tc");
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, NDENSE, dense, NDENSE, nullptr, e->w1_img, e->b1, tmp, HU, st))) return rc;
+    if ((rc = gemm(e, SL_GEMM_DENSE, 1, R, HU, HU, tmp, HU, nullptr, e->w2_img, e->b2, allf + 2 * EMB, LD, st))) return rc;
+    float* obs = obs_out;
+    if (!obs) {
+      if ((rc = reserve(e, e->ws_obs, (size_t)R * OBSD * 4))) return rc;
+      obs = reinterpret_cast<float*>(e->ws_obs.p);
+    }
+    if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, LD + NCAT * EMB, allf, LD, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr,
+                   nullptr, HEAD_BNT, e->emb_cat, cat, LD, NCAT))) return rc;
+    if (p1_out || probs_out) {
+      { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
+        k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
+      R4_LAUNCH_CHECK(e, "k_reward_head");
+    }
+    return R4_OK;
+  }
   if (e->sim == R4_SIM_WIDEDEEP) {
     // nets/widedeep.py:31-38: simulator_obs = [Dense256(ELU)(seq mean-pools) | dense tower | Flatten(E_c[cat])]; softmax head on it.
     // The sequence ids of the pass rows are in e->ws_seq (obs / reward passes: k_seq_ids_rows; r4_dien_forward: the caller's).
@@ -574,8 +640,8 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
     return fail(nullptr, R4_ERR_ARG, "r4_create: SeqSlateRecEnv needs max_steps to be a multiple of page_items");
   if (cfg->category_hash_size < cfg->action_size)
     return fail(nullptr, R4_ERR_ARG, "r4_create: category_hash_size must cover the item ids");
-  if (cfg->simulator < R4_SIM_DIEN || cfg->simulator > R4_SIM_WIDEDEEP)
-    return fail(nullptr, R4_ERR_ARG, "r4_create: simulator must be R4_SIM_DIEN, R4_SIM_DNN or R4_SIM_WIDEDEEP (config['algo'] = 'dien' | 'dnn' | 'widedeep')");
+  if (cfg->simulator < R4_SIM_DIEN || cfg->simulator > R4_SIM_LSTM)
+    return fail(nullptr, R4_ERR_ARG, "r4_create: simulator must be R4_SIM_DIEN, R4_SIM_DNN, R4_SIM_WIDEDEEP or R4_SIM_LSTM (config['algo'] = 'dien' | 'dnn' | 'widedeep' | 'lstm')");
   cudaError_t st = cudaSetDevice(device);
   if (st != cudaSuccess) return fail(nullptr, R4_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(st));
   r4_env* e = new r4_env();
@@ -680,6 +746,58 @@ int r4_finalize_weights(r4_env* e, void* stream) {
   R4_CUDA(e, cudaSetDevice(e->device));
   const size_t Hh = (size_t)e->hash;
   struct Need { const char* n; size_t sz; };
+  if (e->sim == R4_SIM_LSTM) {
+    // W-table of nets/lstm.py:8-45 (rl4rs_b200/synth.py: lstm_weight_shapes): Keras GRU layers = kernel [128, 384],
+    // recurrent kernel [128, 384], ONE bias [384], gate columns [z | r | h].  The recurrence kernel wants [r | u | c]
+    // (u = Keras z), the x-side projection carries the whole bias.
+    std::vector<Need> need = {{"emb_cat", Hh * EMB}, {"emb_seq", Hh * EMB}, {"dense_w1", (size_t)NDENSE * HU}, {"dense_b1", HU},
+                              {"dense_w2", (size_t)HU * HU}, {"dense_b2", HU}, {"cgru_k", (size_t)EMB * 3 * EMB},
+                              {"cgru_rk", (size_t)EMB * 3 * EMB}, {"cgru_b", 3 * EMB}, {"sgru0_k", (size_t)EMB * 3 * EMB},
+                              {"sgru0_rk", (size_t)EMB * 3 * EMB}, {"sgru0_b", 3 * EMB}, {"sgru1_k", (size_t)EMB * 3 * EMB},
+                              {"sgru1_rk", (size_t)EMB * 3 * EMB}, {"sgru1_b", 3 * EMB},
+                              {"obs_w", (size_t)(4 * EMB + NCAT * EMB) * OBSD}, {"obs_b", OBSD}, {"rew_w", OBSD * 2}, {"rew_b", 2}};
+    for (auto& nd : need)
+      if (!hw_get(e, nd.n, nd.sz)) return fail(e, R4_ERR_ARG, std::string("r4_finalize_weights(lstm): missing or mis-shaped ") + nd.n);
+    for (void* p : e->owned) cudaFree(p);
+    e->owned.clear();
+    int rc;
+    if ((rc = upload(e, e->hw["emb_cat"], &e->emb_cat)) || (rc = upload(e, e->hw["emb_seq"], &e->emb_seq)) ||
+        (rc = upload(e, e->hw["dense_b1"], &e->b1)) || (rc = upload(e, e->hw["dense_b2"], &e->b2)) ||
+        (rc = upload(e, e->hw["obs_b"], &e->bo)) || (rc = upload(e, e->hw["rew_w"], &e->wr)) ||
+        (rc = upload(e, e->hw["rew_b"], &e->br)) ||
+        (rc = upload_image(e, e->hw["dense_w1"].data(), NDENSE, HU, &e->w1_img)) ||
+        (rc = upload_image(e, e->hw["dense_w2"].data(), HU, HU, &e->w2_img)) ||
+        (rc = upload_image(e, e->hw["obs_w"].data(), 4 * EMB + NCAT * EMB, OBSD, &e->wo_img, HEAD_BNT))) return rc;
+    auto keras_gru = [&](const std::string& pre, uint8_t** wx_img, float** bx_dev, uint8_t** rec_img) -> int {
+      const float* k = e->hw[pre + "_k"].data(); const float* rk = e->hw[pre + "_rk"].data(); const float* b = e->hw[pre + "_b"].data();
+      std::vector<float> wx((size_t)EMB * XIN_LD), bx(XIN_LD), wgh((size_t)EMB * 2 * EMB), wch((size_t)EMB * EMB);
+      const int src_of[3] = {EMB, 0, 2 * EMB};            // ours [r | u | c] <- Keras [z | r | h] column blocks
+      for (int kk = 0; kk < EMB; ++kk)
+        for (int g = 0; g < 3; ++g)
+          for (int n = 0; n < EMB; ++n) {
+            wx[(size_t)kk * XIN_LD + g * EMB + n] = k[(size_t)kk * 3 * EMB + src_of[g] + n];
+            const float r = rk[(size_t)kk * 3 * EMB + src_of[g] + n];
+            if (g < 2) wgh[(size_t)kk * 2 * EMB + g * EMB + n] = r; else wch[(size_t)kk * EMB + n] = r;
+          }
+      for (int g = 0; g < 3; ++g) for (int n = 0; n < EMB; ++n) bx[g * EMB + n] = b[src_of[g] + n];
+      std::vector<uint8_t> gi(r4tc::G1_IMAGE_BYTES);
+      r4tc::build_gru_image(wgh.data(), wch.data(), gi.data());
+      int rc2;
+      if ((rc2 = upload(e, gi, rec_img)) || (rc2 = upload(e, bx, bx_dev)) || (rc2 = upload_image(e, wx.data(), EMB, XIN_LD, wx_img))) return rc2;
+      return R4_OK;
+    };
+    if ((rc = keras_gru("cgru", &e->cg_wx_img, &e->cg_bx, &e->cg_img)) ||
+        (rc = keras_gru("sgru0", &e->ps[0].gru_wx_img, &e->ps[0].gru_bx, &e->ps[0].gru_img)) ||
+        (rc = keras_gru("sgru1", &e->ps[1].gru_wx_img, &e->ps[1].gru_bx, &e->ps[1].gru_img))) return rc;
+    e->hw.clear();
+    e->weights_ready = true;
+    // SlateRecEnv's second sequence is the constant [0] (slate.py:75 -> 64 x id 0): cache its last GRU state once
+    cudaStream_t st = S(stream);
+    if ((rc = reserve(e, e->ws_ids1, (size_t)std::max(e->B, 1) * MAXLEN * 4))) return rc;
+    R4_CUDA(e, cudaMemsetAsync(e->ws_ids1.p, 0, (size_t)MAXLEN * 4, st));
+    if ((rc = build_cache(e, 1, reinterpret_cast<const int32_t*>(e->ws_ids1.p), 1, e->c1const, st))) return rc;
+    return R4_OK;
+  }
   if (e->sim == R4_SIM_WIDEDEEP) {
     // W-table of nets/widedeep.py:8-45: emb_cat, dense tower, emb_seq (ONE table for both sequences), fc [256,256] (the
     // Dense on the pooled sequences, :34), simulator_reward [3072,2]; 'simulator_obs' is a Concatenate (no weights)
@@ -863,7 +981,7 @@ int r4_reset(r4_env* e, const int32_t* row_idx, const r4_out* out, void* stream)
   e->has_reset = true;
   // user-history GRU-1 + input projections: once per episode (they do not depend on the actions); the dnn simulator
   // has no sequence branch
-  if (e->sim == R4_SIM_DIEN && (rc = build_cache(e, 0, (const int32_t*)e->ws_ids0.p, B, e->c0, st))) return rc;
+  if ((e->sim == R4_SIM_DIEN || e->sim == R4_SIM_LSTM) && (rc = build_cache(e, 0, (const int32_t*)e->ws_ids0.p, B, e->c0, st))) return rc;
   if ((rc = obs_pass(e, 0, 0, out, st))) return rc;
   if (out && out->reward) { k_fill_f64<<<(B + 255) / 256, 256, 0, st>>>(B, 0.0, out->reward); R4_LAUNCH_CHECK(e, "k_fill_f64"); }
   if (out && out->done) { k_fill_u8<<<(B + 255) / 256, 256, 0, st>>>(B, 0, out->done); R4_LAUNCH_CHECK(e, "k_fill_u8"); }
@@ -883,7 +1001,7 @@ int r4_step(r4_env* e, const void* action, int action_is_f64, const r4_out* out,
   bool conti = (e->cfg.flags & R4_FLAG_CONTI) != 0;
   // SeqSlate: entering a new page, the second sequence becomes the items of all previous pages
   // (seqslate.py:109-110) -> rebuild its GRU-1 cache once per page.
-  if (e->sim == R4_SIM_DIEN && e->seq && cur > 0 && cur % e->P == 0) {
+  if ((e->sim == R4_SIM_DIEN || e->sim == R4_SIM_LSTM) && e->seq && cur > 0 && cur % e->P == 0) {
     if ((rc = reserve(e, e->ws_ids1, (size_t)B * MAXLEN * 4))) return rc;
     k_seq_ids<<<(B * MAXLEN + 255) / 256, 256, 0, st>>>(B, e->T, cur, e->row_idx, e->log_seq, e->prev_actions,
                                                          nullptr, (int32_t*)e->ws_ids1.p, nullptr);
@@ -1291,7 +1409,7 @@ int r4_dien_forward(r4_env* e, const int32_t* seq, const float* dense, const int
   R4_CUDA(e, cudaSetDevice(e->device));
   cudaStream_t st = S(stream);
   int rc;
-  if (e->sim != R4_SIM_DIEN) {          // dnn: no sequence branch; widedeep: raw ids, no sequence cache
+  if (e->sim == R4_SIM_DNN || e->sim == R4_SIM_WIDEDEEP) {          // dnn: no sequence branch; widedeep: raw ids, no sequence cache
     rc = R4_OK;
     int chunk = std::min(n_rows, e->max_rows);
     for (int r0 = 0; !rc && r0 < n_rows; r0 += chunk) {

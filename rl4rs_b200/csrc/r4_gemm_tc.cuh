@@ -85,6 +85,7 @@ struct GemmTcParams {
   // kernel's thread (= lane) reads 4 consecutive columns with ONE 128-bit load (ncu, round 2: with one 32-bit load per
   // column the AUGRU epilogue spent 18 % of its cycles in lg_throttle, 192 LDGs per thread and step).
   int tm_ns, cr_base, ldT; float* outT; float* outK;
+  int tm_steps = STEPS;       // steps per sequence in sequence mode (64; 21 for the `lstm` simulator's category GRU)
   int bnt = G_BNMAX;          // n-tile width of the weight image (build_gemm_image)
   // Second, GATHERED part of the A operand (the observation head: K = 768 + 21 x 128): for k >= k2_start, A[m][k] is
   // A2[gather2[m * g2_n + j] * 128 + (k - k2_start) % 128] with j = (k - k2_start) / 128 -- the Flatten() of the category
@@ -213,7 +214,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
           for (int it = 0; it < 2; ++it) {
             int m = m0 + it * 64 + r8;
             if (m >= p.M) m = p.M - 1;
-            if (p.tm_ns > 0) m = (m % p.tm_ns) * 64 + (m / p.tm_ns);
+            if (p.tm_ns > 0) m = (m % p.tm_ns) * p.tm_steps + (m / p.tm_ns);
             size_t src = p.gather ? (size_t)__ldg(p.gather + m) : (size_t)m;
             arow[it] = p.A + src * p.lda + kc * 8;
             if (p.A2) { grow[it] = p.gather2 + (size_t)m * p.g2_n; id_next[it] = __ldg(grow[it]); }   // slot 0: needed k2_start / 32 K blocks later
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
           asm volatile("bar.sync 1, 128;" ::: "memory");
           if (tid == G_EPI_T0) {
             const int t = m0 / p.tm_ns, nb = (p.cr_base + m0 % p.tm_ns) / G_BM;
-            float* dst = p.outT + (((size_t)nb * STEPS + t) * p.ldT + (n0 + c)) * TM;
+            float* dst = p.outT + (((size_t)nb * p.tm_steps + t) * p.ldT + (n0 + c)) * TM;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(smem_u32(ob)), "r"(G_OUT_BYTES) : "memory");
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -367,8 +368,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n0 + c + j;
-            if (col < p.ldT) p.outT[xt_index((size_t)(nabs / TM) * STEPS + t, p.ldT, col, nabs % TM)] = a[j];
-            else p.outK[((size_t)nabs * STEPS + t) * (p.N - p.ldT) + (col - p.ldT)] = a[j];
+            if (col < p.ldT) p.outT[xt_index((size_t)(nabs / TM) * p.tm_steps + t, p.ldT, col, nabs % TM)] = a[j];
+            else p.outK[((size_t)nabs * p.tm_steps + t) * (p.N - p.ldT) + (col - p.ldT)] = a[j];
           }
         } else if (m < p.M) {
           float* o = p.C + (size_t)m * p.ldc + n0 + c;

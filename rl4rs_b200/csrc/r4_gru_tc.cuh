@@ -43,11 +43,20 @@ inline void build_gru_image(const float* Wg, const float* Wc, uint8_t* img) {
 }
 
 struct GruTcParams {
-  const float* XT;        // [ceil(n/128), 64, 384 / 4, 128, 4]  input halves (+bias), lane-major tiles, quad layout
+  const float* XT;        // [ceil(n/128), steps, 384 / 4, 128, 4]  input halves (+bias), lane-major tiles, quad layout
   const uint8_t* Wimg;    // G1_IMAGE_BYTES
-  float* H;               // [n, 64, 128] outputs of every step
+  float* H;               // [n, steps, 128] outputs of every step, or nullptr
   int n;
+  int steps = STEPS;      // recurrence length (<= 64): 64 for the behaviour sequences, 21 for the `lstm` simulator's category GRU
+  int hard = 0;           // 1: Keras v1 GRU gates, hard sigmoid clip(0.2 x + 0.5, 0, 1) (nets/utils.py:34,92); 0: TF1 GRUCell
+  float* Hlast = nullptr; // [n, ld_last] the LAST state only (the `lstm` simulator), or nullptr
+  int ld_last = GH;
 };
+
+// gate non-linearity of the r / u gates
+__device__ __forceinline__ float gru_gate(float x, int hard) {
+  return hard ? fminf(fmaxf(fmaf(0.2f, x, 0.5f), 0.0f), 1.0f) : fast_sigmoid(x);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -81,7 +90,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
     if (warp == 9) {
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
-        for (int t = 0; t < STEPS; ++t) {
+        for (int t = 0; t < p.steps; ++t) {
           const uint8_t* src = p.Wimg;
           for (int i = 0; i < G1_STAGES_PER_STEP; ++i, src += G1_STAGE) {
             mbar_wait(&bar_empty[stage], phase ^ 1);
@@ -128,7 +137,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
           }
         };
         const uint32_t hHi = smem_u32(sHhi), hLo = smem_u32(sHlo), rHi = smem_u32(sRhi), rLo = smem_u32(sRlo);
-        for (int t = 0; t < STEPS; ++t) {
+        for (int t = 0; t < p.steps; ++t) {
           const uint32_t par = t & 1;
           mbar_wait(&bar_h, par);
           tc_fence_after();
@@ -151,9 +160,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
     int n = m0 + row;
     const bool valid = n < p.n;
     if (!valid) n = p.n - 1;
-    const float* xt = p.XT + ((size_t)(n / TM) * STEPS) * G1_XT_COLS * TM;
+    const float* xt = p.XT + ((size_t)(n / TM) * p.steps) * G1_XT_COLS * TM;
     const int ln4 = (n % TM) * 4;
-    float* hout = p.H + (size_t)n * STEPS * GH + c0;
+    float* hout = p.H ? p.H + (size_t)n * p.steps * GH + c0 : nullptr;
+    const int hard = p.hard;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row_off = (uint32_t)(row / 8) * G1_A_SBO + (uint32_t)(row % 8) * 16;
     float h[64];
@@ -168,7 +178,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
     proxy_fence();
     mbar_arrive(&bar_h);
 
-    for (int t = 0; t < STEPS; ++t) {
+    for (int t = 0; t < p.steps; ++t) {
       const uint32_t par = t & 1;
       const float* xs = xt + (size_t)t * G1_XT_COLS * TM;
 #define R4_LOADX(dst, colbase) load_x16(dst, xs, (colbase), ln4)
@@ -185,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
           tmem_wait_ld();
           if (ch < 3) { R4_LOADX(x[nxt], c0 + (ch + 1) * 16); tmem_ld16(tlane + G1_T_R + c0 + (ch + 1) * 16, a[nxt]); }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[cur][j]) * h[ch * 16 + j];
+          for (int j = 0; j < 16; ++j) a[cur][j] = gru_gate(a[cur][j] + x[cur][j], hard) * h[ch * 16 + j];
 #pragma unroll
           for (int g = 0; g < 2; ++g) {
             uint4 hi, lo;
@@ -212,7 +222,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
           tmem_wait_ld();
           if (ch < 3) { R4_LOADX(x[nxt], GH + c0 + (ch + 1) * 16); tmem_ld16(tlane + G1_T_U + c0 + (ch + 1) * 16, a[nxt]); }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[cur][j]);
+          for (int j = 0; j < 16; ++j) a[cur][j] = gru_gate(a[cur][j] + x[cur][j], hard);
           tmem_st16(tlane + G1_T_U + c0 + ch * 16, a[cur]);
         }
         tmem_wait_st();
@@ -249,7 +259,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
             *reinterpret_cast<uint4*>(sHhi + off) = hi;
             *reinterpret_cast<uint4*>(sHlo + off) = lo;
           }
-          if (valid) {
+          if (valid && hout) {
             float* o = hout + (size_t)t * GH + ch * 16;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(a[cur][j], a[cur][j + 1], a[cur][j + 2], a[cur][j + 3]);
@@ -260,6 +270,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_gru_tc(GruTcParams p) {
       tc_fence_before();
       proxy_fence();
       mbar_arrive(&bar_h);
+    }
+    if (valid && p.Hlast) {
+      float* o = p.Hlast + (size_t)n * p.ld_last + c0;
+#pragma unroll
+      for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
     }
   }
   tc_fence_before();

@@ -393,6 +393,16 @@ __global__ void __launch_bounds__(128) k_seq_pool(int R, const int32_t* __restri
     *reinterpret_cast<float4*>(out + (size_t)r * 2 * EMB + s * EMB + lane * 4) = make_float4(acc.x / n, acc.y / n, acc.z / n, acc.w / n);
   }
 }
+// lstm simulator (nets/utils.py:78-97): the cached LAST states of the two sequence GRUs -> columns [0, 256) of the
+// feature slab of a pass (pass row i -> cache row (row0 + i) / div, or row 0 of a shared one-row cache).
+__global__ void k_seq_last_rows(int R, int row0, int div, const float* __restrict__ h0, int shared0,
+                                const float* __restrict__ h1, int shared1, float* __restrict__ out, int ld) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // one thread = one float4 of one row: 64 per row
+  if (i >= R * 64) return;
+  const int r = i >> 6, c = (i & 63) * 4, s = c >= EMB;
+  const int ci = (s ? shared1 : shared0) ? 0 : (row0 + r) / div;
+  *reinterpret_cast<float4*>(out + (size_t)r * ld + c) = ldg4((s ? h1 : h0) + (size_t)ci * EMB + (c & (EMB - 1)));
+}
 // sequence ids of the rows of one simulator pass (pass row i -> env row (row0 + i) / div): seq0 = user history, seq1 = the
 // items of the previous pages (seqslate.py:36-37,109-110) or zeros, as k_seq_ids
 __global__ void k_seq_rows(int R, int row0, int div, int T, int p0, const int32_t* __restrict__ row_idx,

@@ -17,11 +17,17 @@
 namespace r4tc {
 
 constexpr int S_K = 128, S_N = 64, S_KEYS = 64;
-constexpr int S_A_SPLIT = TM * S_K * 2;            // 32 KB per split
-constexpr int S_A_STAGE = 2 * S_A_SPLIT;           // hi + lo = 64 KB
+// A operand (built by the producer warps): K-adjacent core matrices 160 B apart instead of 128.  A producer quarter-warp
+// holds (2 rows x 4 K chunks) -- the mapping that keeps its global loads in whole 128-byte lines -- and with LBO = 128 the
+// four K chunks of a row hit the same banks: every 128-bit operand store replayed 4x and the kernel ran at 84 % of the
+// L1/shared pipe on those replays (ncu, round 2).  With 160 the bank group of (row, kc) is (row + 2 kc) mod 8: distinct.
+constexpr int S_A_LBO = 160;
+constexpr int S_A_SBO = (S_K / 8) * S_A_LBO;       // 2560: 8-row groups of the A operand
+constexpr int S_A_SPLIT = (TM / 8) * S_A_SBO;      // 40 KB per split
+constexpr int S_A_STAGE = 2 * S_A_SPLIT;           // hi + lo = 80 KB
 constexpr int S_B_SPLIT = S_N * S_K * 2;           // 16 KB per split
 constexpr int S_B_BYTES = 3 * S_B_SPLIT;           // 48 KB, resident
-constexpr int S_SBO = (S_K / 8) * 128;             // 2048: 8-row groups (A and B)
+constexpr int S_SBO = (S_K / 8) * 128;             // 2048: 8-row groups (B: the weight image)
 constexpr int S_SMEM_BYTES = 2 * S_A_STAGE + S_B_BYTES + 1024;
 constexpr int S_THREADS = 320;                     // 4 producer + 4 epilogue + MMA + loader warps
 constexpr int S_KP_LD = 64;                        // cached key half k_t (Wk - Wd): Kp [n_cached, 64 keys, 64]
@@ -157,8 +163,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
         const uint32_t d = tbase + s * S_N;
 #pragma unroll
         for (int j = 0; j < S_K / 16; ++j) {
-          const uint32_t ko = j * 2 * LBO;
-          uint64_t ah = make_desc(a0 + ko, LBO, S_SBO), al = make_desc(a0 + S_A_SPLIT + ko, LBO, S_SBO);
+          const uint32_t ko = j * 2 * LBO, ka = j * 2 * S_A_LBO;
+          uint64_t ah = make_desc(a0 + ka, S_A_LBO, S_A_SBO), al = make_desc(a0 + S_A_SPLIT + ka, S_A_LBO, S_A_SBO);
           uint64_t bh = make_desc(b0 + ko, LBO, S_SBO), bm = make_desc(b0 + S_B_SPLIT + ko, LBO, S_SBO);
           uint64_t bl = make_desc(b0 + 2 * S_B_SPLIT + ko, LBO, S_SBO);
           mma_bf16(d, al, bm, idesc, j ? 1u : 0u);
@@ -197,7 +203,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
                         h1.x * q1.x, h1.y * q1.y, h1.z * q1.z, h1.w * q1.w};
           uint4 hi, lo;
           split8(v, hi, lo);
-          const uint32_t off = (uint32_t)(m / 8) * S_SBO + (uint32_t)(k / 8) * LBO + (uint32_t)(m % 8) * 16;
+          const uint32_t off = (uint32_t)(m / 8) * S_A_SBO + (uint32_t)(k / 8) * S_A_LBO + (uint32_t)(m % 8) * 16;
           *reinterpret_cast<uint4*>(a + off) = hi;
           *reinterpret_cast<uint4*>(a + S_A_SPLIT + off) = lo;
         }

@@ -220,9 +220,9 @@ class SlateRecEnv(RecSimBase):
 
     def get_model(self, config):
         algo = config.get("algo", "dien")                              # slate.py:239-242: rl4rs/nets/<algo>.py
-        if algo not in ("dien", "dnn", "widedeep"):
-            raise NotImplementedError("simulator %r is not built: 'dien' (nets/dien.py), 'dnn' (nets/dnn.py) and 'widedeep' "
-                                      "(nets/widedeep.py) are (SURVEY.md section 8f n4)" % (algo,))
+        if algo not in ("dien", "dnn", "widedeep", "lstm"):
+            raise NotImplementedError("simulator %r is not a graph of rl4rs/nets: 'dien', 'dnn', 'widedeep' and 'lstm' are built "
+                                      "(SURVEY.md section 8f n4)" % (algo,))
         w = config.get("weights")
         if w is None:
             w = self.load_model_file(config["model_file"], config)
@@ -234,7 +234,8 @@ class SlateRecEnv(RecSimBase):
         ``<prefix>.index`` + ``<prefix>.data-*``, README.md:124-137), or an .npz of the W-table."""
         from ..utils import tf_checkpoint
         if tf_checkpoint.is_saver_prefix(model_file):
-            load = {"dnn": tf_checkpoint.load_dnn_checkpoint, "widedeep": tf_checkpoint.load_widedeep_checkpoint}.get(
+            load = {"dnn": tf_checkpoint.load_dnn_checkpoint, "widedeep": tf_checkpoint.load_widedeep_checkpoint,
+                    "lstm": tf_checkpoint.load_lstm_checkpoint}.get(
                 config.get("algo", "dien"), tf_checkpoint.load_dien_checkpoint)
             return load(model_file, config, name_map=config.get("variable_name_map"))
         return dict(np.load(model_file))

@@ -306,6 +306,36 @@ def make_widedeep_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0
     return _make_plain(widedeep_weight_shapes(cfg), seed, stress, bias_noise)
 
 
+def lstm_weight_shapes(cfg=None):
+    """W-table of the `lstm` simulator (rl4rs/nets/lstm.py:8-45, nets/utils.py:28-36,78-97): Keras GRU layers -- kernel
+    [in, 3U], recurrent kernel [U, 3U], ONE bias [3U] (reset_after = False), gate order [z | r | h]."""
+    cfg = cfg or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D, C, S = cfg.get("dense_feature_num", 432), cfg.get("category_feature_num", 21), cfg.get("seq_num", 2)
+    shapes = [("emb_cat", (H, E)), ("cgru_k", (E, 3 * U)), ("cgru_rk", (U, 3 * U)), ("cgru_b", (3 * U,)),
+              ("dense_w1", (D, U)), ("dense_b1", (U,)), ("dense_w2", (U, U)), ("dense_b2", (U,)), ("emb_seq", (H, E))]
+    for i in range(S):
+        shapes += [("sgru%d_k" % i, (E, 3 * U)), ("sgru%d_rk" % i, (U, 3 * U)), ("sgru%d_b" % i, (3 * U,))]
+    return shapes + [("obs_w", (S * U + U + U + C * E, 256)), ("obs_b", (256,)),
+                     ("rew_w", (256, cfg.get("class_num", 2))), ("rew_b", (cfg.get("class_num", 2),))]
+
+
+def make_lstm_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0, gru_stress=1.0, gru_bias_noise=None):
+    """Keras default initialisers for the `lstm` simulator (the recurrent kernels get glorot instead of orthogonal: same
+    scale, and nothing downstream depends on orthogonality).  ``gru_stress`` scales the GRU kernels only and
+    ``gru_bias_noise`` replaces the GRU biases by N(0, gru_bias_noise): with default initialisers the gate pre-activations
+    stay inside (-2.5, 2.5) and the hard sigmoid never clips; (2.5, 1.5) clips ~25 % of the gates and is still
+    well-conditioned (f32 and f64 oracles agree to 2e-6), larger kernels make the recurrence chaotic."""
+    w = _make_plain(lstm_weight_shapes(cfg), seed, stress, bias_noise)
+    rs = np.random.RandomState(seed + 17)
+    for k in sorted(w):
+        if "gru" in k and not k.endswith("_b") and gru_stress != 1.0:
+            w[k] = (w[k] * np.float32(gru_stress)).astype(np.float32)
+        if "gru" in k and k.endswith("_b") and gru_bias_noise is not None:
+            w[k] = rs.normal(0.0, gru_bias_noise, w[k].shape).astype(np.float32)
+    return w
+
+
 def make_weights(cfg=None, seed=WEIGHT_SEED, stress=1.0, bias_noise=0.0, bounded_scores=False):
     """W-table with TF1/Keras default initialisers; ``stress`` scales all non-embedding kernels,
     ``bias_noise`` adds N(0, bias_noise) to every bias (so parity tests see non-trivial biases).

@@ -487,6 +487,42 @@ def save_widedeep_checkpoint(prefix, weights, config=None):
     return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})
 
 
+def lstm_layer_plan(config=None):
+    """nets/lstm.py:8-45 in creation order: id_input_processing_lstm -> Embedding #0, GRU #0; dense tower -> Dense #0, #1;
+    sequence_input_LSTM -> Embedding #1, GRU #1, #2 (one per sequence); simulator_obs; simulator_reward.  A Keras (v1,
+    reset_after = False) GRU layer owns kernel [in, 3U], recurrent_kernel [U, 3U], bias [3U]."""
+    cfg = config or {}
+    H, E, U = cfg.get("category_hash_size", 100000), cfg.get("emb_size", 128), cfg.get("hidden_units", 128)
+    D, C, S, cls = cfg.get("dense_feature_num", 432), cfg.get("category_feature_num", 21), cfg.get("seq_num", 2), cfg.get("class_num", 2)
+    plan = [("emb_cat", "embedding", (H, E)), ("cgru_k", "gru", (E, 3 * U)), ("cgru_rk", "gru", (U, 3 * U)), ("cgru_b", "gru", (3 * U,)),
+            ("dense_w1", "dense", (D, U)), ("dense_b1", "dense", (U,)), ("dense_w2", "dense_1", (U, U)), ("dense_b2", "dense_1", (U,)),
+            ("emb_seq", "embedding_1", (H, E))]
+    for i in range(S):
+        sc = "gru_%d" % (i + 1)
+        plan += [("sgru%d_k" % i, sc, (E, 3 * U)), ("sgru%d_rk" % i, sc, (U, 3 * U)), ("sgru%d_b" % i, sc, (3 * U,))]
+    return plan + [("obs_w", "simulator_obs", (S * U + U + U + C * E, 256)), ("obs_b", "simulator_obs", (256,)),
+                   ("rew_w", "simulator_reward", (256, cls)), ("rew_b", "simulator_reward", (cls,))]
+
+
+def lstm_variable_names(config=None):
+    def inner(name):
+        if name.startswith("emb_"):
+            return "embeddings"
+        if name.endswith("_rk"):
+            return "recurrent_kernel"
+        return "kernel" if name.endswith(("_k", "_w", "_w1", "_w2")) else "bias"
+    return {name: scope + "/" + inner(name) for name, scope, _ in lstm_layer_plan(config)}
+
+
+def load_lstm_checkpoint(prefix, config=None, name_map=None):
+    return _load_by_plan(prefix, lstm_layer_plan(config), lstm_variable_names(config), name_map)
+
+
+def save_lstm_checkpoint(prefix, weights, config=None):
+    names = lstm_variable_names(config)
+    return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})
+
+
 def save_dnn_checkpoint(prefix, weights, config=None):
     names = dnn_variable_names(config)
     return write_bundle(prefix, {names[k]: np.asarray(v, dtype=np.float32) for k, v in weights.items() if k in names})

@@ -136,3 +136,54 @@ def test_widedeep_env_matches_oracle(seq):
         assert_close_rel(rew, rrew, what="widedeep env reward step %d" % t)
         paid += int((np.asarray(rrew) != 0).any())
     assert paid >= 1
+
+
+# ---- lstm (config['algo'] = 'lstm'; rl4rs/nets/lstm.py:8-45): Keras GRUs over both sequences and over the category embeddings ----
+def _lstm_setup(B, seq, stress=1.0, bias_noise=0.0, gru=(2.5, 1.5), **flags):
+    from rl4rs_b200 import synth
+    cfg = dict(_cfg(B, seq, **flags), algo="lstm")
+    cat = synth.make_catalog()
+    log = synth.make_log(4 * B, pages=4 if seq else 1, catalog=cat, hash_size=100000, corrupt_frac=0.1)
+    # gru = (kernel scale, bias sigma): ~25 % of the hard-sigmoid gates clip (synth.make_lstm_weights)
+    return cfg, cat, log, synth.make_lstm_weights(cfg, stress=stress, bias_noise=bias_noise, gru_stress=gru[0], gru_bias_noise=gru[1])
+
+
+@pytest.mark.parametrize("n_rows,gru", [(300, (2.5, 1.5)), (700, (1.0, None))])
+def test_lstm_forward_alone_matches_oracle(n_rows, gru):
+    from oracle.lstm_np import LstmOracle
+    from test_gpu_parity_regimes import _random_feature_rows
+    cfg, cat, log, w = _lstm_setup(8, False, stress=1.5, bias_noise=0.1, gru=gru)
+    env = make_env(cfg, False, cat, log, w, output_format="numpy")
+    seq, dense, catf = _random_feature_rows(n_rows, 8, 100000)
+    obs, probs = env.sim.engine.dien_forward(seq, dense, catf)
+    o_ref, p_ref = LstmOracle(w, np.float32).forward(seq, dense, catf)
+    o64, p64 = LstmOracle(w, np.float64).forward(seq, dense, catf)
+    assert obs.shape == (n_rows, 256)
+    assert_close_rel(obs.cpu().numpy(), o_ref, what="lstm obs")
+    assert_close_rel(obs.cpu().numpy(), o64, what="lstm obs vs f64")
+    assert_close_rel(probs.cpu().numpy(), p_ref, what="lstm probs")
+
+
+@pytest.mark.parametrize("seq", [False, True])
+def test_lstm_env_matches_oracle(seq):
+    from oracle.lstm_np import LstmOracle
+    from oracle.env_np import OracleEnv
+    B = 40
+    cfg, cat, log, w = _lstm_setup(B, seq, stress=1.5, bias_noise=0.1, support_rllib_mask=True)
+    env = make_env(cfg, seq, cat, log, w, output_format="numpy")
+    assert env.observation_space["obs"].shape == (256,)
+    ref = OracleEnv(cfg, log, cat, LstmOracle(w, np.float32), seq=seq)
+    rs = np.random.RandomState(11)
+    o, r = env.reset(), ref.reset()
+    assert_close_rel(o["obs"], r["obs"], what="lstm env reset obs")
+    paid = 0
+    for t in range(cfg["max_steps"]):
+        a = np.where(rs.rand(B) < 0.85, ref.offline_action, rs.randint(0, 284, B))
+        o, rew, done, info = env.step(a)
+        r, rrew, rdone, _ = ref.step(a)
+        np.testing.assert_array_equal(o["action_mask"], r["action_mask"], err_msg="mask %d" % t)
+        assert_close_rel(o["obs"], r["obs"], what="lstm env obs step %d" % t)
+        assert_close_rel(rew, rrew, what="lstm env reward step %d" % t)
+        np.testing.assert_array_equal(done, rdone)
+        paid += int((np.asarray(rrew) != 0).any())
+    assert paid >= 1

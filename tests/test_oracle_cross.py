@@ -74,3 +74,22 @@ def test_dnn_checkpoint_round_trip(tmp_path):
     assert set(got) == set(w)
     for k in w:
         np.testing.assert_array_equal(got[k], w[k])
+
+
+def test_lstm_numpy_oracle_matches_independent_torch_restatement(tmp_path):
+    from oracle.lstm_np import LstmOracle
+    from rl4rs_b200.utils import tf_checkpoint as tfc
+    w = synth.make_lstm_weights(SMALL, stress=2.0, bias_noise=0.2)
+    seq, dense, cat = _rows(24, 5, 600)
+    o_np, p_np = LstmOracle(w, np.float64).forward(seq, dense, cat)
+    o_t, p_t = torch_ref.lstm_forward(w, seq, dense, cat)
+    assert o_np.shape == (24, 256)
+    np.testing.assert_allclose(o_np, o_t, rtol=0, atol=1e-12 * max(1.0, np.abs(o_t).max()))
+    np.testing.assert_allclose(p_np, p_t, rtol=0, atol=1e-13)
+    o32, _ = LstmOracle(w, np.float32).forward(seq, dense, cat)
+    assert np.abs(o32 - o_t).max() < 1e-4 * max(1.0, np.abs(o_t).max())
+    p = tfc.save_lstm_checkpoint(str(tmp_path / "lstm"), w, SMALL)
+    got = tfc.load_lstm_checkpoint(p, SMALL)
+    assert set(got) == set(w) and all(np.array_equal(got[k], w[k]) for k in w)
+    names = tfc.lstm_variable_names(SMALL)
+    assert names["cgru_rk"] == "gru/recurrent_kernel" and names["sgru1_b"] == "gru_2/bias" and names["emb_seq"] == "embedding_1/embeddings"

@@ -185,7 +185,7 @@ int main(int argc, char** argv) {
 #ifdef PAIR
         for (int t = 10; t < 13; ++t) {
           long long* d = hd + t * 16;
-          printf("  step %d MMA thread: wait h %lld | issue r %lld | issue u %lld | wait rh %lld | issue c %lld | total %lld (ring waits: own %lld peer %lld)\n", t, d[1] - d[0],
+          printf("  step %d MMA thread: wait h %lld | issue r %lld | issue u %lld | wait rh %lld | issue c %lld | total %lld (waits: operand quarters %lld, ring stages %lld)\n", t, d[1] - d[0],
                  d[2] - d[1], d[3] - d[2], d[4] - d[3], d[5] - d[4], hd[(t + 1) * 16] - d[0], d[6], d[7]);
           printf("      epilogue thread 0: wait r %lld | R %lld | wait u %lld | U %lld | wait c %lld | C %lld\n", d[9] - d[8], d[10] - d[9],
                  d[11] - d[10], d[12] - d[11], d[13] - d[12], d[14] - d[13]);
