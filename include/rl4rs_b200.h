@@ -170,8 +170,9 @@ int r4_augru_kernel_for(int ctas, int sms);
 /* Process-wide kernel-choice overrides for parity tests and A/B timing (no reference counterpart):
  *   "augru_kernel"     0 = by r4_augru_kernel_for (default), 1 = always k_augru_tc, 2 = always the 2-CTA pair kernel,
  *                      3 = always the ping-pong pair kernel (two recurrences per pair)
- *   "augru_pair_impl"  which pair kernel: 1 = k_augru_pair2 as built (default), 2..4 = its other template variants
- *                      (<RELAY,TMAP> = <0,1> <1,0> <0,0>)
+ *   "augru_pair_impl"  hand-over / weight-ring variant of the pair kernels, <RELAY, TMAP>: 1 = <0,0> (default: direct
+ *                      release.cta arrive, per-CTA bulk-copy ring), 2 = <0,1> (tensor-map ring), 3 = <1,0> (relayed
+ *                      release.cluster hand-over), 4 = <1,1>
  *   "augru_cost_single" / "augru_cost_pair" / "augru_cost_pp"  the per-wave costs r4_augru_kernel_for compares (positive ints)
  *   "augru_cluster"    CTAs per cluster of the pair kernel: 2 (one pair), 4 or 8 (2 / 4 pairs share one multicast weight stream)
  * The environment variables R4_AUGRU_SINGLE / R4_AUGRU_PAIR / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE give the initial

@@ -31,10 +31,15 @@ constexpr int P_NB = 128;                             // weight columns (B rows)
 constexpr int P_HALF_BYTES = P_NB * KB * 2;           // 8192: one split of one 32-deep K block of the CTA's 128 columns
 constexpr int P_STAGE_BYTES = 2 * P_HALF_BYTES;       // 16384: ring stage = [hi | lo] of one K block (6 MMAs, 384 cycles)
 constexpr int P_STAGES_PER_STEP = 3 * NKB;            // 24
+// Ring depth.  Measured (tools/augru_probe.cu, round 2, cycles per step of k_augru_pair2 / k_augru_pp): 6 stages 17.1 k /
+// 31.3 k, 4 stages 16.0 k / 31.4 k, 3 stages 15.7 k / 29.6 k, 2 stages 20.5 k.  A deep ring refills in bursts that compete
+// with the gate epilogues for the shared-memory port (the MMA warp's own clocks: with 6 stages it waits 7-8 k cycles per
+// step for operand quarters, i.e. for the epilogue, with 3 stages 2.7 k); 3 stages = 48 KB keeps the weight stream just
+// ahead of the MMAs.  24 % (2 * P_NST) == 0 keeps stage and parity compile-time.
 #ifndef R4P_NST
-#define R4P_NST 6
+#define R4P_NST 3
 #endif
-constexpr int P_NST = R4P_NST;                        // ring depth; 24 % (2 * P_NST) == 0 keeps stage and parity compile-time
+constexpr int P_NST = R4P_NST;
 #ifndef R4P_COMMIT_GROUP
 #define R4P_COMMIT_GROUP 1
 #endif
@@ -71,8 +76,18 @@ __device__ __forceinline__ void arrive_cl(uint32_t caddr) {
 // relaxed form is enough where the data being published lives in the ARRIVING CTA's own shared memory and has
 // already been made visible to the async proxy (TMA completion, or fence.proxy.async by every writer + __syncwarp):
 // the consumer is this SM's tensor core, started by the leader only after it has observed the arrival.
-__device__ __forceinline__ void arrive_cl_relaxed(uint32_t caddr) {
+#ifndef R4P_DIRECT_ARRIVE
+#define R4P_DIRECT_ARRIVE 1   // direct (no relay) remote arrive: 0 = relaxed.cluster, 1 = release.cta (the default semantics of
+#endif                        // mbarrier.arrive: CUTLASS's ClusterBarrier::arrive(cta_id)), 2 = release.cluster.  Measured
+                              // (cycles per step, <RELAY 0, TMAP 0>): 15.5 k | 15.5 k | 30.1 k
+__device__ __forceinline__ void arrive_remote(uint32_t caddr) {
+#if R4P_DIRECT_ARRIVE == 1
+  asm volatile("mbarrier.arrive.release.cta.shared::cluster.b64 _, [%0];" :: "r"(caddr) : "memory");
+#elif R4P_DIRECT_ARRIVE == 2
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(caddr) : "memory");
+#else
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" :: "r"(caddr) : "memory");
+#endif
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {

@@ -9,14 +9,17 @@
 //     reloaded with the next phase's columns the moment it has been consumed, so every L2 load has a whole phase
 //     (~2 k cycles) to land.  Round 1: a 1-deep pipeline over 16-column chunks left each phase (R 5.3 k, U 4.8 k,
 //     C 5.5 k cycles) bound by L2 latency, and the phases run back to back on the same 8 warps.
-//   * hand-over with release semantics (RELAY = 1, default): the peer's epilogue warps arrive on a barrier in their OWN
-//     CTA (cta scope, cheap); one relay lane per barrier (warps 10 / 11 of the peer, idle otherwise) forwards each
-//     completed phase to the leader with mbarrier.arrive.release.cluster.  The ~320-cycle cost of a cluster-scope
-//     release is paid by the relay lane, not by 8 epilogue warps, and the chain  st.shared -> fence.proxy.async ->
-//     arrive(release.cta) -> wait(acquire.cta) -> arrive(release.cluster) -> wait(acquire.cluster) -> tcgen05.mma
-//     is a happens-before chain in the PTX memory model (round-1 advisor finding: a relaxed remote arrive is not).
-//     RELAY = 0 keeps the relaxed direct arrive as an opt-in fast path (-DR4P2_RELAY=0).
-//   * weight ring by tensor-map TMA (TMAP = 1, default): both CTAs issue cp.async.bulk.tensor.2d.cta_group::2 for
+//   * hand-over: every epilogue warp of BOTH CTAs publishes a finished operand quarter with st.shared ->
+//     fence.proxy.async -> __syncwarp -> one mbarrier.arrive.release.cta on the LEADER's barrier (a shared::cluster address
+//     for the peer: the instruction CUTLASS's ClusterBarrier::arrive(cta_id) issues for the peer-epilogue -> leader-MMA
+//     signals of its 2-SM kernels).  The data a peer warp publishes stays in the PEER's shared memory and is read by the
+//     peer SM's half of the cta_group::2 MMA; what crosses the cluster is only the arrival.  Round 1 used a .relaxed remote
+//     arrive (advisor finding: not a release); .release.cluster on the arriving warps costs 2x the kernel (30 k cycles per
+//     step: ~320 cycles per arrive, 8 per step and warp, on the critical path of the chasing MMAs).  RELAY = 1 keeps the
+//     strictly cluster-scoped chain as an option: the peer's warps arrive on a barrier in their OWN CTA and one relay lane
+//     per operand (warps 10 / 11 of the peer) forwards each completed quarter with mbarrier.arrive.release.cluster --
+//     19.3 k cycles per step against 15.5 k.
+//   * weight ring by tensor-map TMA (TMAP = 1, optional; the per-CTA bulk-copy ring measured faster): both CTAs issue cp.async.bulk.tensor.2d.cta_group::2 for
 //     their own half of the stage with the LEADER's "full" barrier as the completion target, the leader's producer
 //     posts one expect_tx for both halves.  No relay thread, no remote arrive: the transaction count is the signal.
 //     The image is viewed as a 2-D tensor of 1 KB rows, a stage is a 256 x 16 box of u32 (16 KB, dense).
@@ -24,11 +27,13 @@
 #include <cuda.h>
 #include "r4_augru_pair.cuh"
 
+// Defaults of the product build (r4_capi.cu: augru_pair_impl 1), chosen by measurement (tools/augru_probe.cu, round 2, 64
+// tiles, cycles per step): <RELAY 0, TMAP 0> 15.5 k | <0,1> 17.2 k | <1,1> 19.3 k.
 #ifndef R4P2_RELAY
-#define R4P2_RELAY 1
+#define R4P2_RELAY 0
 #endif
 #ifndef R4P2_TMAP
-#define R4P2_TMAP 1
+#define R4P2_TMAP 0
 #endif
 #ifndef R4P2_PRESCALE
 #define R4P2_PRESCALE 0   // 1: the cached input halves arrive pre-multiplied (r, u columns by -log2(e), c columns by 2 log2(e)),
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
         int stage = 0; uint32_t phase = 0;
         for (int i = 0; i < STEPS * P_STAGES_PER_STEP; ++i) {
           mbar_wait(&bar_full[stage], phase);
-          arrive_cl_relaxed(remote0 + stage * 8);
+          arrive_remote(remote0 + stage * 8);
           if (++stage == P_NST) { stage = 0; phase ^= 1; }
         }
       }
@@ -344,7 +349,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_augru_pair2(const __grid_consta
       tc_fence_before();
       proxy_fence();
       __syncwarp();
-      if (lane == 0) { if (local_arrive) mbar_arrive(&bars[i]); else arrive_cl_relaxed(bars_leader + i * 8); }
+      if (lane == 0) { if (local_arrive) mbar_arrive(&bars[i]); else arrive_remote(bars_leader + i * 8); }
     };
     float h[64], x[4][16];
 #pragma unroll

@@ -222,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) k_augru
 #pragma unroll
     for (int s = 0; s < 2; ++s) { h_leader[s] = mapa_rank(smem_u32(&bar_h[s]), 0); rh_leader[s] = mapa_rank(smem_u32(&bar_rh[s]), 0); }
     auto arrive = [&](uint64_t* local, uint32_t remote) {      // lane 0, after proxy_fence + __syncwarp
-      if (local_arrive) mbar_arrive(local); else arrive_cl_relaxed(remote);
+      if (local_arrive) mbar_arrive(local); else arrive_remote(remote);
     };
     float h[2][64], x[PP_XD + 1][PP_CH];
 #pragma unroll

@@ -100,7 +100,7 @@ struct r4_env {
   SeqCache c0, c1const, c1page;
   bool c1_is_page = false;
   // workspaces
-  DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1, ws_q;
+  DevBuf ws_cat, ws_dense, ws_scores, ws_allf, ws_tmp, ws_obs, ws_p1, ws_xin, ws_ids0, ws_ids1, ws_q, ws_part;
   // side stream: category attention + dense tower run concurrently with scores + AUGRU (they only
   // meet at the head GEMM), which fills the SMs the 128-row AUGRU tiles leave idle at small batch
   cudaStream_t side = nullptr;
@@ -187,7 +187,8 @@ constexpr int HEAD_BNT = 128;
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
          int ldT = 0, float* outT = nullptr, float* outK = nullptr, int bnt = r4tc::G_BNMAX,
-         const float* A2 = nullptr, const int32_t* gather2 = nullptr, int k2_start = 0, int g2_n = 0, int tm_steps = MAXLEN) {
+         const float* A2 = nullptr, const int32_t* gather2 = nullptr, int k2_start = 0, int g2_n = 0, int tm_steps = MAXLEN,
+         int ksplit_max = 1) {
   if (M <= 0) return R4_OK;
   if ((N & 15) || (K & 7) || (lda & 3) || (ldc & 3)) return fail(e, R4_ERR_ARG, "gemm: unaligned shape");
   ProfScope ps(e, slot, st, 2.0 * M * N * K);
@@ -196,9 +197,24 @@ int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int 
   p.A2 = A2; p.gather2 = gather2; p.k2_start = k2_start; p.g2_n = g2_n;
   p.tm_steps = tm_steps;
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-  const int tiles = ((M + r4tc::G_BM - 1) / r4tc::G_BM) * ((N + bnt - 1) / bnt);
+  int tiles = ((M + r4tc::G_BM - 1) / r4tc::G_BM) * ((N + bnt - 1) / bnt);
+  // split-K when the output tiles leave SMs idle and K is long (each part keeps >= 16 K blocks): the head at 4096 rows
+  static const bool no_splitk = getenv("R4_NO_SPLITK") != nullptr;
+  const int ksplit = no_splitk ? 1 : std::max(1, std::min(std::min(ksplit_max, sms / std::max(tiles, 1)), K / (16 * r4tc::G_BK)));
+  if (ksplit > 1) {
+    if (tm_ns > 0 || !C || (N & 3)) return fail(e, R4_ERR_ARG, "gemm: split-K needs a plain row-major output");
+    int rc;
+    if ((rc = reserve(e, e->ws_part, (size_t)ksplit * M * N * 4))) return rc;
+    p.ksplit = ksplit; p.part = reinterpret_cast<float*>(e->ws_part.p);
+    tiles *= ksplit;
+  }
   r4tc::k_gemm_tc<<<std::min(tiles, sms), r4tc::G_THREADS, r4tc::G_SMEM_BYTES, st>>>(p);
   R4_LAUNCH_CHECK(e, "k_gemm_tc");
+  if (ksplit > 1) {
+    const size_t n4 = (size_t)M * (N / 4);
+    r4tc::k_splitk_finish<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(M, N, ksplit, p.part, bias, act, C, ldc);
+    R4_LAUNCH_CHECK(e, "k_splitk_finish");
+  }
   return R4_OK;
 }
 
@@ -265,10 +281,10 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
 // Kernel-choice options (r4_set_option; the environment gives the initial values).
 struct AugruOpts {
   int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel (one recurrence per pair), 3 ping-pong pair kernel
-  int pair_impl = 1;      // 1 = k_augru_pair2<R4P2_RELAY, R4P2_TMAP>, 2..4 = <0,1> <1,0> <0,0>
-  // cost of one wave, measured (tools/augru_probe.cu, ms x 12.5): k_augru_tc 1.19 ms per 148 tile-sequences,
-  // k_augru_pair2 0.64 ms per 74, k_augru_pp 1.0 ms per 74 TILES (= 148 tile-sequences)
-  int cost_single = 15, cost_pair = 8, cost_pp = 13;
+  int pair_impl = 1;      // k_augru_pair2<RELAY, TMAP>: 1 = <0,0> (default), 2 = <0,1>, 3 = <1,0>, 4 = <1,1>; k_augru_pp<RELAY> follows RELAY
+  // cost of one wave, measured (tools/augru_probe.cu, round 2, ms x 25): k_augru_tc 1.19 ms per 148 tile-sequences,
+  // k_augru_pair2 0.51 ms per 74, k_augru_pp 0.96 ms per 74 TILES (= 148 tile-sequences)
+  int cost_single = 30, cost_pair = 13, cost_pp = 24;
   int cluster = 2;        // CTAs per cluster of the pair kernel: 2, or 4 / 8 = weight stream shared by 2 / 4 pairs (multicast)
   AugruOpts() {
     if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
@@ -341,7 +357,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
       obs = reinterpret_cast<float*>(e->ws_obs.p);
     }
     if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, LD + NCAT * EMB, allf, LD, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr,
-                   nullptr, HEAD_BNT, e->emb_cat, cat, LD, NCAT))) return rc;
+                   nullptr, HEAD_BNT, e->emb_cat, cat, LD, NCAT, MAXLEN, 4))) return rc;
     if (p1_out || probs_out) {
       { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
         k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
@@ -472,8 +488,8 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     else if (which == 3) {
       r4tc::AugruPairParams pp;
       pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
-      if (augru_pair_impl() == 2 || augru_pair_impl() == 4) r4tc::k_augru_pp<0><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
-      else r4tc::k_augru_pp<R4P2_RELAY><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
+      if (augru_pair_impl() >= 3) r4tc::k_augru_pp<1><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
+      else r4tc::k_augru_pp<0><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
     } else {
       r4tc::AugruPairParams pp;
       pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
@@ -486,13 +502,13 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
       lc.gridDim = dim3((pgrid.x + cs - 1) / cs * cs, 2); lc.blockDim = dim3(r4tc::NTHREADS);
       lc.dynamicSmemBytes = r4tc::P_SMEM_BYTES; lc.stream = st; lc.attrs = at; lc.numAttrs = 1;
       cudaError_t le;
-      if (cs == 4) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, 1, 4>, pp);
-      else if (cs == 8) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, 1, 8>, pp);
+      if (cs == 4) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 1, 4>, pp);
+      else if (cs == 8) le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 1, 8>, pp);
       else switch (augru_pair_impl()) {
         case 2: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 1, 2>, pp); break;
         case 3: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<1, 0, 2>, pp); break;
-        case 4: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 0, 2>, pp); break;
-        default: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<R4P2_RELAY, R4P2_TMAP, 2>, pp); break;
+        case 4: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<1, 1, 2>, pp); break;
+        default: le = cudaLaunchKernelEx(&lc, r4tc::k_augru_pair2<0, 0, 2>, pp); break;
       }
       (void)le;
     } }
@@ -506,7 +522,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   }
   // head: K = 768 materialised columns + 21 x 128 gathered from the category embedding table by `cat`
   if ((rc = gemm(e, SL_GEMM_HEAD, 1, R, OBSD, ALLF, allf, ALLF_LD, nullptr, e->wo_img, e->bo, obs, OBSD, st, 0, 0, 0, nullptr, nullptr, HEAD_BNT,
-                 e->emb_cat, cat, ALLF_LD, NCAT))) return rc;
+                 e->emb_cat, cat, ALLF_LD, NCAT, MAXLEN, 4))) return rc;
   if (p1_out || probs_out) {
     { ProfScope ps(e, SL_RHEAD, st, (double)R * 2.0 * OBSD * 2);
     k_reward_head<<<(R + 3) / 4, 128, 0, st>>>(R, obs, e->wr, e->br, p1_out, probs_out); }
@@ -659,8 +675,8 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<R4P2_RELAY, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_pair2<R4P2_RELAY, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
@@ -693,7 +709,7 @@ void r4_destroy(r4_env* e) {
   DevBuf* bufs[] = {&e->c0.H, &e->c0.Kp, &e->c1const.H, &e->c1const.Kp, &e->c1page.H, &e->c1page.Kp,
                     &e->c0.XT, &e->c1const.XT, &e->c1page.XT,
                     &e->ws_cat, &e->ws_dense, &e->ws_scores, &e->ws_allf, &e->ws_tmp, &e->ws_obs, &e->ws_p1,
-                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q, &e->ws_seq};
+                    &e->ws_xin, &e->ws_ids0, &e->ws_ids1, &e->ws_q, &e->ws_seq, &e->ws_cgx, &e->ws_part};
   for (DevBuf* b : bufs) if (b->p) cudaFree(b->p);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);

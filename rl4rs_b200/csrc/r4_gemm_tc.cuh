@@ -92,8 +92,41 @@ struct GemmTcParams {
   // embeddings (nets/utils.py:24) read straight from the embedding table (L2-resident, 51 MB) instead of from a
   // 10.7 KB-per-row copy that k_cat_attn used to write and this kernel used to read back.  k2_start % 32 == 0.
   const float* A2 = nullptr; const int32_t* gather2 = nullptr; int k2_start = 0, g2_n = 0;
+  // Split-K (ksplit > 1): tile t = (output tile t / ksplit, K part t % ksplit); every part writes its raw accumulators
+  // to part[ks][M][N] and k_splitk_finish adds them in part order (deterministic), then bias + activation.  For GEMMs with
+  // fewer output tiles than SMs and a long K (the observation head: 64 tiles x 108 K blocks at 4096 rows).
+  int ksplit = 1; float* part = nullptr;
   long long* dbg = nullptr;   // development probe (tools/gemm_probe.cu): per-role wait/busy cycles of CTA 0
 };
+
+// K blocks [kb0, kb1) of part `ks`: boundaries on multiples of 4 K blocks, so a part never starts inside a 128-wide
+// gathered slot (k2_start / 32 is a multiple of 4)
+__device__ __forceinline__ void gemm_kpart(int kbn, int ksplit, int ks, int& kb0, int& kb1) {
+  if (ksplit <= 1) { kb0 = 0; kb1 = kbn; return; }
+  const int b0 = ks == 0 ? 0 : min(kbn, (int)(((long long)kbn * ks / ksplit + 2) / 4 * 4));
+  const int b1 = ks + 1 >= ksplit ? kbn : min(kbn, (int)(((long long)kbn * (ks + 1) / ksplit + 2) / 4 * 4));
+  kb0 = b0; kb1 = b1;
+}
+
+// out = act(sum_ks part[ks] + bias): the second, deterministic pass of a split-K GEMM.  One thread = 4 columns.
+__global__ void k_splitk_finish(int M, int N, int ksplit, const float* __restrict__ part, const float* __restrict__ bias, int act,
+                                float* __restrict__ C, int ldc) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int n4 = N / 4;
+  if (i >= (size_t)M * n4) return;
+  const int m = (int)(i / n4), n = (int)(i % n4) * 4;
+  float4 a = *reinterpret_cast<const float4*>(part + (size_t)m * N + n);
+  for (int ks = 1; ks < ksplit; ++ks) {
+    const float4 b = *reinterpret_cast<const float4*>(part + ((size_t)ks * M + m) * N + n);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+  }
+  if (bias) { a.x += __ldg(bias + n); a.y += __ldg(bias + n + 1); a.z += __ldg(bias + n + 2); a.w += __ldg(bias + n + 3); }
+  if (act == 1) {
+    a.x = a.x > 0.f ? a.x : expm1f(a.x); a.y = a.y > 0.f ? a.y : expm1f(a.y);
+    a.z = a.z > 0.f ? a.z : expm1f(a.z); a.w = a.w > 0.f ? a.w : expm1f(a.w);
+  }
+  *reinterpret_cast<float4*>(C + (size_t)m * ldc + n) = a;
+}
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
@@ -114,7 +147,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
   __shared__ __align__(16) float bias_s[2][G_BNMAX];          // bias of the tile in each accumulator's epilogue
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int kbn = (p.K + G_BK - 1) / G_BK;
-  const int ntn = (p.N + p.bnt - 1) / p.bnt, mtn = (p.M + G_BM - 1) / G_BM, ntiles = mtn * ntn;
+  const int ntn = (p.N + p.bnt - 1) / p.bnt, mtn = (p.M + G_BM - 1) / G_BM, ksp = max(p.ksplit, 1), ntiles = mtn * ntn * ksp;
 
   if (tid == 0) {
     for (int i = 0; i < G_NST; ++i) { mbar_init(&bar_a[i], 256); mbar_init(&bar_b[i], 1); mbar_init(&bar_empty[i], 1); }
@@ -135,11 +168,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int nt = tile % ntn;
+        const int nt = (tile / ksp) % ntn;
+        int kb0, kb1; gemm_kpart(kbn, ksp, tile % ksp, kb0, kb1);
         const uint32_t bsb = (uint32_t)min(p.bnt, p.N - nt * p.bnt) * G_BK * 2;
         // start of this n-tile in the image: the tiles before it are full width
         const uint8_t* wtile = p.Wimg + (size_t)nt * kbn * G_SPLIT * p.bnt * G_BK * 2;
-        for (int kb = 0; kb < kbn; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&bar_empty[stage], phase ^ 1);
           uint8_t* dst = smem + stage * G_STAGE_BYTES + G_SPLIT * G_A_STAGE;
           mbar_expect_tx(&bar_b[stage], G_SPLIT * bsb);
@@ -158,14 +192,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
       long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();
       const bool probe = p.dbg && blockIdx.x == 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
-        const int nt = tile % ntn;
+        const int nt = (tile / ksp) % ntn;
+        int kb0, kb1; gemm_kpart(kbn, ksp, tile % ksp, kb0, kb1);
         const uint32_t idesc = make_idesc(G_BM, min(p.bnt, p.N - nt * p.bnt));
         const uint32_t acc = tbase + (uint32_t)(li & 1) * G_BNMAX;
         long long c0 = probe ? clock64() : 0;
         mbar_wait(&acc_empty[li & 1], (uint32_t)((li >> 1) & 1) ^ 1u);   // the epilogue has drained this accumulator
         if (probe) w_acc += clock64() - c0;
         tc_fence_after();
-        for (int kb = 0; kb < kbn; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           if (probe) {
             long long c1 = clock64(); mbar_wait(&bar_a[stage], phase);
             long long c2 = clock64(); mbar_wait(&bar_b[stage], phase);
@@ -183,7 +218,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
               b[sp] = make_desc(sb + sp * G_B_STAGE + j * 2 * LBO, LBO, G_B_SBO);
             }
             // smallest products first so they are not absorbed by a large partial sum
-            mma_bf16(acc, a[1], b[1], idesc, (kb | j) ? 1u : 0u);   // mid*mid
+            mma_bf16(acc, a[1], b[1], idesc, (kb > kb0 || j) ? 1u : 0u);   // mid*mid
             mma_bf16(acc, a[0], b[2], idesc, 1u);                   // hi*lo
             mma_bf16(acc, a[2], b[0], idesc, 1u);                   // lo*hi
             mma_bf16(acc, a[0], b[1], idesc, 1u);                   // hi*mid
@@ -205,11 +240,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     const float* arow[2] = {p.A, p.A};
     const int32_t* grow[2] = {p.gather2, p.gather2};
     int id_cur[2] = {0, 0}, id_next[2] = {0, 0};   // gathered part: table row of the current / next 128-wide slot of each row
-    int is_tile = blockIdx.x, is_kb = 0;
+    int is_tile = blockIdx.x, is_kb0 = 0, is_kb1 = kbn;
+    if (is_tile < ntiles) gemm_kpart(kbn, ksp, is_tile % ksp, is_kb0, is_kb1);
+    int is_kb = is_kb0;
     auto issue = [&](int slot) {
       if (is_tile < ntiles) {
-        if (is_kb == 0) {
-          const int m0 = (is_tile / ntn) * G_BM;
+        if (is_kb == is_kb0) {
+          const int m0 = (is_tile / ksp / ntn) * G_BM;
 #pragma unroll
           for (int it = 0; it < 2; ++it) {
             int m = m0 + it * 64 + r8;
@@ -217,7 +254,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
             if (p.tm_ns > 0) m = (m % p.tm_ns) * p.tm_steps + (m / p.tm_ns);
             size_t src = p.gather ? (size_t)__ldg(p.gather + m) : (size_t)m;
             arow[it] = p.A + src * p.lda + kc * 8;
-            if (p.A2) { grow[it] = p.gather2 + (size_t)m * p.g2_n; id_next[it] = __ldg(grow[it]); }   // slot 0: needed k2_start / 32 K blocks later
+            if (p.A2) {        // slot 0: needed k2_start / 32 K blocks later; a K part that starts inside the gathered region: its own slot
+              grow[it] = p.gather2 + (size_t)m * p.g2_n;
+              id_next[it] = __ldg(grow[it] + max(0, (is_kb0 * G_BK - p.k2_start) >> 7));
+            }
           }
         }
         const bool part2 = p.A2 && is_kb * G_BK >= p.k2_start;
@@ -240,7 +280,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
           cp_async16(dst, src, nb);
           cp_async16(dst + 16, src + 4, nb);
         }
-        if (++is_kb == kbn) { is_kb = 0; is_tile += gridDim.x; }
+        if (++is_kb == is_kb1) {
+          is_tile += gridDim.x;
+          if (is_tile < ntiles) gemm_kpart(kbn, ksp, is_tile % ksp, is_kb0, is_kb1);
+          is_kb = is_kb0;
+        }
       }
       cp_async_commit();
     };
@@ -251,7 +295,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     long long w_cp = 0, w_empty = 0;
     const bool probe = p.dbg && blockIdx.x == 0 && tid == 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kbn; ++kb) {
+      int ckb0, ckb1; gemm_kpart(kbn, ksp, tile % ksp, ckb0, ckb1);
+      for (int kb = ckb0; kb < ckb1; ++kb) {
         issue(slot == 0 ? G_RAW - 1 : slot - 1);          // the slot converted in the previous iteration
         long long c0 = probe ? clock64() : 0;
         cp_async_wait<G_RAW - 1>();
@@ -304,7 +349,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
     const int row = q * 32 + lane;
     int li = 0, nchunk = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++li) {
-      const int m0 = (tile / ntn) * G_BM, n0 = (tile % ntn) * p.bnt;
+      const int bt = tile / ksp, ks = tile % ksp;
+      const int m0 = (bt / ntn) * G_BM, n0 = (bt % ntn) * p.bnt;
       const int bn = min(p.bnt, p.N - n0);
       const int m = m0 + row;
       const uint32_t tlane = tbase + (uint32_t)(li & 1) * G_BNMAX + ((uint32_t)(q * 32) << 16);
@@ -326,6 +372,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
         tmem_ld16(tlane + c, a);
         tmem_wait_ld();
         long long e1 = probe ? clock64() : 0;
+        if (ksp > 1) {          // split-K: raw partial sums, bias + activation in k_splitk_finish
+          if (m < p.M) {
+            float* o = p.part + ((size_t)ks * p.M + m) * p.N + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(a[j], a[j + 1], a[j + 2], a[j + 3]);
+          }
+          continue;
+        }
         // bias + activation for the whole chunk first, branch-free: with the bias load, the ELU branch and the store
         // interleaved per element the chunk was a chain of 16 exposed latencies (~2.4k cycles; ncu source page in
         // profiles/) and the epilogue, not the MMAs, set the time of the sequence-mode GEMMs.

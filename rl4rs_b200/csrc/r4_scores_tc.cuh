@@ -29,7 +29,10 @@ constexpr int S_B_SPLIT = S_N * S_K * 2;           // 16 KB per split
 constexpr int S_B_BYTES = 3 * S_B_SPLIT;           // 48 KB, resident
 constexpr int S_SBO = (S_K / 8) * 128;             // 2048: 8-row groups (B: the weight image)
 constexpr int S_SMEM_BYTES = 2 * S_A_STAGE + S_B_BYTES + 1024;
-constexpr int S_THREADS = 320;                     // 4 producer + 4 epilogue + MMA + loader warps
+constexpr int S_PROD_WARPS = 8, S_EPI_WARPS = 8;  // ncu, round 2: with 4 + 4 every SM sub-partition had ONE producer and ONE epilogue
+constexpr int S_W_MMA = S_PROD_WARPS + S_EPI_WARPS, S_W_LOAD = S_W_MMA + 1;   // warp, each a serial dependency chain: 20 k cycles per tile
+constexpr int S_THREADS = (S_W_LOAD + 1) * 32;     // 576: 8 producer + 8 epilogue + MMA + loader warps
+constexpr int S_TC_PART = 2 * S_N;                 // TMEM columns of the epilogue pairs' partial sums (2 buffers x 16)
 constexpr int S_KP_LD = 64;                        // cached key half k_t (Wk - Wd): Kp [n_cached, 64 keys, 64]
 
 // host: Wp [128 k][64 n] fp32 -> 3 splits of [64 n x 128 k] K-major core matrices
@@ -125,14 +128,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&bar_afull[i], 128); mbar_init(&bar_aempty[i], 1);
-      mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], 128);
+      mbar_init(&bar_afull[i], S_PROD_WARPS * 32); mbar_init(&bar_aempty[i], 1);
+      mbar_init(&bar_tfull[i], 1); mbar_init(&bar_tempty[i], S_EPI_WARPS * 32);
     }
     mbar_init(&bar_w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(128));
+  if (warp == S_W_MMA) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(256));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int i = tid; i < S_N * 16; i += S_THREADS) W2_s[i] = __ldg(S.W2 + i);
@@ -142,12 +145,12 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
 
-  if (warp == 9) {
+  if (warp == S_W_LOAD) {
     if (lane == 0) {                                   // Wp image: once per CTA
       mbar_expect_tx(&bar_w, S_B_BYTES);
       bulk_g2s(sB, S.WpImg, S_B_BYTES, &bar_w);
     }
-  } else if (warp == 8) {
+  } else if (warp == S_W_MMA) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(TM, S_N);
       mbar_wait(&bar_w, 0);
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
         umma_commit(&bar_tfull[s]);
       }
     }
-  } else if (warp < 4) {
-    // ===== producers: q (10 gathered embeddings) and A = q * H as bf16 hi/lo =====
+  } else if (warp < S_PROD_WARPS) {
+    // ===== producers: A = q * H as bf16 hi/lo; thread = (row slot tid / 4 of 64, K chunk tid % 4), 2 row passes =====
     const int kc = tid & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -189,8 +192,8 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
 #pragma unroll 2
       for (int kb = 0; kb < S_K / 32; ++kb) {
 #pragma unroll
-        for (int i4 = 0; i4 < 4; ++i4) {
-          const int m = i4 * 32 + (tid >> 2);          // tile row: feature row m/64, key m%64
+        for (int i2 = 0; i2 < 2; ++i2) {
+          const int m = i2 * 64 + (tid >> 2);          // tile row: feature row m/64, key m%64
           const int rr = m >> 6, key = m & 63;
           int r = min(tile * 2 + rr, p.R - 1);
           const size_t ci = S.shared ? 0 : (size_t)((p.row0 + r) / p.div);
@@ -211,11 +214,15 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       proxy_fence();
       mbar_arrive(&bar_afull[s]);
     }
-  } else if (warp < 8) {
-    // ===== epilogue: lane = key row of the tile =====
-    const int e = tid - 128;                     // 0..127
-    const int ew = e >> 5;                       // TMEM lane quarter (warp 4..7 -> 0..3)
+  } else if (warp < S_W_MMA) {
+    // ===== epilogue: lane = key row of the tile; the two warps of a TMEM lane quarter split the 64 hidden units of the
+    // first attention layer (jh = 0: units 0-31, jh = 1: 32-63); jh = 1 hands its 16 partial sums of the second layer to
+    // its partner through 16 spare TMEM columns of their common lanes =====
+    const int e = (tid - S_PROD_WARPS * 32) & 127;   // row of the tile: 0..127
+    const int jh = (tid - S_PROD_WARPS * 32) >> 7;
+    const int ew = e >> 5;                       // TMEM lane quarter
     const int rr = e >> 6, key = e & 63;
+    const int j0 = jh * (S_N / 2);
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
@@ -223,31 +230,31 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       const int r = tile * 2 + rr;
       const int rc = min(r, p.R - 1);
       const size_t ci = S.shared ? 0 : (size_t)((p.row0 + rc) / p.div);
-      // Everything this thread needs from global memory is requested BEFORE it waits for the accumulators: its key's
-      // cached half k_t (Wk - Wd) (16 x 128-bit, one 256-byte line per lane) and, through shared memory, the tile's two
-      // query rows.  (ncu, round 1: with the loads inside the j loop the 64 x 16 FMA tail sat on the long scoreboard --
-      // 16 dependent L2 round trips per tile -- and the kernel ran at 20 % issue utilisation, 5 % of DRAM bandwidth.)
-      const float* kp = S.Kp + (ci * S_KEYS + key) * S_KP_LD;
-      float4 kk[S_N / 4];
+      // Everything this thread needs from global memory is requested BEFORE it waits for the accumulators: its half of
+      // its key's cached half k_t (Wk - Wd) (8 x 128-bit) and, through shared memory, the tile's two query rows.
+      // (ncu, round 1: with the loads inside the j loop the FMA tail sat on the long scoreboard -- 16 dependent L2 round
+      // trips per tile.)
+      const float* kp = S.Kp + (ci * S_KEYS + key) * S_KP_LD + j0;
+      float4 kk[S_N / 8];
 #pragma unroll
-      for (int j = 0; j < S_N / 4; ++j) kk[j] = __ldg(reinterpret_cast<const float4*>(kp) + j);
-      qa_s[s][e] = __ldg(S.qa + (size_t)rc * S_N + key);
-      named_bar_sync(2, 128);                      // epilogue warps only; buffer s is rewritten two tiles later
+      for (int j = 0; j < S_N / 8; ++j) kk[j] = __ldg(reinterpret_cast<const float4*>(kp) + j);
+      if (jh == 0) qa_s[s][e] = __ldg(S.qa + (size_t)rc * S_N + key);
+      named_bar_sync(2, S_EPI_WARPS * 32);         // epilogue warps only; buffer s is rewritten two tiles later
       mbar_wait(&bar_tfull[s], ph);
       tc_fence_after();
-      float z[S_N];
-      const uint32_t ta = tbase + ((uint32_t)(ew * 32) << 16) + s * S_N;
+      float z[S_N / 2];
+      const uint32_t tl = tbase + ((uint32_t)(ew * 32) << 16);
 #pragma unroll
-      for (int c = 0; c < S_N; c += 16) tmem_ld16(ta + c, z + c);
+      for (int c = 0; c < S_N / 2; c += 16) tmem_ld16(tl + s * S_N + j0 + c, z + c);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive(&bar_tempty[s]);               // accumulators are free again
-      const float* qap = qa_s[s] + rr * S_N;
+      const float* qap = qa_s[s] + rr * S_N + j0;
       float o[16];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) o[jj] = b2_s[jj];
+      for (int jj = 0; jj < 16; ++jj) o[jj] = jh ? 0.f : b2_s[jj];
 #pragma unroll
-      for (int j = 0; j < S_N; j += 4) {
+      for (int j = 0; j < S_N / 2; j += 4) {
         const float4 kq = kk[j / 4];
         const float4 qq = *reinterpret_cast<const float4*>(qap + j);
         float zz[4] = {z[j] + qq.x + kq.x, z[j + 1] + qq.y + kq.y, z[j + 2] + qq.z + kq.z, z[j + 3] + qq.w + kq.w};
@@ -255,18 +262,29 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
         for (int u = 0; u < 4; ++u) {
           float a1 = fast_sigmoid(zz[u]);        // ex2.approx + rcp.approx (2^-22 / 1 ulp), as in the AUGRU gates
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) o[jj] = fmaf(a1, W2_s[(j + u) * 16 + jj], o[jj]);
+          for (int jj = 0; jj < 16; ++jj) o[jj] = fmaf(a1, W2_s[(j0 + j + u) * 16 + jj], o[jj]);
         }
       }
-      float sc = S.bk;
+      // pair hand-over: buffer s of the partial-sum columns is rewritten two tiles later, after the partner's read of it
+      // (the partner reads before it arrives at the next tile's pair barrier, which the writer also passes)
+      const uint32_t tpart = tl + S_TC_PART + s * 16;
+      if (jh) { tmem_st16(tpart, o); tmem_wait_st(); tc_fence_before(); }
+      named_bar_sync(4 + ew, 64);
+      if (!jh) {
+        float o2[16];
+        tc_fence_after();
+        tmem_ld16(tpart, o2);
+        tmem_wait_ld();
+        float sc = S.bk;
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) sc = fmaf(fast_sigmoid(o[jj]), kv_s[jj], sc);
-      if (r < p.R) S.scoresT[((size_t)(r >> 7) * S_KEYS + key) * 128 + (r & 127)] = sc;
+        for (int jj = 0; jj < 16; ++jj) sc = fmaf(fast_sigmoid(o[jj] + o2[jj]), kv_s[jj], sc);
+        if (r < p.R) S.scoresT[((size_t)(r >> 7) * S_KEYS + key) * 128 + (r & 127)] = sc;
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(128));
+  if (warp == S_W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(256));
 }
 
 }  // namespace r4tc

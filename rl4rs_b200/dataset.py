@@ -10,8 +10,9 @@ the env is replayed with the LOGGED policy (``env.offline_action``), and every e
 Episodes are shuffled with ``np.random.permutation`` and flattened exactly like the reference.
 
 What differs: the rollout and its buffers stay on the GPU (``output_format='torch'``); one device-to-host copy at
-the end.  d3rlpy / h5py are not available offline, so the result is returned as arrays and saved as ``.npz``
-(keys observations, actions, rewards, terminals, discrete_action) instead of ``MDPDataset.dump``.
+the end.  The result is returned as arrays and saved as ``.npz`` (keys observations, actions, rewards, terminals,
+discrete_action), or -- for a ``*.h5`` path, when h5py is importable (it is not in this image) -- in the layout
+``MDPDataset.dump`` writes.
 """
 import numpy as np
 import torch
@@ -64,8 +65,33 @@ def _generate(config, seq, conti, datasetfile, epochs, total):
         "discrete_action": np.asarray(not conti),
     }
     if datasetfile:
-        np.savez(datasetfile, **out)
+        save_dataset(datasetfile, out)
     return out
+
+
+def save_dataset(datasetfile, out):
+    """``*.h5`` -> the file ``d3rlpy.dataset.MDPDataset.dump`` writes (batchrl_trainer.py:214-217: datasets observations,
+    actions, rewards, terminals, episode_terminals, discrete_action, version), so ``MDPDataset.load`` reads it back; needs
+    h5py, which this image does not have.  Anything else -> ``.npz`` with the same arrays."""
+    if str(datasetfile).endswith((".h5", ".hdf5")):
+        try:
+            import h5py
+        except ImportError as exc:                      # pragma: no cover - h5py is absent offline
+            raise ImportError("writing %s needs h5py; pass a .npz path to get the same arrays without it" % datasetfile) from exc
+        discrete = bool(out["discrete_action"])
+        acts = out["actions"].reshape(-1).astype(np.int32) if discrete else out["actions"]
+        with h5py.File(datasetfile, "w") as f:        # pragma: no cover
+            f.create_dataset("observations", data=out["observations"])
+            f.create_dataset("actions", data=acts)
+            f.create_dataset("rewards", data=out["rewards"])
+            f.create_dataset("terminals", data=out["terminals"])
+            f.create_dataset("episode_terminals", data=out["terminals"])
+            f.create_dataset("discrete_action", data=discrete)
+            f.create_dataset("version", data="1.0")
+            f.flush()
+        return datasetfile
+    np.savez(datasetfile, **out)
+    return datasetfile
 
 
 def data_generate_rl4rs_a(config, datasetfile=None, epochs=None):

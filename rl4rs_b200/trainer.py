@@ -25,7 +25,7 @@ import ctypes as C
 import torch
 import torch.distributed as dist
 
-from .policy import MaskedPolicy
+from .policy import MaskedPolicy, RawStatePolicy
 
 
 def _p(t, byte_offset=0):
@@ -178,9 +178,9 @@ def _world():
 class RolloutBuffer(object):
     """[T, B, ...] device-resident sample batch of one vector episode."""
 
-    def __init__(self, T, B, A, device):
+    def __init__(self, T, B, A, device, obs_dim=256):
         z = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=device)
-        self.obs, self.mask = z(T, B, 256), z(T, B, A, dt=torch.uint8)
+        self.obs, self.mask = z(T, B, obs_dim), z(T, B, A, dt=torch.uint8)
         self.action, self.logp, self.value = z(T, B, dt=torch.int64), z(T, B), z(T, B)
         self.logits, self.reward = z(T, B, A), z(T, B)
         self.T, self.B = T, B
@@ -210,8 +210,14 @@ class _TrainerBase(object):
         self.B = env.config["batch_size"]
         self.A = env.config["action_size"]
         self.device = torch.device(device) if device is not None else env.sim.engine.device
-        self.policy = MaskedPolicy(self.A, self.device, seed=seed)     # same init on every rank
-        self.use_kernels = self.device.type == "cuda" and (config or {}).get("use_kernels", True)
+        # `*_rawstate` algorithms / rawstate_as_obs (modelfree_train.py:218,235-240,270,287-298): the policy embeds the raw
+        # state itself ('mask_model_rawstate'); that twin is plain torch + autograd, the kernels serve the 256-d obs policy
+        self.rawstate = bool(env.config.get("rawstate_as_obs", False))
+        if self.rawstate:
+            self.policy = RawStatePolicy(self.A, self.device, seed=seed, config=env.config)
+        else:
+            self.policy = MaskedPolicy(self.A, self.device, seed=seed)     # same init on every rank
+        self.use_kernels = self.device.type == "cuda" and (config or {}).get("use_kernels", True) and not self.rawstate
         self.opt = torch.optim.Adam([self.policy.flat], lr=self.config["lr"])
         self.ops = KernelOps(self.A, self.device, self.policy.n_params) if self.use_kernels else None
         self.comm = PeerComm(self.policy.n_params, self.device) if self.use_kernels else None
@@ -222,7 +228,7 @@ class _TrainerBase(object):
         self._seed = (seed * 1000003 + rank) & 0x7fffffffffffffff
         if rank and not self.use_kernels:
             torch.manual_seed(seed * 1000003 + rank)
-        self.buf = RolloutBuffer(self.T, self.B, self.A, self.device)
+        self.buf = RolloutBuffer(self.T, self.B, self.A, self.device, obs_dim=self.policy.obs_dim if self.rawstate else 256)
         self.iteration = 0
         self.timesteps_total = 0
 
@@ -232,14 +238,14 @@ class _TrainerBase(object):
         env, buf = self.env, self.buf
         obs = env.reset()
         for t in range(self.T):
-            buf.obs[t].copy_(obs["obs"]); buf.mask[t].copy_(obs["action_mask"])
+            buf.obs[t].copy_(self.policy.pack(obs) if self.rawstate else obs["obs"]); buf.mask[t].copy_(obs["action_mask"])
             if self.use_kernels:       # forward + sampling in ONE kernel, written straight into the rollout buffers
                 a = self._act_i32
                 self.ops.act(self.policy.flat, buf.obs[t], buf.mask[t], explore, self._seed, a,
                              buf.logp[t], buf.value[t], buf.logits[t])
                 buf.action[t].copy_(a)
             else:
-                a, logp, value, logits = self.policy.act(obs["obs"], obs["action_mask"], explore=explore)
+                a, logp, value, logits = self.policy.act(buf.obs[t], obs["action_mask"], explore=explore)
                 buf.action[t].copy_(a); buf.logp[t].copy_(logp); buf.value[t].copy_(value); buf.logits[t].copy_(logits)
             obs, reward, done, info = env.step(a)
             buf.reward[t].copy_(reward)
@@ -294,13 +300,15 @@ class _TrainerBase(object):
         """trainer.compute_actions (modelfree_train.py:454): obs = {'obs': [n,256], 'action_mask': [n,A]}
         (arrays or tensors) or RLlib's {i: {'obs':..,'action_mask':..}} dict."""
         import numpy as np
-        if isinstance(obs, dict) and "obs" not in obs:
+        if isinstance(obs, dict) and "action_mask" not in obs:      # RLlib's {env_id: observation} form
             keys = list(obs.keys())
-            o = np.stack([np.asarray(obs[k]["obs"]) for k in keys])
-            m = np.stack([np.asarray(obs[k]["action_mask"]) for k in keys])
-            a = self.compute_actions({"obs": o, "action_mask": m}, explore)
+            fields = [f for f in obs[keys[0]]]
+            a = self.compute_actions({f: np.stack([np.asarray(obs[k][f]) for k in keys]) for f in fields}, explore)
             return dict(zip(keys, a.tolist()))
-        o = torch.as_tensor(obs["obs"], dtype=torch.float32, device=self.device).contiguous()
+        if self.rawstate:
+            o = self.policy.pack({k: torch.as_tensor(obs[k], device=self.device) for k in ("category_feature", "dense_feature", "sequence_feature")})
+        else:
+            o = torch.as_tensor(obs["obs"], dtype=torch.float32, device=self.device).contiguous()
         m = torch.as_tensor(obs["action_mask"], device=self.device)
         if self.use_kernels:
             n = o.shape[0]
@@ -515,9 +523,10 @@ class A2CTrainer(_TrainerBase):
 
 def get_rl_model(algo, rllib_config, env=None, **kw):
     """script/modelfree_trainer.py:11-36.  Only the algorithms of the BASELINE configs are built."""
-    if algo == "PPO":
+    if algo in ("PPO", "PPO_rawstate"):        # '*_rawstate' = the same trainer on an env built with rawstate_as_obs (modelfree_train.py:55-56)
         return PPOTrainer(rllib_config, env, **kw)
-    if algo == "A2C":
+    if algo in ("A2C", "A2C_rawstate"):
         return A2CTrainer(rllib_config, env, **kw)
+    algo = algo.replace("_rawstate", "")
     assert algo in ("PPO", "DQN", "A2C", "A3C", "PG", "IMPALA", "TD3", "RAINBOW", "SLATEQ", "DDPG")
     raise NotImplementedError("%s is outside the hot-path scope (SURVEY.md section 2, row 11)" % algo)

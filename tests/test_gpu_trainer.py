@@ -29,6 +29,29 @@ def test_trainer_runs_on_cuda_env(algo, seq):
     assert torch.isfinite(tr.policy.flat).all()
 
 
+def test_rawstate_trainer_runs_on_cuda_env():
+    """PPO_rawstate (modelfree_train.py:55-56,235-240): the env hands out the raw state (rawstate_as_obs + rllib mask) and the
+    policy embeds it itself; the rollout stays on the device, the learner is the torch twin."""
+    import torch
+    from test_gpu_parity import _synthetic, make_env
+    from rl4rs_b200.trainer import get_rl_model
+    B = 64
+    cfg, cat, log, w = _synthetic(B, False, support_rllib_mask=True, rawstate_as_obs=True, is_eval=False, cache_size=4 * B)
+    env = make_env(cfg, False, cat, log, w, output_format="torch")
+    tr = get_rl_model("PPO_rawstate", {"sgd_minibatch_size": 64, "num_sgd_iter": 2}, env=env)
+    assert tr.rawstate and tr.buf.obs.shape == (cfg["max_steps"], B, 21 + 432 + 128)
+    r = [tr.train() for _ in range(2)]
+    assert all(np.isfinite(x["total_loss"]) and np.isfinite(x["episode_reward_mean"]) for x in r)
+    assert r[-1]["episode_reward_mean"] > 0
+    buf = tr.buf
+    assert bool((buf.mask.gather(2, buf.action.unsqueeze(-1)) == 1).all())
+    # the packed observation is the env's raw state: category ids of the first step = the log rows' user ids
+    o = env.reset()
+    packed = tr.policy.pack(o)
+    assert torch.equal(packed[:, :21].long(), o["category_feature"].long()) and torch.equal(packed[:, 21 + 432:].long(), o["sequence_feature"].reshape(B, -1).long())
+    assert torch.isfinite(tr.policy.flat).all()
+
+
 def _random_batch(n, A, dev, seed=0):
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)

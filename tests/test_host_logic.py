@@ -196,3 +196,23 @@ def test_ingest_matches_the_reference_preprocessing_fixture():
     assert log.n == 6 and log.items.shape == (6, 36) and log.feedback.shape == (6, 36) and log.lines == traj
     first = [int(x) for p in g["pages"][1:5] for x in p.split("@")[3].split(",")]
     np.testing.assert_array_equal(log.items[0], first)
+
+
+def test_dataset_h5_writer_is_gated_on_h5py(tmp_path):
+    """n2: `*.h5` targets need h5py (absent offline) -> a clear ImportError; with h5py the file has MDPDataset.dump's datasets."""
+    from rl4rs_b200.dataset import save_dataset
+    out = {"observations": np.zeros((20, 266), np.float32), "actions": np.arange(20, dtype=np.float32).reshape(20, 1),
+           "rewards": np.zeros(20, np.float32), "terminals": (np.arange(20) % 10 == 9).astype(np.float32),
+           "discrete_action": np.asarray(True)}
+    try:
+        import h5py
+    except ImportError:
+        with pytest.raises(ImportError, match="h5py"):
+            save_dataset(str(tmp_path / "d.h5"), out)
+    else:
+        save_dataset(str(tmp_path / "d.h5"), out)
+        with h5py.File(str(tmp_path / "d.h5"), "r") as f:
+            assert set(f.keys()) == {"observations", "actions", "rewards", "terminals", "episode_terminals", "discrete_action", "version"}
+            assert f["actions"].dtype == np.int32 and f["actions"].shape == (20,)
+    p = save_dataset(str(tmp_path / "d.npz"), out)
+    assert set(np.load(p).keys()) == set(out)

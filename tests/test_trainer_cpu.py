@@ -166,3 +166,58 @@ def test_world_size_2_minibatch_is_the_total_over_ranks():
     assert step.max() > 1e-4
     assert (diff <= 2e-6).float().mean() > 0.99, float((diff <= 2e-6).float().mean())
     assert abs(r0["stats"]["total_loss"] - st["total_loss"]) <= 1e-4 * max(1.0, abs(st["total_loss"]))
+
+
+class FakeRawEnv(FakeEnv):
+    """rawstate_as_obs protocol (slate.py:246-253): the observation is the raw state dict + the action mask; the reward
+    depends on a category id of the state, so only a policy that reads (and embeds) the raw ids can learn it."""
+
+    HASH = 300
+
+    def __init__(self, B, T=9, seed=0):
+        super().__init__(B, T, seed)
+        self.config.update({"rawstate_as_obs": True, "category_hash_size": self.HASH})
+        self.uid = 7 + torch.randint(0, 2, (B,), generator=self.g)    # two kinds of users: ids 7 and 8
+
+    def _obs(self):
+        o = super()._obs()
+        cat = self.uid[:, None].repeat(1, 21)             # every category slot carries the user id: an undiluted signal
+        return {"category_feature": cat, "dense_feature": 0.1 * torch.randn(self.B, 432, generator=self.g),
+                "sequence_feature": torch.zeros(self.B, 2, 64, dtype=torch.int64), "action_mask": o["action_mask"]}
+
+    def step(self, a):
+        # reward 1 per step whose action parity matches the user id's parity
+        self.acc += ((a.to(torch.int64) % 2) == (self.uid % 2)).to(torch.float64)
+        self.t += 1
+        done = self.t >= self.T
+        r = self.acc.clone() if done else torch.zeros(self.B, dtype=torch.float64)
+        return self._obs(), r, torch.full((self.B,), int(done)), {}
+
+
+def test_rawstate_policy_matches_layer_definitions_and_learns():
+    from rl4rs_b200.policy import RawStatePolicy
+    env = FakeRawEnv(96)
+    pol = RawStatePolicy(A, "cpu", seed=2, config=env.config)
+    assert pol.obs_dim == 21 + 432 + 128
+    o = env.reset()
+    packed = pol.pack(o)
+    logits, value = pol.forward(packed, o["action_mask"])
+    # the same graph written from the reference's layer list (rllib_rawstate_model.py:50-56, nets/utils.py:7-14,48-54,56-77)
+    p = pol.params()
+    elu = torch.nn.functional.elu
+    c = p["emb_cat"][o["category_feature"]].mean(1)
+    d = elu(elu(o["dense_feature"] @ p["dw1"] + p["db1"]) @ p["dw2"] + p["db2"])
+    sq = torch.cat([p["emb_seq"][o["sequence_feature"][:, i]].mean(1) for i in range(2)], 1)
+    ctx = elu(torch.cat([sq, d, c], 1) @ p["wc"] + p["bc"])
+    ref = ctx @ p["w2"] + p["b2"]
+    m = o["action_mask"].bool()
+    assert torch.allclose(logits[m], ref[m], atol=1e-6) and (logits[~m] < -1e30).all()
+    assert torch.allclose(value, (ctx @ p["wv"] + p["bv"]).squeeze(-1), atol=1e-6)
+    tr = get_rl_model("PPO_rawstate", {"lr": 1e-3, "sgd_minibatch_size": 96, "num_sgd_iter": 6}, env=env, seed=3)
+    assert tr.rawstate and not tr.use_kernels and tr.buf.obs.shape[-1] == 581
+    first = tr.train()["episode_reward_mean"]
+    for _ in range(24):
+        last = tr.train()["episode_reward_mean"]
+    assert last > first + 0.5, (first, last)        # chance level is 4.5 of 9
+    acts = tr.compute_actions({k: v.numpy() for k, v in env.reset().items()})
+    assert acts.shape == (96,)
