@@ -415,8 +415,8 @@ def main():
         if os.path.exists(tp):
             tj = json.load(open(tp))
             traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
-        roofline = {"kernel": "AUGRU recurrence, tcgen05.mma kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators: k_augru_pair2 "
-                              "(cta_group::2) / k_augru_tc, chosen per launch by r4_augru_kernel_for",
+        roofline = {"kernel": "AUGRU recurrence, tcgen05.mma.cta_group::2 kind::f16, bf16 hi/lo split x3, fp32 TMEM accumulators: k_augru_pair2 "
+                              "(one recurrence per CTA pair) / k_augru_pp (two per pair), chosen per launch by r4_augru_kernel_for",
                     "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                     "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": traffic_src or "profiles/augru_traffic.json (ncu --set full capture of an observation-pass launch, committed; not re-measured in this run)",

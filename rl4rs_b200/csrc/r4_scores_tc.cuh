@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
   __shared__ __align__(16) float W2_s[S_N * 16];
   __shared__ float b2_s[16], kv_s[16];
   __shared__ __align__(16) float qa_s[2][2 * S_N];      // q (Wq+Wd) + b1 of the tile's two feature rows, double buffered
+  __shared__ __align__(16) float q_s[2][2 * S_K];       // the two query rows themselves (producers), double buffered
   const ScoreTcSeq& S = p.s[blockIdx.y];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ntiles = (p.R + 1) / 2;
@@ -182,26 +183,43 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
     }
   } else if (warp < S_PROD_WARPS) {
     // ===== producers: A = q * H as bf16 hi/lo; thread = (row slot tid / 4 of 64, K chunk tid % 4), 2 row passes =====
+    // All 16 H loads of a thread and tile (4 K blocks x 2 row passes x 32 B) are issued before the first one is used, and
+    // q comes from shared memory: ncu (round 2, second capture) had the producers waiting on two dependent HBM round trips
+    // per tile (the cached H of a 4096-row pass is 134 MB, it streams from HBM) with the epilogue warps waiting for them.
     const int kc = tid & 3;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int s = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&bar_aempty[s], ph ^ 1);          // MMA finished reading this A stage
-      uint8_t* a = sA + s * S_A_STAGE;
-#pragma unroll 2
+      if (tid < 64) {                              // the tile's two query rows: 2 x 128 floats
+        const int r = min(tile * 2 + (tid >> 5), p.R - 1);
+        reinterpret_cast<float4*>(q_s[s])[tid] = __ldg(reinterpret_cast<const float4*>(p.q + (size_t)r * S_K) + (tid & 31));
+      }
+      float4 hv[S_K / 32][2][2];
+#pragma unroll
       for (int kb = 0; kb < S_K / 32; ++kb) {
 #pragma unroll
         for (int i2 = 0; i2 < 2; ++i2) {
           const int m = i2 * 64 + (tid >> 2);          // tile row: feature row m/64, key m%64
-          const int rr = m >> 6, key = m & 63;
-          int r = min(tile * 2 + rr, p.R - 1);
+          const int r = min(tile * 2 + (m >> 6), p.R - 1);
           const size_t ci = S.shared ? 0 : (size_t)((p.row0 + r) / p.div);
+          const float* hp = S.H + (ci * S_KEYS + (m & 63)) * S_K + kb * 32 + kc * 8;
+          hv[kb][i2][0] = __ldg(reinterpret_cast<const float4*>(hp));
+          hv[kb][i2][1] = __ldg(reinterpret_cast<const float4*>(hp + 4));
+        }
+      }
+      named_bar_sync(3, S_PROD_WARPS * 32);        // q_s[s] is complete; it is rewritten two tiles later
+      mbar_wait(&bar_aempty[s], ph ^ 1);          // MMA finished reading this A stage
+      uint8_t* a = sA + s * S_A_STAGE;
+#pragma unroll
+      for (int kb = 0; kb < S_K / 32; ++kb) {
+#pragma unroll
+        for (int i2 = 0; i2 < 2; ++i2) {
+          const int m = i2 * 64 + (tid >> 2);
           const int k = kb * 32 + kc * 8;
-          const float* hp = S.H + (ci * S_KEYS + key) * S_K + k;
-          float4 h0 = __ldg(reinterpret_cast<const float4*>(hp)), h1 = __ldg(reinterpret_cast<const float4*>(hp + 4));
-          const float* qp = p.q + (size_t)r * S_K + k;
-          float4 q0 = __ldg(reinterpret_cast<const float4*>(qp)), q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+          const float4 q0 = *reinterpret_cast<const float4*>(q_s[s] + (m >> 6) * S_K + k);
+          const float4 q1 = *reinterpret_cast<const float4*>(q_s[s] + (m >> 6) * S_K + k + 4);
+          const float4 h0 = hv[kb][i2][0], h1 = hv[kb][i2][1];
           float v[8] = {h0.x * q0.x, h0.y * q0.y, h0.z * q0.z, h0.w * q0.w,
                         h1.x * q1.x, h1.y * q1.y, h1.z * q1.z, h1.w * q1.w};
           uint4 hi, lo;
