@@ -24,7 +24,7 @@ JSON keys beyond the base contract:
   env_only  the same rollout without the learner pass.
   e2e       the reference-facing call with HOST buffers: README.md:14-21 loop, numpy actions in,
             numpy obs/mask/reward out, every copy inside the timed region.
-  roofline  the dominant kernel: the tcgen05 AUGRU recurrence (k_augru_pair2 / k_augru_tc, one profile slot), timed
+  roofline  the dominant kernel: the tcgen05 AUGRU recurrence (k_augru_pair2 / k_augru_pp, one profile slot), timed
             live with CUDA events on the launching stream during the `value` loop; FLOPs = rows x 2 seq x 64 steps x
             2*(256*512 + 256*256) against the measured sustained bf16 GEMM peak.
   hbm_8d    SURVEY.md section 8(d)'s own HBM figure: transitions/s x algorithmic bytes per transition

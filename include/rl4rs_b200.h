@@ -163,19 +163,20 @@ int r4_profile_read(r4_env* env, int slot, const char** name, double* ms, int64_
 /* ABI version of the build */
 int r4_abi_version(void);
 /* Which AUGRU kernel an observation / reward pass of `ctas` = 2 x ceil(rows / 128) tile-sequences runs on a device
- * with `sms` multiprocessors: 1 = k_augru_tc (one CTA per tile), 2 = k_augru_pair (2-CTA tcgen05.mma.cta_group::2).
- * Pure host arithmetic, exposed so the choice is testable and so a caller can predict the rounding regime of a launch
- * (the two kernels agree to the parity tolerance, not bit for bit).  No reference counterpart. */
+ * with `sms` multiprocessors: 2 = k_augru_pair2 (one recurrence per 2-CTA cluster, tcgen05.mma.cta_group::2),
+ * 3 = k_augru_pp (both sequences of a tile per cluster); 0 for bad arguments.  Pure host arithmetic, exposed so the
+ * choice is testable and so a caller can predict the rounding regime of a launch (the two kernels agree to the parity
+ * tolerance, not bit for bit).  No reference counterpart. */
 int r4_augru_kernel_for(int ctas, int sms);
 /* Process-wide kernel-choice overrides for parity tests and A/B timing (no reference counterpart):
- *   "augru_kernel"     0 = by r4_augru_kernel_for (default), 1 = always k_augru_tc, 2 = always the 2-CTA pair kernel,
- *                      3 = always the ping-pong pair kernel (two recurrences per pair)
+ *   "augru_kernel"     0 = by r4_augru_kernel_for (default), 2 = always the pair kernel, 3 = always the ping-pong pair kernel
+ *                      (two recurrences per pair)
  *   "augru_pair_impl"  hand-over / weight-ring variant of the pair kernels, <RELAY, TMAP>: 1 = <0,0> (default: direct
  *                      release.cta arrive, per-CTA bulk-copy ring), 2 = <0,1> (tensor-map ring), 3 = <1,0> (relayed
  *                      release.cluster hand-over), 4 = <1,1>
- *   "augru_cost_single" / "augru_cost_pair" / "augru_cost_pp"  the per-wave costs r4_augru_kernel_for compares (positive ints)
+ *   "augru_cost_pair" / "augru_cost_pp"  the per-wave costs r4_augru_kernel_for compares (positive ints)
  *   "augru_cluster"    CTAs per cluster of the pair kernel: 2 (one pair), 4 or 8 (2 / 4 pairs share one multicast weight stream)
- * The environment variables R4_AUGRU_SINGLE / R4_AUGRU_PAIR / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE give the initial
+ * The environment variables R4_AUGRU_PAIR / R4_AUGRU_PP / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE give the initial
  * values.  Returns 0, or R4_ERR_ARG for an unknown key / out-of-range value. */
 int r4_set_option(const char* key, int value);
 

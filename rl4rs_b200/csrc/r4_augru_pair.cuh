@@ -2,7 +2,7 @@
 // Design notes of the first generation, kept because the layout facts still hold:
 // the AUGRU recurrence (deepctr VecAttGRUCell, nets/utils.py:123-124) as ONE tensor-core
 // instruction stream per 2-CTA cluster: tcgen05.mma.cta_group::2, M = 128 (64 feature rows per CTA), N = 256,
-// bf16 hi/lo operands, fp32 accumulators in both CTAs' TMEM.  Same arithmetic as k_augru_tc (r4_augru_tc.cuh):
+// bf16 hi/lo operands, fp32 accumulators in both CTAs' TMEM.  The arithmetic (r4_augru_tc.cuh):
 //     r = sigmoid(Xr_t + h Wr)      u = sigmoid(Xu_t + h Wu)      c = tanh(Xc_t + (r*h) Wc)
 //     u' = (1 - score_t) u ;  h <- u' h + (1 - u') c              (3 bf16 products per fp32 product)
 // What the pair buys (measured with tools/pair_probe.cu): a 128x256x16 MMA takes 64 cycles instead of 128,

@@ -1,11 +1,9 @@
-// r4_augru_tc.cuh -- the AUGRU recurrence (deepctr VecAttGRUCell, nets/utils.py:123-124) on the
-// 5th-generation tensor cores: tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM),
-// weights streamed by 1-D TMA (cp.async.bulk) into a shared-memory ring, gate math in epilogue warps.
+// r4_augru_tc.cuh -- common ground of the tcgen05 recurrence kernels (AUGRU pair / ping-pong kernels, GRU-1, attention
+// scores, GEMM): constants of the AUGRU problem, the PTX wrappers (mbarrier, bulk copy, tcgen05.mma / ld / st / commit,
+// descriptors), the bf16 hi/lo split, the quad-layout input loads and the parameter structs of the AUGRU kernels.
 //
-// One CTA = 128 feature rows x 64 steps of one sequence.  Per step, with h the 256-wide state:
-//     u = sigmoid(Xu_t + h Wu)         D[:,256:512]   (tensor core, K = 256)
-//     r = sigmoid(Xr_t + h Wr)         D[:,  0:256]
-//     c = tanh   (Xc_t + (r*h) Wc)     D[:,  0:256]   (after r has been consumed)
+// The AUGRU recurrence (deepctr VecAttGRUCell, nets/utils.py:123-124), per step, with h the 256-wide state:
+//     u = sigmoid(Xu_t + h Wu)      r = sigmoid(Xr_t + h Wr)      c = tanh(Xc_t + (r*h) Wc)
 //     u' = (1 - score_t) u ;  h <- u' h + (1 - u') c
 // fp32 parity on a bf16 tensor pipe: every fp32 operand x is split x = hi + lo (both bf16, lo =
 // bf16(x - hi)) and each product is issued as hi*hi + lo*hi + hi*lo (3 MMAs, fp32 accumulate):
@@ -13,12 +11,9 @@
 // f64 (tools/split_sim.py) -- inside the 1e-4 parity bound.  The state h itself stays fp32 in the
 // epilogue threads' registers; only the MMA operand copies are rounded.
 //
-// Shared memory (216 KB): A operand = h (then r*h) as bf16 hi + lo, SWIZZLE_NONE K-major core
-// matrices (8 rows x 16 B), 2 x 64 KB; B ring = 5 stages x 16 KB (one 32-wide K block of one
-// weight split, pre-tiled on the host in exactly this layout so a stage is ONE contiguous bulk
-// copy); mbarriers.  TMEM: 512 columns (r|c in 0..255, u in 256..511).
-// Warp roles: 0-7 epilogue (thread = row x column half), 8 MMA issuer (one elected lane), 9 TMA producer,
-// 10-11 idle (they complete the control warpgroup so setmaxnreg can move registers to the epilogue).
+// The kernels: r4_augru_pair2.cuh (one recurrence per CTA pair) and r4_augru_pp.cuh (two per pair).  The round-1 kernel
+// that lived here (k_augru_tc: one CTA per 128-row tile-sequence, 36.7 k cycles per step against 15.5 k / 14.3 k) lost
+// every regime to them and was deleted at the end of round 2.
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
@@ -33,16 +28,13 @@ constexpr int HID = 256;                // AUGRU hidden = GEMM N and K
 constexpr int STEPS = 64;
 constexpr int KB = 32;                  // K elements per B stage
 constexpr int NKB = HID / KB;           // 8 K blocks per matrix
-constexpr int NST = 5;                  // B ring stages
 constexpr int STAGE_BYTES = HID * KB * 2;            // 16384
 constexpr int A_BYTES = TM * HID * 2;                // 65536 per split
 constexpr int LBO = 128;                             // K-adjacent core matrices
 constexpr int A_SBO = (HID / 8) * 128;               // 4096: 8-row groups of the A operand
 constexpr int B_SBO = (KB / 8) * 128;                // 512:  8-row groups inside a B stage
-constexpr int STAGES_PER_STEP = 3 * NKB * 2;         // u, r, c  x  8 K blocks  x  (hi, lo) = 48
-constexpr int W_IMAGE_BYTES = STAGES_PER_STEP * STAGE_BYTES;   // 786432 per sequence
+constexpr int W_IMAGE_BYTES = 3 * NKB * 2 * STAGE_BYTES;   // 786432 per sequence: r, u, c x 8 K blocks x (hi, lo)
 constexpr int XT_COLS = 3 * HID;                     // transposed input halves: [r | u | c] rows of 128 lanes
-constexpr int SMEM_BYTES = 2 * A_BYTES + NST * STAGE_BYTES + 1024;
 constexpr int NTHREADS = 384;               // 8 epilogue warps + one control warpgroup (MMA, TMA, 2 idle)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -147,7 +139,7 @@ __device__ __forceinline__ void load_x16(float* dst, const float* ts, int colbas
 
 struct AugruTcSeq {
   const float* XT;        // transposed input halves [n_tiles_cached, 64, 768 / 4, 128, 4]  (tile, step, column quad, lane, column % 4)
-  const uint8_t* Wimg;    // pre-tiled bf16 hi/lo weight image, W_IMAGE_BYTES, stream order u, r, c
+  const uint8_t* Wimg;    // pre-tiled bf16 hi/lo weight image of the pair kernels (r4_augru_pair.cuh: build_pair_image)
   const float* scoresT;   // [n_row_tiles, 64, 128]
   float* out;             // final state, row stride out_ld
   int shared;             // 1: every row reads cached sequence 0
@@ -158,263 +150,11 @@ struct AugruTcParams {
   long long* dbg;         // optional: per-step phase timestamps of CTA 0 (development probe), else null
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) k_augru_tc(AugruTcParams p) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sAhi = smem;
-  uint8_t* sAlo = smem + A_BYTES;
-  uint8_t* sB = smem + 2 * A_BYTES;
-  __shared__ uint64_t bar_full[NST], bar_empty[NST], bar_h, bar_u, bar_r, bar_rh, bar_c;
-  __shared__ uint32_t tmem_base_s;
-  const AugruTcSeq& S = p.s[blockIdx.y];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TM;
-
-  if (tid == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-    mbar_init(&bar_h, 256); mbar_init(&bar_rh, 256);
-    mbar_init(&bar_u, 1); mbar_init(&bar_r, 1); mbar_init(&bar_c, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 8) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = tmem_base_s;
-
-  // Register budget: an SMSP hosts 2 epilogue warps + 1 control warp (16384 regs): 2*232 + 40 fits.
-  if (warp >= 8) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-  if (warp == 9) {
-    // ===== TMA producer: the 48-stage weight stream of a step, repeated 64 times =====
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = 0; t < STEPS; ++t) {
-        const uint8_t* src = S.Wimg;
-        for (int i = 0; i < STAGES_PER_STEP; ++i, src += STAGE_BYTES) {
-          mbar_wait(&bar_empty[stage], phase ^ 1);
-          mbar_expect_tx(&bar_full[stage], STAGE_BYTES);
-          bulk_g2s(sB + stage * STAGE_BYTES, src, STAGE_BYTES, &bar_full[stage]);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 8) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TM, HID);
-      const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), bBase = smem_u32(sB);
-      int stage = 0; uint32_t phase = 0;
-      auto gemm = [&](uint32_t dcol) {
-        for (int kb = 0; kb < NKB; ++kb) {
-          // hi split of this K block: A_hi*B_hi + A_lo*B_hi
-          mbar_wait(&bar_full[stage], phase);
-          tc_fence_after();
-          {
-            uint32_t b = bBase + stage * STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < KB / 16; ++j) {
-              uint64_t db = make_desc(b + j * 2 * LBO, LBO, B_SBO);
-              uint32_t koff = (kb * (KB / 16) + j) * 2 * LBO;
-              mma_bf16(tbase + dcol, make_desc(aHi + koff, LBO, A_SBO), db, idesc, (kb | j) ? 1u : 0u);
-              mma_bf16(tbase + dcol, make_desc(aLo + koff, LBO, A_SBO), db, idesc, 1u);
-            }
-          }
-          umma_commit(&bar_empty[stage]);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-          // lo split: A_hi*B_lo
-          mbar_wait(&bar_full[stage], phase);
-          tc_fence_after();
-          {
-            uint32_t b = bBase + stage * STAGE_BYTES;
-#pragma unroll
-            for (int j = 0; j < KB / 16; ++j) {
-              uint64_t db = make_desc(b + j * 2 * LBO, LBO, B_SBO);
-              uint32_t koff = (kb * (KB / 16) + j) * 2 * LBO;
-              mma_bf16(tbase + dcol, make_desc(aHi + koff, LBO, A_SBO), db, idesc, 1u);
-            }
-          }
-          umma_commit(&bar_empty[stage]);
-          if (++stage == NST) { stage = 0; phase ^= 1; }
-        }
-      };
-      for (int t = 0; t < STEPS; ++t) {
-        uint32_t par = t & 1;
-        mbar_wait(&bar_h, par);          // h (hi/lo) of this step is in shared memory
-        tc_fence_after();
-        gemm(HID);                       // u
-        umma_commit(&bar_u);
-        gemm(0);                         // r
-        umma_commit(&bar_r);
-        mbar_wait(&bar_rh, par);         // r*h written, r accumulators consumed
-        tc_fence_after();
-        gemm(0);                         // c
-        umma_commit(&bar_c);
-      }
-    }
-  }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ===== epilogue warps: thread = (row, column half) =====
-    const int q = warp & 3, half = warp >> 2;
-    const int row = q * 32 + lane;
-    const int c0 = half * 128;
-    int r = m0 + row;
-    const bool valid = r < p.R;
-    if (!valid) r = p.R - 1;
-    const int ci = S.shared ? 0 : (p.row0 + r) / p.div;
-    const float* xt = S.XT + ((size_t)(ci / TM) * STEPS) * XT_COLS * TM;
-    const int ln4 = (ci % TM) * 4;
-    const float* st = S.scoresT + ((size_t)((m0 + row) / TM) * STEPS) * TM + row;   // this CTA's tile
-    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const uint32_t a_row_off = (uint32_t)(row / 8) * A_SBO + (uint32_t)(row % 8) * 16;
-    float h[128];
-#pragma unroll
-    for (int i = 0; i < 128; ++i) h[i] = 0.f;
-    // h0 = 0 into the A operand
-#pragma unroll
-    for (int g = 0; g < 16; ++g) {
-      uint32_t off = a_row_off + (uint32_t)((c0 + g * 8) / 8) * LBO;
-      *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(0, 0, 0, 0);
-    }
-    proxy_fence();
-    mbar_arrive(&bar_h);
-
-    for (int t = 0; t < STEPS; ++t) {
-      const uint32_t par = t & 1;
-      const float* xs = xt + (size_t)t * XT_COLS * TM;
-      const float one_minus_s = 1.0f - __ldg(st + (size_t)t * TM);
-      // Pull the NEXT step's input halves (768 columns x 128 lanes x 4 B = 3072 lines) from HBM into L2
-      // now: each thread touches 12 lines; the demand loads one step later then see L2 latency.
-      if (t + 1 < STEPS) {
-        const float* xn = S.XT + (((size_t)(ci / TM) * STEPS + (t + 1)) * XT_COLS) * TM;
-#pragma unroll
-        for (int i = 0; i < 12; ++i)
-          asm volatile("prefetch.global.L2 [%0];" :: "l"(xn + (size_t)(i * 256 + (tid & 255)) * 32));
-      }
-      // Each phase walks its 128 columns in 8 chunks of 16 with a 2-deep software pipeline: the TMEM
-      // load and the coalesced X loads of chunk ch+1 are in flight while chunk ch is computed.
-#define R4_LOADX(dst, colbase) load_x16(dst, xs, (colbase), ln4)
-      // ---- phase U: u' = (1 - s) sigmoid(acc_u + Xu) -> back into TMEM ----
-      {
-        float x[2][16], a[2][16];
-        R4_LOADX(x[0], HID + c0);
-        mbar_wait(&bar_u, par);
-        tc_fence_after();
-        tmem_ld16(tlane + HID + c0, a[0]);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int cur = ch & 1, nxt = cur ^ 1;
-          tmem_wait_ld();
-          if (ch < 7) { R4_LOADX(x[nxt], HID + c0 + (ch + 1) * 16); tmem_ld16(tlane + HID + c0 + (ch + 1) * 16, a[nxt]); }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) a[cur][j] = one_minus_s * fast_sigmoid(a[cur][j] + x[cur][j]);
-          tmem_st16(tlane + HID + c0 + ch * 16, a[cur]);
-        }
-        tmem_wait_st();
-      }
-      // ---- phase R: r*h -> A operand ----
-      {
-        float x[2][16], a[2][16];
-        R4_LOADX(x[0], c0);
-        mbar_wait(&bar_r, par);
-        tc_fence_after();
-        tmem_ld16(tlane + c0, a[0]);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int cur = ch & 1, nxt = cur ^ 1;
-          tmem_wait_ld();
-          if (ch < 7) { R4_LOADX(x[nxt], c0 + (ch + 1) * 16); tmem_ld16(tlane + c0 + (ch + 1) * 16, a[nxt]); }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) a[cur][j] = fast_sigmoid(a[cur][j] + x[cur][j]) * h[ch * 16 + j];
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 hi, lo;
-            split8(a[cur] + g * 8, hi, lo);
-            uint32_t off = a_row_off + (uint32_t)((c0 + ch * 16 + g * 8) / 8) * LBO;
-            *reinterpret_cast<uint4*>(sAhi + off) = hi;
-            *reinterpret_cast<uint4*>(sAlo + off) = lo;
-          }
-        }
-      }
-      tc_fence_before();
-      proxy_fence();
-      mbar_arrive(&bar_rh);
-      // ---- phase C: c = tanh(acc_c + Xc); h <- u' h + (1 - u') c -> A operand ----
-      {
-        float x[2][16], a[2][16], u[2][16];
-        R4_LOADX(x[0], 2 * HID + c0);
-        mbar_wait(&bar_c, par);
-        tc_fence_after();
-        tmem_ld16(tlane + c0, a[0]);
-        tmem_ld16(tlane + HID + c0, u[0]);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          const int cur = ch & 1, nxt = cur ^ 1;
-          tmem_wait_ld();
-          if (ch < 7) {
-            R4_LOADX(x[nxt], 2 * HID + c0 + (ch + 1) * 16);
-            tmem_ld16(tlane + c0 + (ch + 1) * 16, a[nxt]);
-            tmem_ld16(tlane + HID + c0 + (ch + 1) * 16, u[nxt]);
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float c = fast_tanh(a[cur][j] + x[cur][j]);
-            float hn = fmaf(u[cur][j], h[ch * 16 + j] - c, c);          // u' h + (1 - u') c
-            h[ch * 16 + j] = hn;
-            a[cur][j] = hn;
-          }
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 hi, lo;
-            split8(a[cur] + g * 8, hi, lo);
-            uint32_t off = a_row_off + (uint32_t)((c0 + ch * 16 + g * 8) / 8) * LBO;
-            *reinterpret_cast<uint4*>(sAhi + off) = hi;
-            *reinterpret_cast<uint4*>(sAlo + off) = lo;
-          }
-        }
-      }
-#undef R4_LOADX
-      tc_fence_before();
-      proxy_fence();
-      mbar_arrive(&bar_h);
-    }
-    if (valid) {
-      float* o = S.out + (size_t)(m0 + row) * p.out_ld + c0;
-#pragma unroll
-      for (int i = 0; i < 128; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(h[i], h[i + 1], h[i + 2], h[i + 3]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(512));
-}
-
-// host: fp32 recurrent weights -> the pre-tiled bf16 hi/lo stream image (order u, r, c; 8 K blocks; hi, lo).
-// Wg: [256][512] rows = h index, columns [r | u];  Wc: [256][256].
+// host-side bf16 rounding (round to nearest even) shared by the weight-image builders
 inline uint16_t host_bf16_bits(float x) {
   uint32_t u; memcpy(&u, &x, 4);
   if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)(u >> 16);
   u = (u + 0x7fffu + ((u >> 16) & 1u)) >> 16; return (uint16_t)u;
 }
 inline float host_bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
-inline void build_weight_image(const float* Wg, const float* Wc, uint8_t* img) {
-  for (int mat = 0; mat < 3; ++mat)
-    for (int kb = 0; kb < NKB; ++kb)
-      for (int sp = 0; sp < 2; ++sp) {
-        uint8_t* st = img + (size_t)((mat * NKB + kb) * 2 + sp) * STAGE_BYTES;
-        for (int n = 0; n < HID; ++n)
-          for (int kk = 0; kk < KB; ++kk) {
-            int k = kb * KB + kk;
-            float w = mat == 0 ? Wg[(size_t)k * 2 * HID + HID + n] : (mat == 1 ? Wg[(size_t)k * 2 * HID + n] : Wc[(size_t)k * HID + n]);
-            uint16_t hi = host_bf16_bits(w);
-            uint16_t v = sp == 0 ? hi : host_bf16_bits(w - host_bf16_val(hi));
-            memcpy(st + (n / 8) * B_SBO + (kk / 8) * LBO + (n % 8) * 16 + (kk % 8) * 2, &v, 2);
-          }
-      }
-}
-
 }  // namespace r4tc

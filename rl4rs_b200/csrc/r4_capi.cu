@@ -44,7 +44,6 @@ struct PerSeq {
   float *wqd = nullptr, *wp = nullptr, *ab1 = nullptr, *aw2 = nullptr, *ab2 = nullptr, *akv = nullptr;
   uint8_t *gru_wx_img = nullptr, *au_wx_img = nullptr, *wp_img = nullptr, *gru_img = nullptr;   // pre-tiled bf16 hi/lo images of the input projections
   uint8_t* au_pair_img = nullptr;   // the same weights tiled per CTA rank for the 2-CTA kernel (r4_augru_pair.cuh)
-  uint8_t* au_img = nullptr;   // pre-tiled bf16 hi/lo stream image of the recurrent AUGRU weights (r4_augru_tc.cuh)
   CUtensorMap au_pair_tmap;    // au_pair_img as a 2-D tensor of 1 KB rows (r4_augru_pair2.cuh: tensor-map TMA ring)
   bool au_pair_tmap_ok = false;
   float abk = 0.f;
@@ -124,7 +123,7 @@ int fail(r4_env* e, int code, const std::string& msg) {
 enum { SL_ACT = 0, SL_ASSEMBLE, SL_SEQIDS, SL_GEMM_XIN, SL_GRU1, SL_GEMM_XK, SL_SCORES, SL_AUGRU, SL_CAT,
        SL_GEMM_DENSE, SL_GEMM_HEAD, SL_RHEAD, SL_REWARD, SL_XT, SL_MISC, SL_COUNT };
 const char* const SLOT_NAMES[SL_COUNT] = {"k_act", "k_assemble", "k_seq_ids", "k_gemm_tc[gru1 input proj + E_s gather]",
-    "k_gru_tc[GRU-1 tcgen05]", "k_gemm_tc[augru/att input proj]", "k_scores_tc", "k_augru[AUGRU tcgen05: pair2 / pp / tc]", "k_cat_attn | k_cat_pool",
+    "k_gru_tc[GRU-1 tcgen05]", "k_gemm_tc[augru/att input proj]", "k_scores_tc", "k_augru[AUGRU tcgen05: pair2 / pp]", "k_cat_attn | k_cat_pool",
     "k_gemm_tc[dense tower]", "k_gemm_tc[head 3456x256]", "k_reward_head", "k_reward", "k_transpose_x", "k_query"};
 
 // Brackets one launch with CUDA events on the launching stream when profiling is on.
@@ -280,44 +279,39 @@ int build_cache(r4_env* e, int si, const int32_t* ids, int n, SeqCache& c, cudaS
 
 // Kernel-choice options (r4_set_option; the environment gives the initial values).
 struct AugruOpts {
-  int force = 0;          // 0 rule, 1 one-CTA kernel, 2 pair kernel (one recurrence per pair), 3 ping-pong pair kernel
+  int force = 0;          // 0 rule, 2 pair kernel (one recurrence per pair), 3 ping-pong pair kernel (1 was the deleted one-CTA kernel)
   int pair_impl = 1;      // k_augru_pair2<RELAY, TMAP>: 1 = <0,0> (default), 2 = <0,1>, 3 = <1,0>, 4 = <1,1>; k_augru_pp<RELAY> follows RELAY
-  // cost of one wave, measured (tools/augru_probe.cu, round 2, ms x 25): k_augru_tc 1.19 ms per 148 tile-sequences,
-  // k_augru_pair2 0.51 ms per 74, k_augru_pp 0.96 ms per 74 TILES (= 148 tile-sequences)
-  int cost_single = 30, cost_pair = 13, cost_pp = 24;
+  // cost of one wave, measured (tools/augru_probe.cu, round 2, ms x 25): k_augru_pair2 0.51 ms per 74 tile-sequences,
+  // k_augru_pp 0.96 ms per 74 TILES (= 148 tile-sequences)
+  int cost_pair = 13, cost_pp = 24;
   int cluster = 2;        // CTAs per cluster of the pair kernel: 2, or 4 / 8 = weight stream shared by 2 / 4 pairs (multicast)
   AugruOpts() {
-    if (getenv("R4_AUGRU_SINGLE")) force = 1; else if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
+    if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
     if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
     if (const char* e = getenv("R4_AUGRU_CLUSTER")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) cluster = v; }
     if (const char* e = getenv("R4_AUGRU_RULE")) {
-      int a = 0, b = 0, c = 0;
-      int n = sscanf(e, "%d,%d,%d", &a, &b, &c);
-      if (n >= 2 && a > 0 && b > 0) { cost_single = a; cost_pair = b; if (n == 3 && c > 0) cost_pp = c; }
+      int a = 0, b = 0;
+      if (sscanf(e, "%d,%d", &a, &b) == 2 && a > 0 && b > 0) { cost_pair = a; cost_pp = b; }
     }
   }
 };
 AugruOpts& augru_opts() { static AugruOpts o; return o; }
 
-// Which AUGRU kernel runs `ctas` = 2 x row tiles (tile-sequences) of work: 1 = k_augru_tc (one CTA per tile-sequence),
-// 2 = k_augru_pair2 (a CTA pair per tile-sequence), 3 = k_augru_pp (a CTA pair per TILE, both sequences in flight).
-// The pair kernels finish a tile sooner but occupy two SMs for it, the ping-pong kernel keeps the tensor pipe busier but
-// needs twice the tiles to fill the chip: compare wave counts x measured wave times.
+// Which AUGRU kernel runs `ctas` = 2 x row tiles (tile-sequences) of work: 2 = k_augru_pair2 (a CTA pair per tile-sequence),
+// 3 = k_augru_pp (a CTA pair per TILE, both sequences in flight).  The pair kernel finishes a tile sooner, the ping-pong
+// kernel keeps the tensor pipe busier but needs twice the tiles to fill the chip: compare wave counts x measured wave times.
 static int augru_rule(int ctas, int sms) {
   const AugruOpts& o = augru_opts();
   const int pairs = sms / 2;
-  const long c1 = (long)o.cost_single * ((ctas + sms - 1) / sms);
   const long c2 = (long)o.cost_pair * ((ctas + pairs - 1) / pairs);
   const long c3 = (long)o.cost_pp * (((ctas + 1) / 2 + pairs - 1) / pairs);
-  if (c3 <= c2 && c3 <= c1) return 3;
-  return c1 <= c2 ? 1 : 2;
+  return c3 <= c2 ? 3 : 2;
 }
 static int augru_choice(int ctas) {
   static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
   const int force = augru_opts().force;
   return force ? force : augru_rule(ctas, sms);
 }
-static bool augru_use_single(int ctas) { return augru_choice(ctas) == 1; }
 static int augru_pair_impl() { return augru_opts().pair_impl; }
 
 // One simulator pass over `R` feature rows (cat/dense already assembled, chunk-local pointers).
@@ -444,7 +438,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
     s.scoresT = scores + (size_t)i * sc_per_seq;
     s.shared = sh[i];
     r4tc::AugruTcSeq& q = rp.s[i];
-    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = augru_use_single(2 * rtiles) ? w.au_img : w.au_pair_img; q.scoresT = s.scoresT;
+    q.XT = reinterpret_cast<const float*>(cs[i]->XT.p); q.Wimg = w.au_pair_img; q.scoresT = s.scoresT;
     q.out = allf + i * AUH; q.shared = sh[i];
   }
   sp.R = R; sp.row0 = row0; sp.div = div; sp.q = qbuf;
@@ -484,8 +478,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
     const dim3 pgrid(rtiles * 2, 2);
     const int which = augru_choice(2 * rtiles);
-    if (which == 1) r4tc::k_augru_tc<<<dim3(rtiles, 2), r4tc::NTHREADS, r4tc::SMEM_BYTES, st>>>(rp);
-    else if (which == 3) {
+    if (which == 3) {
       r4tc::AugruPairParams pp;
       pp.b = rp; pp.tmap[0] = e->ps[0].au_pair_tmap; pp.tmap[1] = e->ps[1].au_pair_tmap;
       if (augru_pair_impl() >= 3) r4tc::k_augru_pp<1><<<dim3(rtiles * 2), r4tc::NTHREADS, r4tc::PP_SMEM_BYTES, st>>>(pp);
@@ -512,7 +505,7 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
       }
       (void)le;
     } }
-  R4_LAUNCH_CHECK(e, augru_choice(2 * rtiles) == 1 ? "k_augru_tc" : (augru_choice(2 * rtiles) == 3 ? "k_augru_pp" : "k_augru_pair2"));
+  R4_LAUNCH_CHECK(e, augru_choice(2 * rtiles) == 3 ? "k_augru_pp" : "k_augru_pair2");
   if (!no_side && !side_early && (rc = side_work())) return rc;
   if (!no_side) R4_CUDA(e, cudaStreamWaitEvent(st, e->ev_join, 0));
   float* obs = obs_out;
@@ -674,7 +667,6 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
             cudaMalloc(&e->sflag, (size_t)e->B) == cudaSuccess;
   if (!ok) { r4_destroy(e); return fail(nullptr, R4_ERR_NOMEM, "r4_create: cudaMalloc failed"); }
   cudaFuncSetAttribute(r4tc::k_gru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G1_SMEM_BYTES);
-  cudaFuncSetAttribute(r4tc::k_augru_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_augru_pp<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::PP_SMEM_BYTES);
@@ -937,8 +929,6 @@ int r4_finalize_weights(r4_env* e, void* stream) {
       if ((rc = upload(e, wpi, &w.wp_img))) return rc;
     }
     std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
-    r4tc::build_weight_image(awgh.data(), awch.data(), img.data());
-    if ((rc = upload(e, img, &w.au_img))) return rc;
     r4tc::build_pair_image(awgh.data(), awch.data(), img.data());
     if ((rc = upload(e, img, &w.au_pair_img))) return rc;
     {
@@ -1124,9 +1114,8 @@ int r4_set_option(const char* key, int value) {
   if (!key) return fail(nullptr, R4_ERR_ARG, "r4_set_option: null key");
   AugruOpts& o = augru_opts();
   const std::string k(key);
-  if (k == "augru_kernel" && value >= 0 && value <= 3) o.force = value;
+  if (k == "augru_kernel" && (value == 0 || value == 2 || value == 3)) o.force = value;
   else if (k == "augru_pair_impl" && value >= 1 && value <= 4) o.pair_impl = value;
-  else if (k == "augru_cost_single" && value > 0) o.cost_single = value;
   else if (k == "augru_cost_pair" && value > 0) o.cost_pair = value;
   else if (k == "augru_cost_pp" && value > 0) o.cost_pp = value;
   else if (k == "augru_cluster" && (value == 2 || value == 4 || value == 8)) o.cluster = value;

@@ -7,7 +7,7 @@
 // registers, cp.async.bulk weight ring) but with hidden 128 everything fits without aliasing:
 //   TMEM  r | u | c = 3 x 128 columns;  shared: h operand 64 KB + SEPARATE r*h operand 64 KB + 4 x 8 KB ring,
 // so the u-GEMM runs while the epilogue converts r*h, and sigmoid(u) is written back in place during the c-GEMM.
-// One CTA = 128 sequences.  Warp roles as in k_augru_tc (8 epilogue warps: thread = row x 64-column half).
+// One CTA = 128 sequences.  Warp roles: 8 epilogue warps (thread = row x 64-column half), MMA issuer, TMA producer.
 #pragma once
 #include "r4_augru_tc.cuh"
 

@@ -10,7 +10,7 @@
 // tiles; producer warps gather the 10 slate embeddings, build A = q*H as bf16 hi/lo core matrices (double
 // buffered), one lane issues 5 MMAs per K16 (A hi/lo x Wp hi/mid/lo: 2-way x 3-way split), epilogue warps
 // (lane = key) add q(Wq+Wd)+b1 and the cached key half, run the 64->16->1 tail in registers and write the
-// scores in the lane-major tile layout k_augru_tc reads.
+// scores in the lane-major tile layout the AUGRU kernels read.
 #pragma once
 #include "r4_augru_tc.cuh"
 

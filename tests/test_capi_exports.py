@@ -66,19 +66,19 @@ def test_product_never_imports_oracle():
 
 
 def test_augru_kernel_choice_rule():
-    """r4_augru_kernel_for(ctas = 2 x row tiles, sms): 1 = k_augru_tc (a CTA per tile-sequence), 2 = k_augru_pair2 (a CTA
-    pair per tile-sequence), 3 = k_augru_pp (a CTA pair per tile, both sequences in flight) -- the cheapest by wave
-    count x measured wave cost (defaults 30 : 13 : 24).  B200 (148 SMs): a 4096-row observation pass = 64 tile-sequences
-    -> pair2 (one wave on 128 SMs beats one ping-pong wave on 64); the 36 864-row reward pass = 576 and 8192-row
-    passes = 128 -> ping-pong."""
+    """r4_augru_kernel_for(ctas = 2 x row tiles, sms): 2 = k_augru_pair2 (a CTA pair per tile-sequence), 3 = k_augru_pp (a
+    CTA pair per tile, both sequences in flight) -- the cheaper by wave count x measured wave cost (defaults 13 : 24).
+    B200 (148 SMs): a 4096-row observation pass = 64 tile-sequences -> pair2 (one wave on 128 SMs beats one ping-pong wave
+    on 64); the 36 864-row reward pass = 576 and 8192-row passes = 128 -> ping-pong.  (1 was the round-1 one-CTA kernel,
+    deleted: it lost every regime.)"""
     from rl4rs_b200 import _capi
     lib = _capi.load_library()
     f = lib.r4_augru_kernel_for
 
-    def want(ctas, sms, cs=30, cp=13, cpp=24):
+    def want(ctas, sms, cp=13, cpp=24):
         pairs = sms // 2
-        c1, c2, c3 = cs * -(-ctas // sms), cp * -(-ctas // pairs), cpp * -(-((ctas + 1) // 2) // pairs)
-        return 3 if (c3 <= c2 and c3 <= c1) else (1 if c1 <= c2 else 2)
+        c2, c3 = cp * -(-ctas // pairs), cpp * -(-((ctas + 1) // 2) // pairs)
+        return 3 if c3 <= c2 else 2
 
     assert f(64, 148) == 2 and f(2, 148) == 2 and f(74, 148) == 2
     assert f(576, 148) == 3 and f(128, 148) == 3 and f(148, 148) == 3
@@ -88,9 +88,10 @@ def test_augru_kernel_choice_rule():
     # r4_set_option: overrides are validated, and the rule follows the costs it is given
     assert lib.r4_set_option(b"augru_cost_pp", 100) == 0
     assert f(576, 148) == 2 and f(64, 148) == 2          # without the ping-pong kernel: the pair kernel takes every pass
-    assert lib.r4_set_option(b"augru_cost_single", 3) == 0 and lib.r4_set_option(b"augru_cost_pair", 2) == 0
-    assert f(576, 148) == 1
-    for k, v in ((b"augru_cost_single", 30), (b"augru_cost_pair", 13), (b"augru_cost_pp", 24)):
+    assert lib.r4_set_option(b"augru_cost_pair", 60) == 0
+    assert f(576, 148) == 3
+    for k, v in ((b"augru_cost_pair", 13), (b"augru_cost_pp", 24)):
         assert lib.r4_set_option(k, v) == 0
+    assert lib.r4_set_option(b"augru_kernel", 1) != 0 and lib.r4_set_option(b"augru_cost_single", 3) != 0   # the deleted kernel
     assert lib.r4_set_option(b"augru_kernel", 7) != 0 and lib.r4_set_option(b"no_such_key", 1) != 0
     assert lib.r4_set_option(b"augru_kernel", 0) == 0

@@ -5,7 +5,8 @@
 * full-size batches (4096 and 8192 rows per GPU, the BASELINE configs[1] / north-star per-GPU sizes): a 128-row oracle
   sample of the big env, rows compared by index;
 * every AUGRU kernel forced in turn (``r4_set_option('augru_kernel', ...)``): the simulator alone and env fixtures
-  through the one-CTA k_augru_tc and through the 2-CTA pair kernel, plus a launch big enough for the natural rule;
+  through the pair kernel (one recurrence per CTA pair) and the ping-pong kernel (two per pair), every hand-over /
+  weight-ring variant of both, plus a launch big enough for the natural rule;
 * the chunked sequence-cache build (> 8192 sequences) and the multi-wave persistent GEMM (tiles > SMs).
 
 Oracle = oracle/env_np.py + oracle/dien_np.py (f32), reference lines: rl4rs/nets/utils.py:117-125,
@@ -44,7 +45,7 @@ def augru_option():
     from rl4rs_b200 import _capi
 
     def force(mode):
-        _capi.set_option("augru_kernel", {"auto": 0, "single": 1, "pair": 2, "pp": 3}[mode])
+        _capi.set_option("augru_kernel", {"auto": 0, "pair": 2, "pp": 3}[mode])
     yield force
     _capi.set_option("augru_kernel", 0)
 
@@ -131,7 +132,7 @@ def _random_feature_rows(R, seed, hash_size):
 
 
 @pytest.mark.parametrize("regime", ["default", "stress"])
-@pytest.mark.parametrize("kernel", ["single", "pair", "pp"])
+@pytest.mark.parametrize("kernel", ["pair", "pp"])
 def test_dien_forward_each_augru_kernel(kernel, regime, augru_option):
     """The simulator alone on 200 random feature rows through EACH AUGRU kernel, both weight regimes."""
     from oracle.dien_np import DienOracle
@@ -173,7 +174,7 @@ def test_dien_forward_each_pair_variant(kernel, impl, augru_option):
     assert_close_rel(probs.cpu().numpy(), p_ref, what="dien probs [%s, impl %d]" % (kernel, impl))
 
 
-@pytest.mark.parametrize("kernel", ["single", "pair", "pp"])
+@pytest.mark.parametrize("kernel", ["pair", "pp"])
 @pytest.mark.parametrize("name", ["slate_rllib_replay", "seqslate27_plain_mixed"])
 def test_env_fixture_each_augru_kernel(name, kernel, augru_option):
     """Two reference-made fixtures end to end with the AUGRU kernel forced (obs + reward passes)."""
@@ -219,7 +220,7 @@ def test_augru_kernels_agree_bit_patterns_under_load():
     """Stress for the pair kernel's cross-CTA hand-over (round-1 advisor): the same 1 024-row forward 6 times through
     the pair kernel while a second stream keeps the memory system and the remaining SMs busy; every repetition must
     reproduce the first BIT FOR BIT (a stale h / r*h operand read would show up as a changed mantissa), and all of
-    them must agree with the one-CTA kernel to the parity tolerance."""
+    them must agree with the ping-pong kernel (a different schedule of the same arithmetic) to the parity tolerance."""
     import torch
     from rl4rs_b200 import _capi
     cfg, cat, log, w = _default_regime(8, False)
@@ -227,7 +228,7 @@ def test_augru_kernels_agree_bit_patterns_under_load():
     seq, dense, catf = _random_feature_rows(1024, 21, 100000)
     eng = env.sim.engine
     try:
-        _capi.set_option("augru_kernel", 1)
+        _capi.set_option("augru_kernel", 3)
         base, _ = eng.dien_forward(seq, dense, catf)
         base = base.cpu().numpy()
         _capi.set_option("augru_kernel", 2)
@@ -245,4 +246,4 @@ def test_augru_kernels_agree_bit_patterns_under_load():
         _capi.set_option("augru_kernel", 0)
     for o in outs[1:]:
         np.testing.assert_array_equal(o.view(np.uint32), outs[0].view(np.uint32))
-    assert_close_rel(outs[0], base, what="pair vs one-CTA kernel")
+    assert_close_rel(outs[0], base, what="pair vs ping-pong kernel")

@@ -1,4 +1,5 @@
-// augru_probe.cu -- standalone check + timing of k_augru_tc against a CPU (f64) recurrence.
+// augru_probe.cu -- standalone check + timing of the AUGRU pair kernels (-DPAIR: k_augru_pair2, -DPAIR -DPP: k_augru_pp)
+// against a CPU (f64) recurrence.
 // Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o tools/build/augru_probe tools/augru_probe.cu
 #include "../rl4rs_b200/csrc/r4_augru_tc.cuh"
 #ifdef PAIR
@@ -9,10 +10,10 @@
 #ifdef PAIR2
 #include "../rl4rs_b200/csrc/r4_augru_pair2.cuh"
 #ifndef P2RELAY
-#define P2RELAY 1
+#define P2RELAY R4P2_RELAY
 #endif
 #ifndef P2TMAP
-#define P2TMAP 1
+#define P2TMAP R4P2_TMAP
 #endif
 #ifdef PP
 #include "../rl4rs_b200/csrc/r4_augru_pp.cuh"
@@ -32,17 +33,8 @@
 #endif
 #define KTHREADS NTHREADS
 #define GRIDX(t) (2 * (t))
-#elif defined(V2)
-#include "experiments/r4_augru_tc2.cuh"
-#define KERNEL r4tc2::k_augru_tc2
-#define KSMEM r4tc2::SMEM2_BYTES
-#define KTHREADS r4tc2::NTHREADS2
-#define GRIDX(t) (2 * (t))
 #else
-#define KERNEL k_augru_tc
-#define KSMEM SMEM_BYTES
-#define KTHREADS NTHREADS
-#define GRIDX(t) (t)
+#error "build with -DPAIR (k_augru_pair2) or -DPAIR -DPP (k_augru_pp): the one-CTA kernel was deleted at the end of round 2"
 #endif
 #include <cstdio>
 #include <cstdlib>
@@ -58,13 +50,7 @@ static float bf16_val(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; mem
 
 void build_image(const std::vector<float>& Wg, const std::vector<float>& Wc, std::vector<uint8_t>& img) {
   img.assign(W_IMAGE_BYTES, 0);
-#ifdef PAIR
   build_pair_image(Wg.data(), Wc.data(), img.data());
-#elif defined(V2)
-  r4tc2::build_weight_image2(Wg.data(), Wc.data(), img.data());
-#else
-  build_weight_image(Wg.data(), Wc.data(), img.data());
-#endif
 }
 
 int main(int argc, char** argv) {
