@@ -198,6 +198,10 @@ int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_
                    const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
                    float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
                    float* flat_grad, float* stats_accum, float stat_scale, void* stream);
+/* Generalised advantage estimation over complete episodes (RLlib postprocessing compute_advantages, bootstrap value 0):
+ * reward / value / adv / target are f32 [T, B] device arrays; target = adv + value; gamma_lambda = the product gamma * lambda
+ * (rounded once by the caller, as the reference's float arithmetic does).  One launch instead of a host loop. */
+int r4_gae(const float* reward, const float* value, int T, int B, float gamma, float gamma_lambda, float* adv, float* target, void* stream);
 /* Adam (torch.optim.Adam semantics) with optional global-norm clipping (clip <= 0 off; norm_scratch f32[1]).
  * grad_scale multiplies the gradient first (1/world after a SUM all-reduce). step is 1-based. */
 int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,

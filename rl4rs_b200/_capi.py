@@ -62,6 +62,7 @@ EXPORTS = {
                        [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "r4_ppo_epoch": (C.c_int, [C.c_void_p] * 10 + [C.c_int] * 3 + [C.c_float] * 5 + [C.c_void_p] * 5 + [C.c_int] +
                      [C.c_float] * 5 + [C.c_void_p, C.c_void_p]),
+    "r4_gae": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r4_comm_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "r4_comm_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
     "r4_comm_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

@@ -1233,6 +1233,13 @@ int r4_policy_grad(int mode, const float* params, const float* obs, const uint8_
                           stream, true);
 }
 
+int r4_gae(const float* reward, const float* value, int T, int B, float gamma, float gamma_lambda, float* adv, float* target, void* stream) {
+  if (!reward || !value || !adv || !target || T < 1 || B < 1) return fail(nullptr, R4_ERR_ARG, "r4_gae: bad argument");
+  r4ppo::k_gae<<<(B + 255) / 256, 256, 0, S(stream)>>>(T, B, reward, value, gamma, gamma_lambda, adv, target);
+  R4_PCHECK("k_gae");
+  return R4_OK;
+}
+
 int r4_adam_step(float* params, const float* grad, float* m, float* v, int n, int step, float lr, float beta1,
                  float beta2, float eps, float grad_scale, float clip, float* norm_scratch, void* stream) {
   if (!params || !grad || !m || !v || n < 1 || step < 1 || (clip > 0.f && !norm_scratch))

@@ -444,6 +444,24 @@ __global__ void k_reduce_adam(int n, int G, const float* __restrict__ partial, f
   }
 }
 
+// GAE over complete episodes (RLlib compute_advantages with a zero bootstrap value): one thread = one env row, the same
+// recursion in the same order as the torch loop it replaces (45 tiny launches per iteration at T = 9):
+//     delta_t = r_t + gamma v_{t+1} - v_t ;  adv_t = delta_t + gamma lambda adv_{t+1} ;  target_t = adv_t + v_t
+__global__ void k_gae(int T, int B, const float* __restrict__ reward, const float* __restrict__ value, float gamma, float gamma_lam,
+                      float* __restrict__ adv, float* __restrict__ target) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float last = 0.f, nv = 0.f;
+  for (int t = T - 1; t >= 0; --t) {
+    const float v = value[(size_t)t * B + b];
+    const float delta = __fadd_rn(__fadd_rn(reward[(size_t)t * B + b], __fmul_rn(gamma, nv)), -v);
+    last = __fadd_rn(delta, __fmul_rn(gamma_lam, last));
+    adv[(size_t)t * B + b] = last;
+    target[(size_t)t * B + b] = __fadd_rn(last, v);
+    nv = v;
+  }
+}
+
 __global__ void k_sumsq(int n, const float* __restrict__ x, float* __restrict__ out) {
   __shared__ float red[32];
   float s = 0.f;

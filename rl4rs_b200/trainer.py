@@ -112,6 +112,14 @@ class KernelOps(object):
         self._check(rc, "r4_grad_exchange")
         self.launches += 2
 
+    def gae(self, reward, value, gamma, lam):
+        """-> (target, adv) of a [T, B] rollout in one launch (r4_gae)."""
+        adv, target = torch.empty_like(reward), torch.empty_like(reward)
+        rc = self.lib.r4_gae(_p(reward), _p(value), reward.shape[0], reward.shape[1], gamma, gamma * lam, _p(adv), _p(target), self._stream())
+        self._check(rc, "r4_gae")
+        self.launches += 1
+        return target, adv
+
     def adam(self, flat, lr, grad_scale, clip):
         self.step += 1
         rc = self.lib.r4_adam_step(_p(flat), _p(self.grad), _p(self.m), _p(self.v), self.n, self.step, lr, 0.9, 0.999,
@@ -251,6 +259,13 @@ class _TrainerBase(object):
             buf.reward[t].copy_(reward)
         return buf
 
+    def _gae(self, buf):
+        c = self.config
+        lam = c.get("lambda", 1.0)
+        if self.use_kernels and buf.reward.dtype == torch.float32 and buf.reward.is_contiguous() and buf.value.is_contiguous():
+            return self.ops.gae(buf.reward, buf.value, c["gamma"], lam)
+        return buf.returns_and_advantages(c["gamma"], lam)
+
     def _allreduce_grad(self, average):
         w = _world()
         if w > 1:
@@ -357,7 +372,8 @@ class PPOTrainer(_TrainerBase):
     def __init__(self, config, env, device=None, seed=0):
         super().__init__(config, env, device, seed)
         self.kl_coeff = self.config["kl_coeff"]
-        self._gen = torch.Generator(device="cpu").manual_seed(seed)
+        # minibatch permutations are drawn on the device the rollout lives on (a CPU randperm + copy stalled the GPU ~1 ms per epoch)
+        self._gen = torch.Generator(device=self.device if self.device.type == "cuda" else "cpu").manual_seed(seed)
 
     def loss(self, obs, mask, action, old_logp, old_logits, old_value, adv, target):
         """RLlib 1.5 ppo_surrogate_loss."""
@@ -379,7 +395,7 @@ class PPOTrainer(_TrainerBase):
 
     def learn(self, buf):
         c = self.config
-        target, adv = buf.returns_and_advantages(c["gamma"], c["lambda"])
+        target, adv = self._gae(buf)
         n = buf.T * buf.B
         flat = lambda x: x.reshape((n,) + x.shape[2:])
         obs, mask, act = flat(buf.obs), flat(buf.mask), flat(buf.action)
@@ -408,7 +424,9 @@ class PPOTrainer(_TrainerBase):
 
     def _perm(self, n, device):
         c = self.config
-        return (torch.randperm(n, generator=self._gen) if c["shuffle_sequences"] else torch.arange(n)).to(device)
+        if not c["shuffle_sequences"]:
+            return torch.arange(n, device=device)
+        return torch.randperm(n, generator=self._gen, device=self._gen.device).to(device)
 
     def _sgd_eager(self, data, n, mb):
         c = self.config
@@ -486,7 +504,7 @@ class A2CTrainer(_TrainerBase):
 
     def learn(self, buf):
         c = self.config
-        target, adv = buf.returns_and_advantages(c["gamma"], c["lambda"])
+        target, adv = self._gae(buf)
         n = buf.T * buf.B
         flat = lambda x: x.reshape((n,) + x.shape[2:])
         if self.use_kernels:

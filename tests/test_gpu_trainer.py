@@ -52,6 +52,19 @@ def test_rawstate_trainer_runs_on_cuda_env():
     assert torch.isfinite(tr.policy.flat).all()
 
 
+def test_gae_kernel_matches_the_torch_loop_bitwise():
+    import torch
+    from rl4rs_b200.trainer import KernelOps, RolloutBuffer
+    dev = torch.device("cuda")
+    for T, B, gamma, lam in ((9, 1000, 1.0, 1.0), (27, 333, 0.99, 0.95), (1, 5, 0.5, 0.0)):
+        buf = RolloutBuffer(T, B, 284, dev)
+        g = torch.Generator().manual_seed(T)
+        buf.reward.copy_(torch.randn(T, B, generator=g) * 10); buf.value.copy_(torch.randn(T, B, generator=g))
+        t_ref, a_ref = buf.returns_and_advantages(gamma, lam)
+        t_k, a_k = KernelOps(284, dev, 34973).gae(buf.reward, buf.value, gamma, lam)
+        assert torch.equal(a_k, a_ref) and torch.equal(t_k, t_ref)
+
+
 def _random_batch(n, A, dev, seed=0):
     import torch
     g = torch.Generator(device="cpu").manual_seed(seed)
