@@ -108,6 +108,12 @@ __global__ void __launch_bounds__(128) k_query(int R, const int32_t* __restrict_
   for (int i = 0; i < 8; ++i) if (r0 + i < R) o[(size_t)(r0 + i) * S_N + j] = acc[i];
 }
 
+// acc <- a * b + acc on two fp32 lanes at once (PTX fma.rn.f32x2, sm_100+): each lane rounds like a scalar fma.rn.f32
+__device__ __forceinline__ void ffma2(float2& acc, float2 a, float2 b) {
+  uint64_t& c = reinterpret_cast<uint64_t&>(acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(reinterpret_cast<uint64_t&>(a)), "l"(reinterpret_cast<uint64_t&>(b)));
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
@@ -268,9 +274,11 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
       tc_fence_before();
       mbar_arrive(&bar_tempty[s]);               // accumulators are free again
       const float* qap = qa_s[s] + rr * S_N + j0;
-      float o[16];
+      // second layer 64 -> 16 as packed fp32 FMAs (fma.rn.f32x2 = SASS FFMA2: two independent fp32 FMAs per issue slot, same
+      // rounding as the scalar form): the kernel is issue-bound on these 512 FMAs + 128 LDS per thread and tile
+      float2 o2[8];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) o[jj] = jh ? 0.f : b2_s[jj];
+      for (int jj = 0; jj < 8; ++jj) o2[jj] = jh ? make_float2(0.f, 0.f) : make_float2(b2_s[2 * jj], b2_s[2 * jj + 1]);
 #pragma unroll
       for (int j = 0; j < S_N / 2; j += 4) {
         const float4 kq = kk[j / 4];
@@ -278,11 +286,20 @@ __global__ void __launch_bounds__(S_THREADS, 1) k_scores_tc(ScoreTcParams p, con
         float zz[4] = {z[j] + qq.x + kq.x, z[j + 1] + qq.y + kq.y, z[j + 2] + qq.z + kq.z, z[j + 3] + qq.w + kq.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          float a1 = fast_sigmoid(zz[u]);        // ex2.approx + rcp.approx (2^-22 / 1 ulp), as in the AUGRU gates
+          const float a1 = fast_sigmoid(zz[u]);  // ex2.approx + rcp.approx (2^-22 / 1 ulp), as in the AUGRU gates
+          const float2 aa = make_float2(a1, a1);
+          const float4* wrow = reinterpret_cast<const float4*>(W2_s + (j0 + j + u) * 16);
 #pragma unroll
-          for (int jj = 0; jj < 16; ++jj) o[jj] = fmaf(a1, W2_s[(j0 + j + u) * 16 + jj], o[jj]);
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const float4 ww = wrow[q4];
+            ffma2(o2[2 * q4], aa, make_float2(ww.x, ww.y));
+            ffma2(o2[2 * q4 + 1], aa, make_float2(ww.z, ww.w));
+          }
         }
       }
+      float o[16];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) { o[2 * jj] = o2[jj].x; o[2 * jj + 1] = o2[jj].y; }
       // pair hand-over: buffer s of the partial-sum columns is rewritten two tiles later, after the partner's read of it
       // (the partner reads before it arrives at the next tile's pair barrier, which the writer also passes)
       const uint32_t tpart = tl + S_TC_PART + s * 16;
