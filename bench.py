@@ -233,6 +233,10 @@ def workload_config(args, seq):
             "parallelism": "env rows sharded by contiguous blocks, dp%d, no data-path collective" % args.gpus,
             "per_n_defaults": "batch/GPU 4096 at N=1 (BASELINE configs[1]), 8192 at N>1 (N=8: north_star global batch 65 536); "
                               "PPO sgd_minibatch_size 256 x N so that an iteration is 144 x (batch/4096) optimizer steps at every N",
+            "simulator_passes": "every observation and every reward is computed; a paying step's observation is row 8 of its "
+                                "page's reward rows (the reference evaluates that one feature row twice: slate.py:203-213 = "
+                                ":117-131 at j = 8), so %d simulator row-forwards per env row and episode instead of %d "
+                                "(R4_NO_PAY_OBS_REUSE=1 launches the duplicate pass)" % ((2 * T + 1 - T // 9), 2 * T + 1),
             "l2": "per-step working set (AUGRU input-projection cache ~0.21 MB/row, 0.87 GB at batch 4096) "
                   "exceeds the 126 MB L2; no explicit flush"}
 

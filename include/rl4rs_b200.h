@@ -176,7 +176,11 @@ int r4_augru_kernel_for(int ctas, int sms);
  *                      release.cluster hand-over), 4 = <1,1>
  *   "augru_cost_pair" / "augru_cost_pp"  the per-wave costs r4_augru_kernel_for compares (positive ints)
  *   "augru_cluster"    CTAs per cluster of the pair kernel: 2 (one pair), 4 or 8 (2 / 4 pairs share one multicast weight stream)
- * The environment variables R4_AUGRU_PAIR / R4_AUGRU_PP / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE give the initial
+ *   "pay_obs_reuse"    1 (default): r4_step takes the observation of a PAYING step (the last step of a slate / page) from that
+ *                      step's reward pass -- the state the step leaves (rl4rs/env/slate.py:203-213, seqslate.py:104-122) is the
+ *                      last of the page's complete states (slate.py:117-131, seqslate.py:27-50), so the reference runs the same
+ *                      feature row through the simulator twice; 0: launch the separate observation pass as well
+ * The environment variables R4_AUGRU_PAIR / R4_AUGRU_PP / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE / R4_NO_PAY_OBS_REUSE give the initial
  * values.  Returns 0, or R4_ERR_ARG for an unknown key / out-of-range value. */
 int r4_set_option(const char* key, int value);
 

@@ -285,7 +285,13 @@ struct AugruOpts {
   // k_augru_pp 0.96 ms per 74 TILES (= 148 tile-sequences)
   int cost_pair = 13, cost_pp = 24;
   int cluster = 2;        // CTAs per cluster of the pair kernel: 2, or 4 / 8 = weight stream shared by 2 / 4 pairs (multicast)
+  int scores_impl = 2;    // 2 = k_scores_tc2 (both attention layers on the tensor pipe), 1 = k_scores_tc (second layer as FFMA2)
+  int scores_shared_pct = 75;    // k_scores_tc2: CTA share of a shared (L2-resident) sequence, per cent of an even split (tools/scores_probe.cu:
+                                 // 100 % 96.5 us, 75 % 90.3 us, 60 % 109 us per 4096-row pass)
+  int pay_obs_reuse = 1;  // a paying step takes its observation from its reward pass (r4_step); 0 = separate observation pass
   AugruOpts() {
+    if (getenv("R4_NO_PAY_OBS_REUSE")) pay_obs_reuse = 0;
+    if (const char* e = getenv("R4_SCORES_IMPL")) { int v = atoi(e); if (v == 1 || v == 2) scores_impl = v; }
     if (getenv("R4_AUGRU_PAIR")) force = 2; else if (getenv("R4_AUGRU_PP")) force = 3;
     if (const char* e = getenv("R4_AUGRU_PAIR_IMPL")) { int v = atoi(e); if (v >= 1 && v <= 4) pair_impl = v; }
     if (const char* e = getenv("R4_AUGRU_CLUSTER")) { int v = atoi(e); if (v == 2 || v == 4 || v == 8) cluster = v; }
@@ -472,7 +478,13 @@ int forward_rows(r4_env* e, int R, int row0, int div, const int32_t* cat, const 
                                                 qbuf, qa0, qa1); }
   R4_LAUNCH_CHECK(e, "k_query");
   { ProfScope ps(e, SL_SCORES, st, (double)R * 2 * MAXLEN * 2.0 * (EMB * AH1 + AH1 * AH2 + AH2));
-    r4tc::k_scores_tc<<<dim3(std::min((R + 1) / 2, 74), 2), r4tc::S_THREADS, r4tc::S_SMEM_BYTES, st>>>(sp, cat, e->emb_seq); }
+    const int nt = (R + 1) / 2;
+    if (augru_opts().scores_impl == 1) r4tc::k_scores_tc<<<dim3(std::min(nt, 74), 2), r4tc::S_THREADS, r4tc::S_SMEM_BYTES, st>>>(sp, cat, e->emb_seq);
+    else {
+      const int ctas = std::min(2 * nt, 148);
+      r4tc::k_scores_tc2<false><<<ctas, r4tc::S2_THREADS, r4tc::S2_SMEM_BYTES, st>>>(
+          sp, r4tc::scores_grid_split(ctas, nt, sh[0], sh[1], augru_opts().scores_shared_pct));
+    } }
   R4_LAUNCH_CHECK(e, "k_scores_tc");
   if (!no_side && !side_early) R4_CUDA(e, cudaEventRecord(e->ev_fork, st));
   { ProfScope ps(e, SL_AUGRU, st, (double)R * 2 * MAXLEN * 2.0 * (AUH * 2 * AUH + AUH * AUH));
@@ -573,8 +585,13 @@ int obs_pass(r4_env* e, int mode, int step, const r4_out* out, cudaStream_t st) 
   return R4_OK;
 }
 
-// reward pass: rpe rows per env row (slate.py:286-302 / seqslate.py:138-153)
-int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st) {
+// reward pass: rpe rows per env row (slate.py:286-302 / seqslate.py:138-153).
+// obs_take != null: also the step's observation.  A step pays when it completes a slate / a page, and the state it leaves
+// behind (slate.py:203-213, seqslate.py:104-122: the complete page + the last action) is, field for field, the LAST of the
+// page's complete states (slate.py:117-131, seqslate.py:27-50 with j = cur_steps - 1): the same feature row goes through the
+// same network twice in the reference (obs_layer at base.py:160, reward_layer at slate.py:296).  Here row rpe - 1 of every
+// env row's reward rows keeps its simulator_obs output and the separate observation pass is not launched.
+int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st, float* obs_take = nullptr) {
   int rc;
   const int B = e->B;
   const int rpe = e->seq ? e->P : e->T;
@@ -593,6 +610,12 @@ int reward_pass(r4_env* e, int cur_after, const r4_out* out, cudaStream_t st) {
     const SeqCache& c1 = seq1_cache(e);
     if ((rc = forward_rows(e, nr, b0 * rpe, rpe, cat, dense, e->c0, 0, c1, e->c1_is_page ? 0 : 1, nullptr,
                            p1 + (size_t)b0 * rpe, nullptr, st))) return rc;
+    if (obs_take) {                     // forward_rows left simulator_obs of the chunk's rows in ws_obs [nr, obs_dim]
+      const int ld4 = e->obs_dim / 4;
+      k_take_rows<<<(int)(((size_t)nb * ld4 + 255) / 256), 256, 0, st>>>(nb, rpe, rpe - 1, ld4, reinterpret_cast<const float4*>(e->ws_obs.p),
+                                                                         reinterpret_cast<float4*>(obs_take + (size_t)b0 * e->obs_dim));
+      R4_LAUNCH_CHECK(e, "k_take_rows");
+    }
   }
   int zero = 1;                                                   // slate.py:303 `if 1:`
   if (e->seq) zero = (e->cfg.flags & (R4_FLAG_RLLIB_MASK | R4_FLAG_D3RL_MASK)) ? 1 : 0;   // seqslate.py:154-157
@@ -677,6 +700,7 @@ int r4_create(const r4_config* cfg, int device, r4_env** out) {
   cudaFuncSetAttribute(r4tc::k_augru_pair2<0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::P_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::G_SMEM_BYTES);
   cudaFuncSetAttribute(r4tc::k_scores_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S_SMEM_BYTES);
+  cudaFuncSetAttribute(r4tc::k_scores_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, r4tc::S2_SMEM_BYTES);
   cudaFuncSetAttribute(k_cat_attn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAT);
   cudaFuncSetAttribute(k_cat_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, POOL_SMEM);
   st = cudaGetLastError();
@@ -924,8 +948,8 @@ int r4_finalize_weights(r4_env* e, void* stream) {
     if ((rc = upload_image(e, wx.data(), EMB, XIN_LD, &w.gru_wx_img)) ||
         (rc = upload_image(e, awx.data(), EMB, XK_LD, &w.au_wx_img))) return rc;
     {
-      std::vector<uint8_t> wpi(r4tc::S_B_BYTES);
-      r4tc::build_scores_image(wp.data(), wpi.data());
+      std::vector<uint8_t> wpi(r4tc::S_IMG_BYTES);      // Wp image, then the W2 image of k_scores_tc2
+      r4tc::build_scores_image2(wp.data(), aw2, wpi.data());
       if ((rc = upload(e, wpi, &w.wp_img))) return rc;
     }
     std::vector<uint8_t> img(r4tc::W_IMAGE_BYTES);
@@ -1027,10 +1051,13 @@ int r4_step(r4_env* e, const void* action, int action_is_f64, const r4_out* out,
                                                          nullptr, nullptr, out->seq);
     R4_LAUNCH_CHECK(e, "k_seq_ids");
   }
-  if ((rc = obs_pass(e, 1, cur, out, st))) return rc;
+  const bool pay = e->seq ? (e->cur_steps % e->P == 0) : (e->cur_steps >= e->T);
+  // paying step with a network observation and no feature outputs: the reward pass delivers the observation as well
+  const bool reuse = augru_opts().pay_obs_reuse && pay && out && out->reward && out->obs && !out->cat && !out->dense &&
+                     !(e->cfg.flags & R4_FLAG_RAWSTATE);
+  if (!reuse && (rc = obs_pass(e, 1, cur, out, st))) return rc;
   if (out && out->reward) {
-    bool pay = e->seq ? (e->cur_steps % e->P == 0) : (e->cur_steps >= e->T);
-    if (pay) { if ((rc = reward_pass(e, e->cur_steps, out, st))) return rc; }
+    if (pay) { if ((rc = reward_pass(e, e->cur_steps, out, st, reuse ? out->obs : nullptr))) return rc; }
     else { k_fill_f64<<<(B + 255) / 256, 256, 0, st>>>(B, 0.0, out->reward); R4_LAUNCH_CHECK(e, "k_fill_f64"); }
   }
   if (out && out->done) {       // base.py:165-168 with the pre-increment step (Q1)
@@ -1119,6 +1146,9 @@ int r4_set_option(const char* key, int value) {
   else if (k == "augru_cost_pair" && value > 0) o.cost_pair = value;
   else if (k == "augru_cost_pp" && value > 0) o.cost_pp = value;
   else if (k == "augru_cluster" && (value == 2 || value == 4 || value == 8)) o.cluster = value;
+  else if (k == "pay_obs_reuse" && (value == 0 || value == 1)) o.pay_obs_reuse = value;
+  else if (k == "scores_impl" && (value == 1 || value == 2)) o.scores_impl = value;
+  else if (k == "scores_shared_pct" && value >= 10 && value <= 100) o.scores_shared_pct = value;
   else return fail(nullptr, R4_ERR_ARG, "r4_set_option: unknown key or value out of range: " + k);
   return R4_OK;
 }

@@ -72,6 +72,15 @@ __host__ __device__ __forceinline__ size_t xt_index(size_t tile_step, int ld, in
   return (tile_step * ld + (size_t)(col & ~3)) * TM + (size_t)lane * 4 + (col & 3);
 }
 
+// float index of column quad `quad` (4 consecutive columns) of (sequence nabs, step t) in the key-half cache Kp: layout
+// [sequence][column quad][step][4].  The scores kernels read it with lane = step (key): the 32 lanes of a warp read 512
+// contiguous bytes per 128-bit load.  (Round 2, ncu on k_scores_tc: with the row-major [sequence][step][64] layout every
+// lane read its own 256-byte row -- 32 L1 wavefronts per warp load, 2 k of the kernel's 4.5 k global-load wavefronts per
+// tile, with the LSU data pipe at 70 % the unit that set the tile time.)
+__host__ __device__ __forceinline__ size_t kq_index(size_t nabs, int nquads, int quad, int steps, int t) {
+  return ((nabs * nquads + quad) * steps + t) * 4;
+}
+
 struct GemmTcParams {
   const float* A; int lda; const int32_t* gather;
   const uint8_t* Wimg; const float* bias; float* C; int ldc;
@@ -79,7 +88,7 @@ struct GemmTcParams {
   // "sequence" mode (tm_ns > 0): the M = tm_ns * 64 rows are (sequence n, step t) pairs enumerated t-major
   // (m = t * tm_ns + n; source row n * 64 + t), and the result is written in the lane-major tile layout the
   // recurrent kernels read: columns < ldT -> outT[((nabs/128) * 64 + t) * ldT + col) * 128 + nabs % 128],
-  // columns >= ldT -> outK[(nabs * 64 + t) * (N - ldT) + col - ldT], nabs = cr_base + n.  Consecutive threads are
+  // columns >= ldT -> outK in the quad layout [nabs][(col - ldT) / 4][t][4] (kq_index), nabs = cr_base + n.  Consecutive threads are
   // consecutive sequences of one step, so both reads and transposed writes stay coalesced.
   // Inside a tile-step the columns are grouped in QUADS, [col / 4][lane][col % 4] (xt_index below): a recurrent
   // kernel's thread (= lane) reads 4 consecutive columns with ONE 128-bit load (ncu, round 2: with one 32-bit load per
@@ -419,11 +428,17 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_gemm_tc(GemmTcParams p) {
           ++nchunk;
         } else if (m < p.M && p.tm_ns > 0) {
           const int t = m / p.tm_ns, nabs = p.cr_base + m % p.tm_ns;
+          if (n0 + c >= p.ldT) {            // ldT % 16 == 0: a 16-column chunk lies on one side.  outK in the quad layout (kq_index)
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int col = n0 + c + j;
-            if (col < p.ldT) p.outT[xt_index((size_t)(nabs / TM) * p.tm_steps + t, p.ldT, col, nabs % TM)] = a[j];
-            else p.outK[((size_t)nabs * p.tm_steps + t) * (p.N - p.ldT) + (col - p.ldT)] = a[j];
+            for (int j4 = 0; j4 < 4; ++j4)
+              *reinterpret_cast<float4*>(p.outK + kq_index(nabs, (p.N - p.ldT) / 4, (n0 + c - p.ldT) / 4 + j4, p.tm_steps, t)) =
+                  make_float4(a[4 * j4], a[4 * j4 + 1], a[4 * j4 + 2], a[4 * j4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + c + j;
+              if (col < p.ldT) p.outT[xt_index((size_t)(nabs / TM) * p.tm_steps + t, p.ldT, col, nabs % TM)] = a[j];
+            }
           }
         } else if (m < p.M) {
           float* o = p.C + (size_t)m * p.ldc + n0 + c;

@@ -550,6 +550,15 @@ __global__ void k_fill_u8(int n, uint8_t v, uint8_t* out) {
   if (i < n) out[i] = v;
 }
 
+// out[b, :] = src[b * rpe + j, :] (128-bit columns): the observation of a paying step is row j = rpe - 1 of that step's
+// reward pass (see reward_pass in r4_capi.cu)
+__global__ void k_take_rows(int nb, int rpe, int j, int ld4, const float4* __restrict__ src, float4* __restrict__ out) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)nb * ld4) return;
+  const size_t b = i / ld4, c = i % ld4;
+  out[i] = src[(b * rpe + j) * ld4 + c];
+}
+
 // d3rl 'masked_actions' (slate.py:98-104 / seqslate.py:18-23)
 __global__ void k_masked_actions(int B, int T, int w0, int W, const int32_t* __restrict__ prev_actions,
                                  int32_t* __restrict__ out) {

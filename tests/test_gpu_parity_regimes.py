@@ -247,3 +247,40 @@ def test_augru_kernels_agree_bit_patterns_under_load():
     for o in outs[1:]:
         np.testing.assert_array_equal(o.view(np.uint32), outs[0].view(np.uint32))
     assert_close_rel(outs[0], base, what="pair vs ping-pong kernel")
+
+
+@pytest.mark.parametrize("kind", ["slate", "seqslate27"])
+def test_pay_step_observation_comes_from_the_reward_pass(kind):
+    """A paying step's state is the last complete state of its page (slate.py:203-213 vs :117-131, seqslate.py:104-122 vs
+    :27-50), so r4_step takes that step's observation from its reward pass instead of launching a second pass over the
+    same feature rows (r4_set_option('pay_obs_reuse', 1), the default).  A/B against the separate observation pass:
+    same rewards, masks and observations (different AUGRU kernel / tile shapes: fp32 rounding only), and the option
+    does change the launch count."""
+    from rl4rs_b200 import _capi
+    seq = kind == "seqslate27"
+    B = 48
+    cfg, cat, log, w = _default_regime(B, seq, support_rllib_mask=True)
+    runs = {}
+    try:
+        for reuse in (1, 0):
+            _capi.set_option("pay_obs_reuse", reuse)
+            env = make_env(cfg, seq, cat, log, w, output_format="numpy")
+            rs = np.random.RandomState(3)
+            env.reset()
+            n0 = env.sim.engine.launch_count()
+            steps = []
+            for t in range(cfg["max_steps"]):
+                a = np.where(rs.rand(B) < 0.8, np.asarray(env.offline_action), rs.randint(0, 284, B))
+                o, rew, done, _ = env.step(a)
+                steps.append((o["obs"].copy(), o["action_mask"].copy(), np.asarray(rew).copy()))
+            runs[reuse] = (steps, env.sim.engine.launch_count() - n0)
+    finally:
+        _capi.set_option("pay_obs_reuse", 1)
+    paid = 0
+    for t, ((o1, m1, r1), (o0, m0, r0)) in enumerate(zip(runs[1][0], runs[0][0])):
+        np.testing.assert_array_equal(m1, m0)
+        assert_close_rel(o1, o0, what="%s pay-step reuse obs step %d" % (kind, t))
+        assert_close_rel(r1, r0, what="%s pay-step reuse reward step %d" % (kind, t))
+        paid += int((r0 != 0).any())
+    assert paid >= 1                            # (a page of 48 random-replaced slates can be all violations: reward 0)
+    assert runs[1][1] < runs[0][1], (runs[1][1], runs[0][1])        # one observation pass fewer per paying step
