@@ -181,7 +181,14 @@ int upload(r4_env* e, const std::vector<T>& h, T** dptr) {
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // n-tile width of the observation-head GEMM (K = 3456, N = 256): 128 doubles its CTA count (64 at batch 4096).
-constexpr int HEAD_BNT = 128;
+// n-tile width of the observation head's weight image.  256: every 128-row tile converts its A rows (fp32 -> bf16 hi/mid/lo,
+// the producers' work and the kernel's limiter) ONCE, and split-K (4 parts at 4096 rows: 32 tiles x 4 = 128 CTAs) fills the
+// SMs; 128 (R4_HEAD_BNT=128, the earlier default) converted every A row twice for 64 tiles x 2 K parts.
+static int head_bnt() {
+  static const int v = [] { const char* e = getenv("R4_HEAD_BNT"); int x = e ? atoi(e) : 256; return (x == 128 || x == 256) ? x : 256; }();
+  return v;
+}
+#define HEAD_BNT head_bnt()
 
 int gemm(r4_env* e, int slot, int act, int M, int N, int K, const float* A, int lda, const int32_t* gather,
          const uint8_t* Wimg, const float* bias, float* C, int ldc, cudaStream_t st, int tm_ns = 0, int cr_base = 0,
@@ -1220,7 +1227,7 @@ static int policy_grad_impl(int mode, const float* params, const float* obs, con
                             const float* old_logp, const float* old_logits, const float* old_value, const float* adv,
                             const float* target, const int64_t* idx, int n, int action_size, float clip, float vf_clip,
                             float vf_coeff, float kl_coeff, float ent_coeff, float inv_n, float* scratch, int G,
-                            float* flat_grad, float* stats_accum, float stat_scale, void* stream, bool reduce) {
+                            float* flat_grad, float* stats_accum, float stat_scale, void* stream, bool reduce, bool pdl = false) {
   if (!params || !obs || !mask || !action || !old_logits || !adv || !target || !scratch || !flat_grad || n < 1 ||
       G < 1 || action_size < 2 || action_size > 512 || (mode == 0 && (!old_logp || !old_value)))
     return fail(nullptr, R4_ERR_ARG, "r4_policy_grad: bad argument");
@@ -1240,7 +1247,14 @@ static int policy_grad_impl(int mode, const float* params, const float* obs, con
   }
   float* partial = scratch;
   float* stat_partial = scratch + (size_t)G * L.n;
-  if (single)
+  if (single && pdl) {
+    cudaLaunchConfig_t lc = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.gridDim = dim3(G); lc.blockDim = dim3(r4ppo::NT); lc.dynamicSmemBytes = smem; lc.stream = S(stream); lc.attrs = at; lc.numAttrs = 1;
+    cudaLaunchKernelEx(&lc, r4ppo::k_policy_grad<true>, L, hp, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, idx, n,
+                       partial, stat_partial);
+  } else if (single)
     r4ppo::k_policy_grad<true><<<G, r4ppo::NT, smem, S(stream)>>>(L, hp, params, obs, mask, action, old_logp, old_logits,
                                                                  old_value, adv, target, idx, n, partial, stat_partial);
   else
@@ -1296,13 +1310,23 @@ int r4_ppo_epoch(float* params, const float* obs, const uint8_t* mask, const int
   const int np = r4ppo::make_layout(action_size).n;
   int steps = 0;
   const bool fused = !(grad_clip > 0.f);      // global-norm clipping needs the reduced gradient first
+  // programmatic dependent launch for the grad / optimiser chain of the epoch (R4_NO_PDL=1: plain stream order)
+  static const bool pdl = getenv("R4_NO_PDL") == nullptr;
   if (!params || !m || !v || !flat_grad || !scratch) return fail(nullptr, R4_ERR_ARG, "r4_ppo_epoch: bad argument");
   for (int s = 0; s + mb <= n; s += mb, ++steps) {
     int rc = policy_grad_impl(0, params, obs, mask, action, old_logp, old_logits, old_value, adv, target, perm + s, mb,
                               action_size, clip, vf_clip, vf_coeff, kl_coeff, ent_coeff, 1.0f / mb, scratch, G, flat_grad,
-                              stats_accum, 1.0f / mb, stream, !fused);
+                              stats_accum, 1.0f / mb, stream, !fused, fused && pdl);
     if (rc) return rc;
-    if (fused) {
+    if (fused && pdl) {
+      cudaLaunchConfig_t lc = {};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+      lc.gridDim = dim3((np + 255) / 256); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = S(stream); lc.attrs = at; lc.numAttrs = 1;
+      cudaLaunchKernelEx(&lc, r4ppo::k_reduce_adam, np, G, (const float*)scratch, flat_grad, (const float*)(scratch + (size_t)G * np), stats_accum,
+                         1.0f / mb, params, m, v, step0 + steps + 1, lr, beta1, beta2, eps);
+      R4_PCHECK("k_reduce_adam");
+    } else if (fused) {
       r4ppo::k_reduce_adam<<<(np + 255) / 256, 256, 0, S(stream)>>>(np, G, scratch, flat_grad, scratch + (size_t)G * np, stats_accum,
                                                                     1.0f / mb, params, m, v, step0 + steps + 1, lr, beta1, beta2, eps);
       R4_PCHECK("k_reduce_adam");

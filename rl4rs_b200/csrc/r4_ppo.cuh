@@ -193,6 +193,12 @@ __global__ void __launch_bounds__(NT) k_policy_grad(Layout L, LossHyper hp, cons
                                                     const int64_t* __restrict__ idx, int n, float* __restrict__ partial,
                                                     float* __restrict__ stat_partial /*[grid,5]*/) {
   extern __shared__ __align__(16) float sm[];
+  // Programmatic dependent launch (r4_ppo_epoch launches its 288 kernels per epoch with
+  // cudaLaunchAttributeProgrammaticStreamSerialization): let the next kernel of the chain be scheduled while this one runs, and
+  // do not touch global memory before the previous one (the optimiser step that wrote `prm` and read `partial`) has completed.
+  // Both are no-ops for a plain launch.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   float* g_s = sm;                              // !SINGLE: [L.n] gradient accumulator; SINGLE: w1 | w2 copies
   const int head = SINGLE ? (OBS * HID + ((HID * L.A + 3) & ~3)) : ((L.n + 3) & ~3);
   float* obs_s = g_s + head;
@@ -427,6 +433,8 @@ __global__ void k_reduce_adam(int n, int G, const float* __restrict__ partial, f
                               const float* __restrict__ stat_partial, float* __restrict__ stats_accum, float stat_scale,
                               float* __restrict__ prm, float* __restrict__ m, float* __restrict__ v, int step, float lr,
                               float b1, float b2, float eps) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // see k_policy_grad
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float s = 0.f;
