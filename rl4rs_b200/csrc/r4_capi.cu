@@ -293,8 +293,8 @@ struct AugruOpts {
   int cost_pair = 13, cost_pp = 24;
   int cluster = 2;        // CTAs per cluster of the pair kernel: 2, or 4 / 8 = weight stream shared by 2 / 4 pairs (multicast)
   int scores_impl = 2;    // 2 = k_scores_tc2 (both attention layers on the tensor pipe), 1 = k_scores_tc (second layer as FFMA2)
-  int scores_shared_pct = 75;    // k_scores_tc2: CTA share of a shared (L2-resident) sequence, per cent of an even split (tools/scores_probe.cu:
-                                 // 100 % 96.5 us, 75 % 90.3 us, 60 % 109 us per 4096-row pass)
+  int scores_shared_pct = 85;    // k_scores_tc2: CTA share of a shared (L2-resident) sequence, per cent of an even split (tools/scores_probe.cu,
+                                 // us per 4096-row pass: 100 % 98.5, 85 % 86.8, 75 % 90.1, 65 % 100.6, 55 % 120.8)
   int pay_obs_reuse = 1;  // a paying step takes its observation from its reward pass (r4_step); 0 = separate observation pass
   AugruOpts() {
     if (getenv("R4_NO_PAY_OBS_REUSE")) pay_obs_reuse = 0;

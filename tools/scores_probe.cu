@@ -56,7 +56,8 @@ int main(int argc, char** argv) {
     if (which == 0) k_scores_tc<<<grid, S_THREADS, S_SMEM_BYTES>>>(p, nullptr, nullptr);
     else {
       const int ctas = std::min(2 * ((rows + 1) / 2), 148);
-      k_scores_tc2<false><<<ctas, S2_THREADS, S2_SMEM_BYTES>>>(p, scores_grid_split(ctas, (rows + 1) / 2, 0, 1, pct));
+      if (pct < 0) k_scores_tc2<false, true><<<ctas, S2_THREADS, S2_SMEM_BYTES>>>(p, scores_grid_split(ctas, (rows + 1) / 2, 0, 1, -pct));
+      else k_scores_tc2<false><<<ctas, S2_THREADS, S2_SMEM_BYTES>>>(p, scores_grid_split(ctas, (rows + 1) / 2, 0, 1, pct));
     }
   };
   // ---- correctness on RC rows (odd counts exercise the half-filled last tile), then on all R rows for the first / last rows
@@ -101,9 +102,10 @@ int main(int argc, char** argv) {
   printf("%s\n", bad_total ? "FAIL" : "PASS");
   // ---- timing
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-  for (int cfg = 0; cfg < 6; ++cfg) {
+  CK((cudaFuncSetAttribute(k_scores_tc2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2_SMEM_BYTES)));
+  for (int cfg = 0; cfg < 8; ++cfg) {
     const int which = cfg ? 1 : 0;
-    const int pcts[6] = {100, 100, 75, 60, 50, 40};
+    const int pcts[8] = {100, 100, 85, 75, 65, 55, 45, -75};    // negative: WITH the L2 prefetch probe switch
     pct = pcts[cfg];
     for (int i = 0; i < 3; ++i) launch(which, R);
     CK(cudaEventRecord(e0));
