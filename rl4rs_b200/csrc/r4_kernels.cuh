@@ -264,27 +264,54 @@ __global__ void __launch_bounds__(128) k_cat_attn(int R, const int32_t* __restri
   if (r >= R) return;
   const int32_t* crow = cat + (size_t)r * NCAT;
   float* out = allf + (size_t)r * ALLF_LD;
-  for (int j = 0; j < NCAT; ++j) {
-    float4 v = ldg4(emb_cat + (size_t)crow[j] * EMB + lane * 4);
-    *reinterpret_cast<float4*>(&e[j * CAT_LD + lane * 4]) = v;
+  {                                  // ids with one coalesced load, then all 21 row gathers in flight together
+    const int myid = lane < NCAT ? crow[lane] : 0;
+    float4 v[NCAT];
+#pragma unroll
+    for (int j = 0; j < NCAT; ++j) v[j] = ldg4(emb_cat + (size_t)__shfl_sync(0xffffffffu, myid, j) * EMB + lane * 4);
+#pragma unroll
+    for (int j = 0; j < NCAT; ++j) *reinterpret_cast<float4*>(&e[j * CAT_LD + lane * 4]) = v[j];
   }
   __syncwarp();
-  // S[t][j] = <e_t, e_j>, symmetric: 231 pairs spread over lanes
-  for (int pidx = lane; pidx < NCAT * (NCAT + 1) / 2; pidx += 32) {
-    int t = 0, rem = pidx;
-    while (rem >= NCAT - t) { rem -= NCAT - t; ++t; }
-    int j = t + rem;
-    float s = 0.f;
-    const float* a = e + t * CAT_LD;
-    const float* b = e + j * CAT_LD;
-#pragma unroll 8
+  // S[t][j] = <e_t, e_j>, symmetric.  The 21 rows form 7 groups of 3; lane b < 28 owns the 3 x 3 block (gi <= gj) of the group
+  // pair b: per 4 columns it reads 6 row quads (instead of 2 per PAIR in the first version: 462 128-bit shared loads per lane
+  // against 192 here -- the kernel sat on the shared-memory pipe) and feeds 9 accumulators.  Every dot product is still the
+  // same k-ascending fmaf chain, so the scores are bit-identical to the pair-per-lane form.
+  if (lane < 28) {
+    int gi = 0, rem = lane;
+    while (rem >= 7 - gi) { rem -= 7 - gi; ++gi; }
+    const int gj = gi + rem;
+    const float* a = e + 3 * gi * CAT_LD;
+    const float* b = e + 3 * gj * CAT_LD;
+    float acc[3][3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+      for (int y = 0; y < 3; ++y) acc[x][y] = 0.f;
+#pragma unroll 4
     for (int k = 0; k < EMB; k += 4) {
-      float4 x = *reinterpret_cast<const float4*>(a + k);
-      float4 y = *reinterpret_cast<const float4*>(b + k);
-      s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+      float4 av[3], bv[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        av[x] = *reinterpret_cast<const float4*>(a + x * CAT_LD + k);
+        bv[x] = *reinterpret_cast<const float4*>(b + x * CAT_LD + k);
+      }
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) {
+          float s = acc[x][y];
+          s = fmaf(av[x].x, bv[y].x, s); s = fmaf(av[x].y, bv[y].y, s); s = fmaf(av[x].z, bv[y].z, s); s = fmaf(av[x].w, bv[y].w, s);
+          acc[x][y] = s;
+        }
     }
-    Ssm[t * 24 + j] = s;
-    Ssm[j * 24 + t] = s;
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+      for (int y = 0; y < 3; ++y) {
+        Ssm[(3 * gi + x) * 24 + 3 * gj + y] = acc[x][y];
+        Ssm[(3 * gj + y) * 24 + 3 * gi + x] = acc[x][y];
+      }
   }
   __syncwarp();
   float wcol = 0.f;      // lane j accumulates sum_t P[t][j]

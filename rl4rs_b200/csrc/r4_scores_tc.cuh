@@ -98,11 +98,16 @@ __global__ void __launch_bounds__(128) k_query(int R, const int32_t* __restrict_
   const float b = __ldg((sq ? b11 : b10) + j);
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = b;
-#pragma unroll 4
-  for (int k = 0; k < S_K; ++k) {
-    float w = __ldg(W + k * S_N + j);
+  // 16 weight loads in flight per thread (with 4 the 128-long loop was 32 exposed L2 round trips; the kernel sits between
+  // k_assemble and k_scores_tc on the critical path of every pass)
+  for (int k0 = 0; k0 < S_K; k0 += 16) {
+    float w[16];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(q_s[i][k], w, acc[i]);
+    for (int u = 0; u < 16; ++u) w[u] = __ldg(W + (k0 + u) * S_N + j);
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(q_s[i][k0 + u], w[u], acc[i]);
   }
   float* o = sq ? qa1 : qa0;
 #pragma unroll
