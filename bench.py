@@ -29,7 +29,9 @@ JSON keys beyond the base contract:
             2*(256*512 + 256*256) against the measured sustained bf16 GEMM peak.
   hbm_8d    SURVEY.md section 8(d)'s own HBM figure: transitions/s x algorithmic bytes per transition
             (176 768 B Slate-9, 170 565 B Seq-27) / (N x measured HBM peak), for `value` and `env_only`.
-  cpu_baseline  the oracle port (oracle/env_np.py + dien_np.py) on this box's host cores, bounded sample.
+  cpu_baseline  the oracle port (oracle/env_np.py + dien_np.py, run by oracle/cpu_arm.py) on ALL host threads of this box:
+            one single-threaded worker process per host thread, the batch's rows spread over them (<= 128 each),
+            episodes started together; the same arm is `--impl reference`.
 """
 import argparse
 import json
@@ -50,7 +52,8 @@ UNIT = "transitions/s"
 BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}     # SURVEY.md section 8(d), dien: 83 732 B per row-forward
 G_DNN = 12564                                                   # dnn: algorithmic bytes per row-forward (section 8d)
 ROW_FORWARDS_PER_TRANSITION = {9: 19.0 / 9, 27: 55.0 / 27, 36: 73.0 / 36}
-CPU_THREADS = 16                                                # BLAS threads of the CPU arm (fixed: run-to-run spread)
+CPU_THREADS_PER_WORKER = 1                                      # CPU arm: one single-threaded worker process per host thread
+                                                                # (8 x 1 beats 1 x 8 BLAS threads 9-fold on these matrix sizes)
 
 
 def base_config(B, seq=False, max_steps=None, conti=False, simulator="dien"):
@@ -123,92 +126,70 @@ class ClockSampler(object):
         return out
 
 
-class _TimedDien(object):
-    """Wraps the oracle's network so the CPU arm can report its host-Python vs NN split."""
-
-    def __init__(self, dien):
-        self.d, self.nn_s = dien, 0.0
-
-    def _t(self, fn, feat):
-        t0 = time.perf_counter()
-        out = fn(feat)
-        self.nn_s += time.perf_counter() - t0
-        return out
-
-    def obs_layer(self, feat):
-        return self._t(self.d.obs_layer, feat)
-
-    def reward_layer(self, feat):
-        return self._t(self.d.reward_layer, feat)
+def cpu_arm_rows(batch, cap):
+    """Rows per worker and episode of the CPU arm: the whole batch spread over the workers, at most `cap` each."""
+    from oracle import cpu_arm
+    W, threads, _ = cpu_arm.plan(CPU_THREADS_PER_WORKER, _cpu_workers_cap())
+    return max(1, min(cap, -(-batch // W))), W, threads
 
 
-def cpu_reference_episodes(B, seq, log, catalog, weights, episodes, warmup, threads=CPU_THREADS, simulator="dien"):
-    """The reference's CPU path (oracle port; NumPy/OpenBLAS pinned to `threads` threads): offline-action replay
-    episodes of B rows.  -> dict(value tr/s from the MEDIAN episode, per-episode times, NN share, threads)."""
-    from oracle.dien_np import DienOracle
-    from oracle.dnn_np import DnnOracle
-    from oracle.env_np import OracleEnv
+def _cpu_workers_cap():
+    """One worker per host thread unless memory says otherwise (0.35 GB per worker: two 51 MB tables + the oracle)."""
     try:
-        from threadpoolctl import threadpool_limits
+        import psutil
+        return max(1, int(psutil.virtual_memory().available * 0.5 / 0.4e9))
     except Exception:
-        threadpool_limits = None
-    cfg = dict(base_config(B, seq), is_eval=False, cache_size=min(2048, log.n))
-    threads = max(1, min(threads, os.cpu_count() or 1))
-    T = cfg["max_steps"]
+        return None
 
-    def run():
-        np.random.seed(0)
-        net = _TimedDien((DnnOracle if simulator == "dnn" else DienOracle)(weights, np.float32))
-        env = OracleEnv(cfg, log, catalog, net, seq=seq)
-        times, nn = [], []
-        for ep in range(warmup + episodes):
-            net.nn_s = 0.0
-            t0 = time.perf_counter()
-            env.reset()
-            for _ in range(T):
-                env.step(env.offline_action)
-            if ep >= warmup:
-                times.append(time.perf_counter() - t0)
-                nn.append(net.nn_s)
-        return times, nn
 
-    if threadpool_limits is not None:
-        with threadpool_limits(limits=threads):
-            times, nn = run()
-    else:
-        times, nn = run()
-    med = float(np.median(times))
-    return {"value": B * T / med, "episode_s": [round(t, 3) for t in times], "median_s": med, "total_s": float(sum(times)),
-            "spread": float((max(times) - min(times)) / med) if med > 0 else 0.0,
-            "nn_share": float(sum(nn) / max(sum(times), 1e-9)), "threads": threads, "host_cores": os.cpu_count(),
-            "transitions_per_episode": B * T}
+def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=True, log=None, catalog=None, weights=None):
+    """The reference's CPU path (oracle port, oracle/cpu_arm.py): offline-action replay episodes.  parallel: one
+    single-threaded worker process per host thread, B rows each, episodes started together (value = W x B x T / median
+    episode); otherwise one process with all its BLAS threads (configs[0], batch 32, the README loop)."""
+    from oracle import cpu_arm
+    cfg = dict(base_config(B, seq), is_eval=False, cache_size=2048)
+    if parallel:
+        try:
+            return cpu_arm.run_parallel(cfg, seq, simulator, episodes, warmup, threads=CPU_THREADS_PER_WORKER,
+                                        workers=_cpu_workers_cap())
+        except Exception as e:                                # noqa: BLE001 -- e.g. no process spawning in a sandbox
+            sys.stderr.write("bench: parallel CPU arm failed (%s); single process\n" % e)
+    from rl4rs_b200 import synth
+    catalog = catalog or synth.make_catalog()
+    log = log or synth.make_log(max(4 * B, 2048), pages=4 if seq else 1, catalog=catalog)
+    if weights is None:
+        weights = synth.make_dnn_weights(cfg) if simulator == "dnn" else synth.make_weights(cfg)
+    return cpu_arm.run_single(cfg, log, catalog, weights, seq, simulator, episodes, warmup, threads=len(cpu_arm.host_cores()))
+
+
+def cpu_sample_text(r, batch):
+    return ("%d of %d env rows per step: %d worker processes x %d rows, one pinned BLAS thread group of %d per worker, "
+            "%d of %d host threads busy; one step = one offline-action replay episode = %d transitions; median of %d "
+            "episodes, spread (max-min)/median %.2f, NN share of the busy time %.2f"
+            % (r["rows_per_episode"], batch, r["workers"], r["rows_per_episode"] // r["workers"], r["threads_per_worker"],
+               r["threads"], r["host_cores"], r["transitions_per_episode"], len(r["episode_s"]), r["spread"], r["nn_share"]))
 
 
 def run_reference(args):
-    """--impl reference: the oracle port of the reference's CPU env; one step = one episode of a bounded row sample.
-    Also reports BASELINE configs[0] itself (batch 32, the README loop) over 3 episodes."""
+    """--impl reference: the oracle port of the reference's CPU env on every host thread; one step = one episode of
+    a bounded row sample of the batch (the whole batch when the box has enough threads).  Also reports BASELINE
+    configs[0] itself (batch 32, one process, the README loop) over 3 episodes."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from rl4rs_b200 import synth
     seq = args.env == "seqslate"
-    Bs = args.cpu_sample_rows
-    cat = synth.make_catalog()
-    log = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=cat)
-    w = synth.make_dnn_weights(base_config(Bs, seq)) if args.simulator == "dnn" else synth.make_weights(base_config(Bs, seq))
-    r = cpu_reference_episodes(Bs, seq, log, cat, w, max(args.steps, 1), max(args.warmup, 1), simulator=args.simulator)
-    c1 = cpu_reference_episodes(32, seq, log, cat, w, 3, 1, simulator=args.simulator)
-    T = base_config(Bs, seq)["max_steps"]
-    sample = ("%d of %d env rows per step (one offline-action replay episode = %d transitions); median of %d episodes, "
-              "spread (max-min)/median %.2f, NN share of the time %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"
-              % (Bs, args.batch_per_gpu, Bs * T, len(r["episode_s"]), r["spread"], r["nn_share"], r["threads"], r["host_cores"]))
+    rows, W, threads = cpu_arm_rows(args.batch_per_gpu, args.cpu_sample_rows)
+    r = cpu_reference_episodes(rows, seq, max(args.steps, 1), max(args.warmup, 1), simulator=args.simulator)
+    c1 = cpu_reference_episodes(32, seq, 3, 1, simulator=args.simulator, parallel=False)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["median_s"] * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, seq),
-            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port", "sample": sample,
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                             "sample": cpu_sample_text(r, args.batch_per_gpu),
                              "episode_s": r["episode_s"], "nn_share": r["nn_share"],
-                             "configs0_batch32": {"value": c1["value"], "episode_s": c1["episode_s"], "nn_share": c1["nn_share"]}},
+                             "configs0_batch32": {"value": c1["value"], "episode_s": c1["episode_s"], "nn_share": c1["nn_share"],
+                                                  "threads": c1["threads"]}},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -247,8 +228,10 @@ def emit(line):
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+_REAL_STDOUT = 1
+if __name__ == "__main__":                      # not when imported (tests, the CPU arm's worker processes)
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def main():
@@ -264,7 +247,7 @@ def main():
                     help="config['algo']: dien (BASELINE configs, tensor-bound) or dnn (nets/dnn.py, the gather-bound simulator)")
     ap.add_argument("--batch-per-gpu", type=int, default=None, help="default: 4096 at N=1, 8192 at N>1")
     ap.add_argument("--sgd-minibatch", type=int, default=None, help="PPO sgd_minibatch_size, TOTAL over GPUs (default 256 x N)")
-    ap.add_argument("--cpu-sample-rows", type=int, default=128)
+    ap.add_argument("--cpu-sample-rows", type=int, default=128, help="CPU arm: at most this many env rows per worker process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernels", action="store_true", help="also print a per-kernel time breakdown (stderr)")
     args = ap.parse_args()
@@ -471,13 +454,10 @@ def main():
         line["kernels"] = [{"name": k["name"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 4),
                             "launches": k["launches"]} for k in sorted(kernels, key=lambda k: -k["ms"])]
     if world == 1 and not args.no_cpu_baseline:
-        Bs = args.cpu_sample_rows
-        clog = synth.make_log(max(4 * Bs, 2048), pages=4 if seq else 1, catalog=catalog)
-        r = cpu_reference_episodes(Bs, seq, clog, catalog, weights, episodes=3, warmup=1, simulator=args.simulator)
+        rows, _, _ = cpu_arm_rows(B, args.cpu_sample_rows)
+        r = cpu_reference_episodes(rows, seq, episodes=3, warmup=1, simulator=args.simulator)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                                "sample": "median of 3 offline-replay episodes of %d env rows (%d transitions each) after 1 warm-up, "
-                                          "%.1f s, spread %.2f, NN share %.2f, NumPy/OpenBLAS pinned to %d of %d host threads"
-                                          % (Bs, Bs * T, r["total_s"], r["spread"], r["nn_share"], r["threads"], r["host_cores"]),
+                                "sample": cpu_sample_text(r, B) + "; %.1f s timed" % r["total_s"],
                                 "episode_s": r["episode_s"], "nn_share": r["nn_share"]}
     emit(line)
     if world > 1:

@@ -1,0 +1,173 @@
+"""TEST / MEASUREMENT INFRASTRUCTURE ONLY -- the CPU arm of bench.py (`--impl reference` and `cpu_baseline`).
+
+Runs the oracle port of the reference's CPU env (oracle/env_np.py + dien_np.py / dnn_np.py) on ALL host cores the way
+the reference itself scales on CPU: by processes over independent env rows (its RLlib rollout workers / HTTP env
+servers, `script/modelfree_train.py:179-217`, are one process per env batch).  W worker processes, each pinned to its
+own block of `threads` cores (sched_setaffinity + a BLAS thread limit), each replaying offline-action episodes of
+`rows` env rows of its own log slice; the episodes start together behind a barrier, an episode's time is the slowest
+worker's, the arm's throughput is W x rows x max_steps / median episode time.
+
+Nothing under rl4rs_b200/ imports this module.
+"""
+import multiprocessing as mp
+import os
+import time
+
+import numpy as np
+
+
+class _TimedNet(object):
+    """Wraps the oracle's network so the arm can report its host-Python vs NN split."""
+
+    def __init__(self, net):
+        self.d, self.nn_s = net, 0.0
+
+    def _t(self, fn, feat):
+        t0 = time.perf_counter()
+        out = fn(feat)
+        self.nn_s += time.perf_counter() - t0
+        return out
+
+    def obs_layer(self, feat):
+        return self._t(self.d.obs_layer, feat)
+
+    def reward_layer(self, feat):
+        return self._t(self.d.reward_layer, feat)
+
+
+def _episodes(cfg, log, catalog, weights, seq, simulator, episodes, warmup, sync=None):
+    from oracle.dien_np import DienOracle
+    from oracle.dnn_np import DnnOracle
+    from oracle.env_np import OracleEnv
+    np.random.seed(0)
+    net = _TimedNet((DnnOracle if simulator == "dnn" else DienOracle)(weights, np.float32))
+    env = OracleEnv(cfg, log, catalog, net, seq=seq)
+    T = cfg["max_steps"]
+    t_begin, t_end, nn = [], [], []
+    for ep in range(warmup + episodes):
+        net.nn_s = 0.0
+        if sync is not None:
+            sync()
+        t0 = time.time()
+        env.reset()
+        for _ in range(T):
+            env.step(env.offline_action)
+        t1 = time.time()
+        if ep >= warmup:
+            t_begin.append(t0); t_end.append(t1); nn.append(net.nn_s)
+    return t_begin, t_end, nn
+
+
+def _limit_threads(threads):
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=threads)
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def _worker(idx, cores, spec, barrier, out):
+    try:
+        if cores:
+            try:
+                os.sched_setaffinity(0, cores)
+            except Exception:
+                pass
+        from rl4rs_b200 import synth
+        cfg = spec["cfg"]
+        catalog = synth.make_catalog()
+        log = synth.make_log(spec["n_log"], pages=4 if spec["seq"] else 1, catalog=catalog, seed=synth.LOG_SEED + idx)
+        weights = synth.make_dnn_weights(cfg) if spec["simulator"] == "dnn" else synth.make_weights(cfg)
+        with _limit_threads(spec["threads"]):
+            res = _episodes(cfg, log, catalog, weights, spec["seq"], spec["simulator"], spec["episodes"], spec["warmup"],
+                            sync=lambda: barrier.wait(timeout=spec["timeout_s"]))
+        out.put((idx, res, None))
+    except Exception as e:                                   # noqa: BLE001 -- reported to the parent, which falls back
+        try:
+            barrier.abort()
+        except Exception:
+            pass
+        out.put((idx, None, "%s: %s" % (type(e).__name__, e)))
+
+
+def host_cores():
+    try:
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return list(range(os.cpu_count() or 1))
+
+
+def plan(threads=None, workers=None):
+    """-> (workers, threads per worker, core blocks).  Default: blocks of 4 cores, every core used."""
+    cores = host_cores()
+    n = len(cores)
+    threads = max(1, min(threads or 4, n))
+    workers = max(1, min(workers or n // threads, n // threads))
+    return workers, threads, [cores[w * threads:(w + 1) * threads] for w in range(workers)]
+
+
+def _summary(B, T, workers, threads, ep_s, nn_share, n_cores, note=None):
+    med = float(np.median(ep_s))
+    out = {"value": workers * B * T / med, "episode_s": [round(t, 3) for t in ep_s], "median_s": med,
+           "total_s": float(sum(ep_s)), "spread": float((max(ep_s) - min(ep_s)) / med) if med > 0 else 0.0,
+           "nn_share": nn_share, "workers": workers, "threads_per_worker": threads, "threads": workers * threads,
+           "host_cores": n_cores, "rows_per_episode": workers * B, "transitions_per_episode": workers * B * T}
+    if note:
+        out["note"] = note
+    return out
+
+
+def run_single(cfg, log, catalog, weights, seq, simulator, episodes, warmup, threads):
+    """One process, `threads` BLAS threads: configs[0] (batch 32) and the fallback."""
+    threads = max(1, min(threads, len(host_cores())))
+    with _limit_threads(threads):
+        t0, t1, nn = _episodes(cfg, log, catalog, weights, seq, simulator, episodes, warmup)
+    ep = [b - a for a, b in zip(t0, t1)]
+    return _summary(cfg["batch_size"], cfg["max_steps"], 1, threads, ep, float(sum(nn) / max(sum(ep), 1e-9)),
+                    len(host_cores()))
+
+
+def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=None, timeout_s=900.0):
+    """All host cores: W processes x `threads` cores, cfg['batch_size'] rows per worker and episode."""
+    W, threads, blocks = plan(threads, workers)
+    B, T = cfg["batch_size"], cfg["max_steps"]
+    spec = {"cfg": cfg, "seq": seq, "simulator": simulator, "episodes": episodes, "warmup": warmup,
+            "threads": threads, "n_log": max(4 * B, 2048), "timeout_s": timeout_s}
+    ctx = mp.get_context("spawn")
+    barrier, out = ctx.Barrier(W), ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(w, blocks[w], spec, barrier, out), daemon=True) for w in range(W)]
+    # the children size their BLAS pools when numpy loads: tell them before they start (W x host_cores threads otherwise)
+    names = ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS")
+    saved = {k: os.environ.get(k) for k in names}
+    os.environ.update({k: str(threads) for k in names})
+    try:
+        for p in procs:
+            p.start()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    results, err = {}, None
+    try:
+        for _ in range(W):
+            idx, res, e = out.get(timeout=timeout_s)
+            if e is not None:
+                err = err or "worker %d: %s" % (idx, e)
+            else:
+                results[idx] = res
+    except Exception as e:                                   # noqa: BLE001 -- queue timeout
+        err = "no result within %.0f s (%s)" % (timeout_s, type(e).__name__)
+    for p in procs:
+        p.join(timeout=5)
+        if p.is_alive():
+            p.terminate()
+    if err is not None or len(results) != W:
+        raise RuntimeError(err or "a worker died")
+    # episode e: from the first worker's start to the last worker's end (they start together behind the barrier)
+    ep = [max(results[w][1][e] for w in range(W)) - min(results[w][0][e] for w in range(W)) for e in range(episodes)]
+    busy = sum(b - a for w in range(W) for a, b in zip(results[w][0], results[w][1]))
+    nn = sum(sum(results[w][2]) for w in range(W))
+    return _summary(B, T, W, threads, ep, float(nn / max(busy, 1e-9)), len(host_cores()))
