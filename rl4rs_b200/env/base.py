@@ -214,83 +214,85 @@ class RecSimBase(ABC):
         return samples, obs
 
 
+def build_spaces(config, obs_dim):
+    """(observation_space, action_space) of an env, from the CONFIG alone.  The reference measures the first sampled
+    observation (base.py:188-217); here the widths are configuration (the feature rows live in HBM and a 'torch' /
+    'numpy' observation is one array per field, not a list of rows), the bounds and the key layout are the reference's:
+    raw-state fields or one `obs` vector, wrapped with `action_mask` for RLlib; a Box of action_emb_size for the
+    continuous env (base.py:214-215), Discrete(action_size) otherwise."""
+    box, n_actions = gym.spaces.Box, config["action_size"]
+    if config.get("rawstate_as_obs", False):
+        fields = {"category_feature": (config.get("category_feature_num", 21),),
+                  "dense_feature": (config.get("dense_feature_num", 432),),
+                  "sequence_feature": (config.get("seq_num", 2), config.get("maxlen", 64))}
+        parts = {name: box(-1000000.0, 1000000.0, shape=shape) for name, shape in fields.items()}
+    else:
+        parts = {"obs": box(-100000.0, 100000.0, shape=(obs_dim,))}
+    if config.get("support_rllib_mask", False):
+        observation = gym.spaces.Dict(dict({"action_mask": box(0, 1, shape=(n_actions,))}, **parts))
+    else:
+        observation = gym.spaces.Dict(parts) if "obs" not in parts else parts["obs"]
+    if config.get("support_conti_env", False):
+        action = box(-1, 1, shape=(config["action_emb_size"],))
+    else:
+        action = gym.spaces.Discrete(n_actions)
+    return observation, action
+
+
+class _PerEnvValue(object):
+    """Read-only env attribute holding one value per env row; a batch of one hands out the bare element
+    (the reference stacks @property on @single_elem_support four times, base.py:236-254)."""
+
+    def __init__(self, source, doc):
+        self._read = single_elem_support(source)
+        self.__doc__ = doc
+
+    def __get__(self, env, owner=None):
+        return self if env is None else self._read(env)
+
+    def __set__(self, env, value):
+        raise AttributeError("read-only: %s" % self.__doc__)
+
+
 class RecEnvBase(gym.Env):
-    """gym env over a RecSimBase (base.py:178-273); registered as SlateRecEnv-v0 / SeqSlateRecEnv-v0."""
+    """gym env over a RecSimBase (base.py:178-273); registered as SlateRecEnv-v0 / SeqSlateRecEnv-v0.
+    One env object = `batch_size` env rows stepping in lock-step on one GPU."""
 
     metadata = {"render.modes": ["human"]}
 
+    state = _PerEnvValue(lambda env: env.obs, "observation of the last reset (base.py:236-239)")
+    user_id = _PerEnvValue(lambda env: env.samples.user, "session ids of the sampled rows (base.py:241-244)")
+    offline_action = _PerEnvValue(lambda env: env.samples.offline_action, "the logged action of this step (base.py:246-249)")
+    offline_reward = _PerEnvValue(lambda env: env.samples.offline_reward, "the logged reward of this step (base.py:251-254)")
+
     def __init__(self, recsim):
-        self.config = recsim.config
+        self.sim, self.config = recsim, recsim.config
         self.batch_size = self.config["batch_size"]
+        self.observation_space, self.action_space = build_spaces(self.config, getattr(recsim, "obs_dim", 256))
+        # the reference draws TWO batches while constructing (base.py:186-187 to size its spaces, then :230) and callers'
+        # seeds / file cursors depend on that (SURVEY Q19): keep both draws although the spaces no longer need the first
+        self._draw(False)
+        self.reset()
+
+    def _draw(self, reset_file):
         self.cur_step = 0
-        self.sim = recsim
-        self.sim.reset()                                              # base.py:186-187 (Q19)
+        self.sim.reset(reset_file)
         self.samples, self.obs = self.sim.sample(self.batch_size)
-        spaces = gym.spaces
-        rllib = self.config.get("support_rllib_mask", False)
-        A = self.config["action_size"]
-        if self.config.get("rawstate_as_obs", False):
-            features = {
-                "category_feature": spaces.Box(-1000000.0, 1000000.0, shape=(self.config.get("category_feature_num", 21),)),
-                "dense_feature": spaces.Box(-1000000.0, 1000000.0, shape=(self.config.get("dense_feature_num", 432),)),
-                "sequence_feature": spaces.Box(-1000000.0, 1000000.0,
-                                               shape=(self.config.get("seq_num", 2), self.config.get("maxlen", 64))),
-            }
-            if rllib:
-                self.observation_space = spaces.Dict({"action_mask": spaces.Box(0, 1, shape=(A,)), **features})
-            else:
-                self.observation_space = spaces.Dict(features)
-        else:
-            obs_dim = self.sim.obs_dim
-            if rllib:
-                self.observation_space = spaces.Dict({
-                    "action_mask": spaces.Box(0, 1, shape=(A,)),
-                    "obs": spaces.Box(-100000.0, 100000.0, shape=(obs_dim,))})
-            else:
-                self.observation_space = spaces.Box(-100000.0, 100000.0, shape=(obs_dim,))
-        if self.config.get("support_conti_env", False):
-            self.action_space = spaces.Box(-1, 1, shape=(self.config["action_emb_size"],))
-        else:
-            self.action_space = spaces.Discrete(A)
-        self.reset()                                                  # base.py:230
 
     def seed(self, sd=0):
         self.sim.seed(sd)
         np.random.seed(sd)
 
-    @property
-    @single_elem_support
-    def state(self):
-        return self.obs
-
-    @property
-    @single_elem_support
-    def user_id(self):
-        return self.samples.user
-
-    @property
-    @single_elem_support
-    def offline_action(self):
-        return self.samples.offline_action
-
-    @property
-    @single_elem_support
-    def offline_reward(self):
-        return self.samples.offline_reward
+    def reset(self, reset_file=False):
+        self._draw(reset_file)
+        return self.state
 
     @single_elem_support
     def step(self, action):
-        if not isinstance(action, (list, np.ndarray)) and not hasattr(action, "is_cuda"):
-            action = [action]
-        obs, reward, done, info = self.sim._step(self.samples, action, step=self.cur_step)
+        batched = isinstance(action, (list, np.ndarray)) or hasattr(action, "is_cuda")      # device tensors pass through
+        result = self.sim._step(self.samples, action if batched else [action], step=self.cur_step)
         self.cur_step += 1
-        return obs, reward, done, info
-
-    def reset(self, reset_file=False):
-        self.cur_step = 0
-        self.sim.reset(reset_file)
-        self.samples, self.obs = self.sim.sample(self.batch_size)
-        return self.state
+        return tuple(result)                                      # (obs, reward, done, info)
 
     def render(self, mode="human", close=False):
         print("Current State:", "\n")
