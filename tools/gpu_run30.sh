@@ -1,5 +1,7 @@
 #!/bin/bash
-# round-2 GPU call 30: persistent k_policy_act with shared-memory weights, k_reduce_adam with 16 loads in flight: trainer / parity tests,
+# round-2 GPU call 30 (the last one of the round): k_reduce_adam with 16 loads in flight: trainer / parity tests,
+# (the call also A/B-measured a persistent k_policy_act variant, R4_ACT_NO_WS below; that variant was never committed -- the session ended
+# first -- and is NOT in the tree: the env var is inert, both lines time the committed kernel)
 # then the bench lines of the round on the final kernels (default + CPU arm, batch 8192, configs[2] SeqSlate A2C 16384, configs[3] conti 8192,
 # the dnn simulator at 65 536 rows)
 mkdir -p gpurun_out
