@@ -9,7 +9,9 @@ fixture for this arithmetic and its third-party halves ar
   * tensorflow-gpu==1.15.0 (environment.yml:214): Embedding / Attention / Dense / ELU /
     GlobalAveragePooling1D, call sites rl4rs/nets/utils.py:20-25,50-53,113 and rl4rs/nets/dien.py:35-36.
 The published algorithms of those layers are restated here and anchored on the reference's own
-call sites.  The integer/state-machine half of the path IS pinned (tests/golden, made by the
+call sites.  The WIRING of the graph (below) is pinned: tests/test_reference_graph.py holds this oracle to
+what the reference's own rl4rs/nets/dien.py + utils.py compute when run over the eager layer stand-ins of
+oracle/tf_eager_stub.py (tests/golden/nets_reference_graph.npz); the arithmetic inside the third-party layers is not.  The integer/state-machine half of the path IS pinned (tests/golden, made by the
 reference's own code through oracle/ref_harness.py).
 
 Graph (rl4rs/nets/dien.py:8-45):

@@ -1,0 +1,102 @@
+"""CPU: the simulator graphs as the REFERENCE'S OWN code wires them (rl4rs/nets/*.py run through oracle/tf_eager_stub.py,
+vectors committed by tests/golden/make_nets_golden.py) against (i) the NumPy oracles the GPU tests compare with and
+(ii) the variable-scope plans of the TF1 checkpoint reader.  Pins wiring and scope order, not the third-party layer
+arithmetic (see the stub's header)."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import make_nets_golden as mk                                   # noqa: E402
+
+from oracle import ref_harness                                  # noqa: E402
+from oracle.dien_np import DienOracle                           # noqa: E402
+from oracle.dnn_np import DnnOracle                             # noqa: E402
+from oracle.lstm_np import LstmOracle                           # noqa: E402
+from oracle.widedeep_np import WideDeepOracle                   # noqa: E402
+from rl4rs_b200.utils import tf_checkpoint as tfc               # noqa: E402
+
+ORACLES = {"dien": DienOracle, "dnn": DnnOracle, "widedeep": WideDeepOracle, "lstm": LstmOracle}
+PLANS = {"dien": tfc.dien_layer_plan, "dnn": tfc.dnn_layer_plan, "widedeep": tfc.widedeep_layer_plan, "lstm": tfc.lstm_layer_plan}
+
+
+@pytest.fixture(scope="module")
+def golden():
+    g = np.load(os.path.join(os.path.dirname(mk.__file__), "nets_reference_graph.npz"))
+    return g, json.loads(str(g["meta"]))
+
+
+@pytest.mark.parametrize("case", sorted(mk.CASES))
+def test_oracle_reproduces_what_the_reference_graph_code_computes(golden, case):
+    g, _ = golden
+    algo = mk.CASES[case][0]
+    w, _ = mk.checkpoint_of(case)
+    obs, probs = ORACLES[algo](w, np.float64).forward(g["seq"], g["dense"], g["cat"])
+    ref_obs, ref_probs = g[case + "_obs"], g[case + "_probs"]
+    assert obs.shape == ref_obs.shape and probs.shape == ref_probs.shape == (len(g["cat"]), 2)
+    np.testing.assert_allclose(obs, ref_obs, rtol=0, atol=1e-11 * max(1.0, np.abs(ref_obs).max()))
+    np.testing.assert_allclose(probs, ref_probs, rtol=0, atol=1e-12)
+    # the f32 oracle (what the CUDA path is held to at 1e-4) sits at f32 rounding of the same vectors
+    o32, p32 = ORACLES[algo](w, np.float32).forward(g["seq"], g["dense"], g["cat"])
+    rms = np.sqrt((ref_obs ** 2).mean(-1, keepdims=True))
+    assert (np.abs(o32 - ref_obs) / np.maximum(np.abs(ref_obs), rms)).max() < 3e-5
+    assert np.abs(p32 - ref_probs).max() < 1e-5
+
+
+@pytest.mark.parametrize("case", sorted(mk.CASES))
+def test_checkpoint_plan_follows_the_reference_creation_order(golden, case):
+    """Keras names layers in construction order; the scopes the reader expects must be the
+    ones the reference's code brings into existence, in that order, with those shapes."""
+    _, meta = golden
+    algo = mk.CASES[case][0]
+    created = [(s, tuple(sh)) for s, _, sh in meta[case]["variables"]]
+    plan = [(scope, tuple(shape)) for _, scope, shape in PLANS[algo](mk.SMALL)]
+    if algo == "dnn":                                            # the reader skips the embedding that feeds nothing
+        assert ("embedding_1", (600, 128)) in created
+        created.remove(("embedding_1", (600, 128)))
+    dedupe = lambda seq: [x for i, x in enumerate(seq) if i == 0 or x != seq[i - 1]]
+    assert dedupe([s for s, _ in created]) == dedupe([s for s, _ in plan])
+    assert sorted(created) == sorted(plan)                       # every scope owns exactly the planned shapes
+    names = {n for _, n, _ in meta[case]["variables"]}
+    expect = getattr(tfc, mk.CASES[case][3])(mk.SMALL)
+    assert set(expect.values()) <= names
+    layers = meta[case]["layers"]
+    assert sum("simulator_obs" in l for l in layers) == 1 and sum("simulator_reward" in l for l in layers) == 1
+
+
+def test_checkpoint_file_feeds_the_reference_graph(golden, tmp_path):
+    """n1 end to end: W-table -> Saver-format bundle on disk -> TensorBundleReader -> the reference's graph code."""
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree absent")
+    from oracle import tf_eager_stub as stub
+    g, _ = golden
+    w, _ = mk.checkpoint_of("dien_stress")
+    rd = tfc.TensorBundleReader(tfc.save_dien_checkpoint(str(tmp_path / "sim"), w, mk.SMALL))
+    ck = {name: rd.get_tensor(name) for name in rd.variables()}
+    r = stub.run_reference_graph("dien", mk.NETS_CONFIG, ck, g["seq"].astype(np.float32), g["dense"], g["cat"])
+    assert not r["unused"]
+    np.testing.assert_array_equal(r["obs"], g["dien_stress_obs"])
+
+
+@pytest.mark.parametrize("case", sorted(mk.CASES))
+def test_committed_vectors_are_what_the_reference_code_computes_now(golden, case):
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree absent")
+    from oracle import tf_eager_stub as stub
+    g, meta = golden
+    _, ck = mk.checkpoint_of(case)
+    r = stub.run_reference_graph(mk.CASES[case][0], mk.NETS_CONFIG, ck, g["seq"].astype(np.float32), g["dense"], g["cat"])
+    np.testing.assert_allclose(r["obs"], g[case + "_obs"], rtol=0, atol=1e-13 * max(1.0, np.abs(r["obs"]).max()))
+    assert [[s, n, list(sh)] for s, n, sh in r["variables"]] == meta[case]["variables"] and r["layers"] == meta[case]["layers"]
+
+
+def test_the_check_has_teeth(golden):
+    """A mis-wired weight set (the two embedding tables swapped) must not reproduce the vectors."""
+    g, _ = golden
+    w, _ = mk.checkpoint_of("dien_stress")
+    w = dict(w, emb_cat=w["emb_seq"], emb_seq=w["emb_cat"])
+    obs, _ = DienOracle(w, np.float64).forward(g["seq"], g["dense"], g["cat"])
+    assert np.abs(obs - g["dien_stress_obs"]).max() > 1e-3
