@@ -11,7 +11,7 @@ fixture for this arithmetic and its third-party halves ar
 The published algorithms of those layers are restated here and anchored on the reference's own
 call sites.  The WIRING of the graph (below) is pinned: tests/test_reference_graph.py holds this oracle to
 what the reference's own rl4rs/nets/dien.py + utils.py compute when run over the eager layer stand-ins of
-oracle/tf_eager_stub.py (tests/golden/nets_reference_graph.npz); the arithmetic inside the third-party layers is not.  The integer/state-machine half of the path IS pinned (tests/golden, made by the
+oracle/tf_eager_stub.py (tests/golden/nets/reference_graph.npz); the arithmetic inside the third-party layers is not.  The integer/state-machine half of the path IS pinned (tests/golden, made by the
 reference's own code through oracle/ref_harness.py).
 
 Graph (rl4rs/nets/dien.py:8-45):

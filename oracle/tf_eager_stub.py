@@ -12,7 +12,7 @@ in a TF1 checkpoint (a {variable name: array} dict) under the names Keras would 
     layers in construction order inside the fresh graph of base.py:119-121 -- the ORDER in which the variable scopes
     `embedding`, `dense_1`, `dynamic_gru_3`, `gru_2` ... come to exist.  That checks the restated graphs in
     oracle/{dien,dnn,widedeep,lstm}_np.py and the scope table of rl4rs_b200/utils/tf_checkpoint.py against the
-    reference's real code (tests/test_reference_graph.py, tests/golden/nets_reference_graph.npz);
+    reference's real code (tests/test_reference_graph.py, tests/golden/nets/reference_graph.npz);
   * the LAYER ARITHMETIC below is still a restatement of the published third-party definitions (Keras 2.2.4-tf layers of
     TF 1.15; deepctr 0.9.0 `DynamicGRU`, `AttentionSequencePoolingLayer`, `LocalActivationUnit`, `DNN`,
     `VecAttGRUCell`; TF1 `GRUCell`), written a third time, layer by layer.  The simulator arithmetic therefore stays

@@ -1,4 +1,4 @@
-"""Generates tests/golden/nets_reference_graph.npz: what the REFERENCE'S OWN graph code (rl4rs/nets/{dien,dnn,widedeep,
+"""Generates tests/golden/nets/reference_graph.npz: what the REFERENCE'S OWN graph code (rl4rs/nets/{dien,dnn,widedeep,
 lstm}.py + nets/utils.py, run from /root/reference through oracle/tf_eager_stub.py) computes on seeded feature rows
 with the seeded synthetic weights, plus the variable scopes in the order that code creates them.
 
@@ -66,7 +66,7 @@ def main():
         meta[case] = {"algo": algo, "variables": [[s, n, list(sh)] for s, n, sh in r["variables"]], "layers": r["layers"]}
         print(case, r["obs"].shape, "variables", len(r["variables"]))
     out["meta"] = np.array(json.dumps(meta))
-    np.savez_compressed(os.path.join(HERE, "nets_reference_graph.npz"), **out)
+    np.savez_compressed(os.path.join(HERE, "nets", "reference_graph.npz"), **out)
 
 
 if __name__ == "__main__":

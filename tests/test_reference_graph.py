@@ -25,7 +25,7 @@ PLANS = {"dien": tfc.dien_layer_plan, "dnn": tfc.dnn_layer_plan, "widedeep": tfc
 
 @pytest.fixture(scope="module")
 def golden():
-    g = np.load(os.path.join(os.path.dirname(mk.__file__), "nets_reference_graph.npz"))
+    g = np.load(os.path.join(os.path.dirname(mk.__file__), "nets", "reference_graph.npz"))
     return g, json.loads(str(g["meta"]))
 
 
