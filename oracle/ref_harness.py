@@ -113,6 +113,13 @@ def install_stubs():
         tf.keras.preprocessing.sequence = mods["tensorflow.keras.preprocessing.sequence"]
         sys.modules["tensorflow"] = tf
         sys.modules.update(mods)
+    # a stand-in without a __spec__ breaks importlib.util.find_spec(name) for every later caller (torch._dynamo probes
+    # 'tensorflow' that way the first time an optimizer is built)
+    import importlib.machinery
+    for name, m in list(sys.modules.items()):
+        if getattr(m, "_r4_stub", False) or name.startswith(("gym.", "tensorflow.")):
+            if getattr(m, "__spec__", None) is None and isinstance(m, types.ModuleType):
+                m.__spec__ = importlib.machinery.ModuleSpec(name, None)
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     import rl4rs.env.base as ref_base  # noqa

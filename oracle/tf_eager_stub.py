@@ -22,6 +22,7 @@ Nothing under rl4rs_b200/ imports this module; /root/reference exists only in th
 """
 import contextlib
 import importlib
+import importlib.machinery
 import re
 import sys
 import types
@@ -306,7 +307,12 @@ def _modules():
     """sys.modules entries standing in for tensorflow / deepctr while the reference's nets code is imported and run."""
     layer_ns = {k: v for k, v in globals().items() if isinstance(v, type) and issubclass(v, Layer) and v is not Layer}
     layer_ns["Input"] = Input
-    mod = lambda name, **attrs: (lambda m: (m.__dict__.update(attrs), m)[1])(types.ModuleType(name))
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)       # importlib.util.find_spec(name) must not raise
+        m.__dict__.update(attrs)
+        return m
+
     layers = mod("tensorflow.keras.layers", **layer_ns)
     backend = mod("tensorflow.keras.backend",
                   get_session=lambda: types.SimpleNamespace(run=lambda *a, **k: None))
