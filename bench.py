@@ -134,12 +134,9 @@ def cpu_arm_rows(batch, cap):
 
 
 def _cpu_workers_cap():
-    """One worker per host thread unless memory says otherwise (0.35 GB per worker: two 51 MB tables + the oracle)."""
-    try:
-        import psutil
-        return max(1, int(psutil.virtual_memory().available * 0.5 / 0.4e9))
-    except Exception:
-        return None
+    """One worker per host thread unless the memory limit (RAM or cgroup) says otherwise."""
+    from oracle import cpu_arm
+    return cpu_arm.workers_cap()
 
 
 def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=True, log=None, catalog=None, weights=None):

@@ -66,7 +66,7 @@ class DienOracle:
 
     def __init__(self, weights, dtype=np.float32):
         self.dt = np.dtype(dtype)
-        self.w = {k: np.asarray(v).astype(self.dt) for k, v in weights.items()}
+        self.w = {k: np.asarray(v, dtype=self.dt) for k, v in weights.items()}      # no copy when the dtype already matches
 
     # -- utils.py:16-25 -------------------------------------------------------------------
     def category_feature(self, cat):

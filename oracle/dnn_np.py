@@ -33,7 +33,7 @@ class DnnOracle:
 
     def __init__(self, weights, dtype=np.float32):
         self.dt = np.dtype(dtype)
-        self.w = {k: np.asarray(v).astype(self.dt) for k, v in weights.items()}
+        self.w = {k: np.asarray(v, dtype=self.dt) for k, v in weights.items()}      # no copy when the dtype already matches
 
     def forward(self, seq, dense, cat):
         w = self.w
