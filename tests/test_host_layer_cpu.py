@@ -1,0 +1,123 @@
+"""CPU: the product's HOST layer (rl4rs_b200/env/{base,slate,seqslate}.py, gymshim, sampler, output formats) end to end
+against the fixtures made by the reference's own env code -- with the device engine replaced by an oracle-backed
+stand-in (tests/oracle_engine.py).  The GPU suite runs the same replay through the CUDA library
+(tests/test_gpu_parity.py::test_cuda_env_matches_reference_fixture); this one keeps the Python half honest on boxes
+without a GPU.  Integers bit-exact; observations / rewards at the oracle's own f32 distance from the fixtures."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, golden_names, assert_close_rel
+from oracle_engine import OracleEngine
+
+
+@pytest.fixture()
+def oracle_engine(monkeypatch):
+    import rl4rs_b200.engine as engine_mod
+    monkeypatch.setattr(engine_mod, "Engine", OracleEngine)
+
+
+def make_env(cfg, seq, catalog, log, weights, **extra):
+    from rl4rs_b200 import gymshim
+    from rl4rs_b200.env.slate import SlateRecEnv, SlateState
+    from rl4rs_b200.env.seqslate import SeqSlateRecEnv, SeqSlateState
+    cfg = dict(cfg, catalog=catalog, log=log, weights=weights, **extra)
+    if seq:
+        return gymshim.make("SeqSlateRecEnv-v0", recsim=SeqSlateRecEnv(cfg, state_cls=SeqSlateState))
+    return gymshim.make("SlateRecEnv-v0", recsim=SlateRecEnv(cfg, state_cls=SlateState))
+
+
+def obs_arrays(obs):
+    if isinstance(obs, list) and isinstance(obs[0], dict):
+        return {k: np.stack([np.asarray(o[k]) for o in obs]) for k in obs[0]}
+    if isinstance(obs, dict):
+        return {k: np.asarray(v) for k, v in obs.items()}
+    return {"obs": np.asarray(obs)}
+
+
+def host(x):
+    return x.numpy() if hasattr(x, "is_cuda") else np.asarray(x)
+
+
+@pytest.mark.parametrize("fmt", ["list", "numpy", "torch"])
+@pytest.mark.parametrize("name", golden_names())
+def test_host_layer_replays_reference_fixture(oracle_engine, name, fmt):
+    g = Golden(name)
+    cfg, a = g.config, g.arr
+    if fmt != "list" and name not in ("slate_rllib_replay", "seqslate36_d3rl_conti", "slate_rawstate_replay", "slate_plain_random"):
+        pytest.skip("array formats checked on four fixtures (one per observation layout)")
+    if "np_seed" in g.meta:
+        np.random.seed(g.meta["np_seed"])
+    env = make_env(cfg, g.seq, g.catalog, g.log, g.weights, output_format=fmt)
+    assert env.observation_space is not None and env.action_space is not None
+    T, k = cfg["max_steps"], 0
+    for ep in range(g.n_episodes):
+        obs = env.reset()
+        if fmt == "torch" and not isinstance(obs, dict):
+            obs = {"obs": host(obs)}
+        obs = obs_arrays({k_: host(v) for k_, v in obs.items()} if isinstance(obs, dict) else obs)
+        np.testing.assert_array_equal(np.asarray([int(u) for u in env.user_id]), a["reset_user"][ep])
+        for key, val in obs.items():
+            ref = a["reset_" + key][ep]
+            if key == "obs":
+                assert_close_rel(val, ref, what="host %s reset obs" % name)
+            else:
+                np.testing.assert_array_equal(val, ref, err_msg="reset " + key)
+        for t in range(T):
+            np.testing.assert_array_equal(host(env.offline_action), a["offline_action"][k], err_msg="offline_action %d" % k)
+            obs, reward, done, info = env.step(a["action_in"][k])
+            if fmt == "torch" and not isinstance(obs, dict):
+                obs = {"obs": host(obs)}
+            obs = obs_arrays({k_: host(v) for k_, v in obs.items()} if isinstance(obs, dict) else obs)
+            np.testing.assert_array_equal(env.samples.prev_actions, a["prev_actions"][k])
+            np.testing.assert_array_equal(env.samples.get_violation(), a["violation"][k])
+            np.testing.assert_array_equal(host(done), a["done"][k])
+            for key, val in obs.items():
+                ref = a["step_" + key][k]
+                if key == "obs":
+                    assert_close_rel(val, ref, what="host %s obs step %d" % (name, k))
+                else:
+                    np.testing.assert_array_equal(val, ref, err_msg="%s step %d" % (key, k))
+            assert_close_rel(np.asarray(host(reward), dtype=np.float64), a["reward"][k], what="host %s reward step %d" % (name, k))
+            assert_close_rel(np.asarray(host(env.offline_reward), dtype=np.float64), a["offline_reward"][k], rtol=1e-12,
+                             what="host offline_reward")
+            if "click_p" in a and t == T - 1:
+                cp = np.stack([i["click_p"] for i in info]) if isinstance(info, list) else info["click_p"]
+                assert_close_rel(cp, a["click_p"][ep], what="host click_p")
+            k += 1
+        with pytest.raises(Exception):
+            env.step(a["action_in"][k - 1])
+
+
+def test_batch_size_one_in_every_format(oracle_engine):
+    """base.py:9-23: a batch of one hands out bare elements -- in the list format (the reference's), and element by
+    element in the array formats (advisor finding of round 1)."""
+    g = Golden("slate_rllib_replay")
+    for fmt in ("list", "numpy", "torch"):
+        cfg = dict(g.config, batch_size=1, cache_size=1, is_eval=True)
+        env = make_env(cfg, g.seq, g.catalog, g.log, g.weights, output_format=fmt)
+        obs = env.reset()
+        assert isinstance(obs, dict) and tuple(obs["obs"].shape) == (256,) and tuple(obs["action_mask"].shape) == (284,)
+        a = env.offline_action
+        assert np.ndim(host(a)) == 0
+        obs, reward, done, info = env.step(a)
+        assert tuple(obs["obs"].shape) == (256,) and np.ndim(host(reward)) == 0 and int(host(done)) == 0
+        assert isinstance(info, dict)
+        assert env.cur_step == 1 and isinstance(env.user_id, str)
+
+
+def test_custom_obs_fn_plugin_reads_the_raw_state_rows(oracle_engine):
+    """base.py:160,174: a RecSimBase subclass with its own obs_fn(state) gets the reference's raw 6-field rows."""
+    from rl4rs_b200 import gymshim
+    from rl4rs_b200.env.slate import SlateRecEnv, SlateState
+
+    class RawRowsEnv(SlateRecEnv):
+        def obs_fn(self, state):
+            rows = state["state"]
+            return [[len(r), int(np.sum(r[3])), float(np.sum(r[2]))] for r in rows]
+
+    g = Golden("slate_rllib_replay")
+    cfg = dict(g.config, catalog=g.catalog, log=g.log, weights=g.weights)
+    env = gymshim.make("SlateRecEnv-v0", recsim=RawRowsEnv(cfg, state_cls=SlateState))
+    env.reset()
+    obs, _, _, _ = env.step(g.arr["action_in"][0])
+    assert len(obs) == cfg["batch_size"] and all(o[0] == 6 for o in obs)
