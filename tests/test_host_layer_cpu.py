@@ -121,3 +121,29 @@ def test_custom_obs_fn_plugin_reads_the_raw_state_rows(oracle_engine):
     env.reset()
     obs, _, _, _ = env.step(g.arr["action_in"][0])
     assert len(obs) == cfg["batch_size"] and all(o[0] == 6 for o in obs)
+
+
+@pytest.mark.parametrize("seq,conti", [(False, False), (False, True), (True, False)])
+def test_dataset_writer_host_loop(oracle_engine, seq, conti, tmp_path):
+    """n2 (batchrl_trainer.py:172-320): rl4rs_b200/dataset.py's rollout / shuffle / flatten over the stand-in engine
+    against the same loop written over the oracle env (the GPU twin is tests/test_gpu_dataset.py)."""
+    from test_gpu_dataset import _oracle_dataset
+    from test_gpu_parity import _synthetic
+    from rl4rs_b200 import dataset
+    B, epochs = 8, 3
+    cfg, cat, log, w = _synthetic(B, seq)
+    fn = {(False, False): dataset.data_generate_rl4rs_a, (False, True): dataset.data_generate_rl4rs_a_conti,
+          (True, False): dataset.data_generate_rl4rs_b}[(seq, conti)]
+    path = str(tmp_path / "ds.npz")
+    np.random.seed(11)
+    got = fn(dict(cfg, catalog=cat, log=log, weights=w), path, epochs=epochs)
+    np.random.seed(11)
+    O, A, R, D = _oracle_dataset(cfg, seq, conti, log, cat, w, epochs)
+    T = cfg["max_steps"]
+    assert got["observations"].shape == (epochs * B * (T + 1), 266) and got["observations"].dtype == np.float32
+    np.testing.assert_allclose(got["observations"], O, rtol=0, atol=1e-6)
+    np.testing.assert_array_equal(got["actions"], A)
+    np.testing.assert_allclose(got["rewards"], R, rtol=1e-6)
+    np.testing.assert_array_equal(got["terminals"], D)
+    assert bool(got["discrete_action"]) == (not conti) and got["terminals"].sum() == epochs * B
+    np.testing.assert_array_equal(np.load(path)["actions"], got["actions"])
