@@ -52,6 +52,7 @@ UNIT = "transitions/s"
 BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}     # SURVEY.md section 8(d), dien: 83 732 B per row-forward
 G_DNN = 12564                                                   # dnn: algorithmic bytes per row-forward (section 8d)
 ROW_FORWARDS_PER_TRANSITION = {9: 19.0 / 9, 27: 55.0 / 27, 36: 73.0 / 36}
+CPU_ARM_BUDGET_S = 240.0                                        # --impl reference: warm-up + timed episodes fit in about this
 CPU_THREADS_PER_WORKER = 1                                      # CPU arm: one single-threaded worker process per host thread
                                                                 # (8 x 1 beats 1 x 8 BLAS threads 9-fold on these matrix sizes)
 
@@ -139,7 +140,8 @@ def _cpu_workers_cap():
     return cpu_arm.workers_cap()
 
 
-def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=True, log=None, catalog=None, weights=None):
+def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=True, log=None, catalog=None, weights=None,
+                           budget_s=None):
     """The reference's CPU path (oracle port, oracle/cpu_arm.py): offline-action replay episodes.  parallel: one
     single-threaded worker process per host thread, B rows each, episodes started together (value = W x B x T / median
     episode); otherwise one process with all its BLAS threads (configs[0], batch 32, the README loop)."""
@@ -148,7 +150,7 @@ def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=
     if parallel:
         try:
             return cpu_arm.run_parallel(cfg, seq, simulator, episodes, warmup, threads=CPU_THREADS_PER_WORKER,
-                                        workers=_cpu_workers_cap())
+                                        workers=_cpu_workers_cap(), budget_s=budget_s)
         except Exception as e:                                # noqa: BLE001 -- e.g. no process spawning in a sandbox
             sys.stderr.write("bench: parallel CPU arm failed (%s); single process\n" % e)
     from rl4rs_b200 import synth
@@ -164,7 +166,8 @@ def cpu_sample_text(r, batch):
             "%d of %d host threads busy; one step = one offline-action replay episode = %d transitions; median of %d "
             "episodes, spread (max-min)/median %.2f, NN share of the busy time %.2f"
             % (r["rows_per_episode"], batch, r["workers"], r["rows_per_episode"] // r["workers"], r["threads_per_worker"],
-               r["threads"], r["host_cores"], r["transitions_per_episode"], len(r["episode_s"]), r["spread"], r["nn_share"]))
+               r["threads"], r["host_cores"], r["transitions_per_episode"], len(r["episode_s"]), r["spread"], r["nn_share"])
+            + ("; " + r["note"] if r.get("note") else ""))
 
 
 def run_reference(args):
@@ -176,7 +179,8 @@ def run_reference(args):
         return
     seq = args.env == "seqslate"
     rows, W, threads = cpu_arm_rows(args.batch_per_gpu, args.cpu_sample_rows)
-    r = cpu_reference_episodes(rows, seq, max(args.steps, 1), max(args.warmup, 1), simulator=args.simulator)
+    r = cpu_reference_episodes(rows, seq, max(args.steps, 1), max(args.warmup, 1), simulator=args.simulator,
+                               budget_s=CPU_ARM_BUDGET_S)
     c1 = cpu_reference_episodes(32, seq, 3, 1, simulator=args.simulator, parallel=False)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["median_s"] * 1e3,
@@ -452,7 +456,7 @@ def main():
                             "launches": k["launches"]} for k in sorted(kernels, key=lambda k: -k["ms"])]
     if world == 1 and not args.no_cpu_baseline:
         rows, _, _ = cpu_arm_rows(B, args.cpu_sample_rows)
-        r = cpu_reference_episodes(rows, seq, episodes=3, warmup=1, simulator=args.simulator)
+        r = cpu_reference_episodes(rows, seq, episodes=3, warmup=1, simulator=args.simulator, budget_s=30.0)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
                                 "sample": cpu_sample_text(r, B) + "; %.1f s timed" % r["total_s"],
                                 "episode_s": r["episode_s"], "nn_share": r["nn_share"]}

@@ -84,7 +84,7 @@ def _limit_threads(threads):
         return contextlib.nullcontext()
 
 
-def _worker(idx, cores, spec, barrier, out):
+def _worker(idx, cores, spec, barrier, out, go, rows):
     try:
         if cores:
             try:
@@ -96,15 +96,23 @@ def _worker(idx, cores, spec, barrier, out):
         catalog = synth.make_catalog()
         log = synth.make_log(spec["n_log"], pages=4 if spec["seq"] else 1, catalog=catalog, seed=synth.LOG_SEED + idx)
         weights = synth.make_dnn_weights(cfg) if spec["simulator"] == "dnn" else synth.make_weights(cfg)
+        sync = lambda: barrier.wait(timeout=spec["timeout_s"])
         with _limit_threads(spec["threads"]):
-            res = _episodes(cfg, log, catalog, weights, spec["seq"], spec["simulator"], spec["episodes"], spec["warmup"],
-                            sync=lambda: barrier.wait(timeout=spec["timeout_s"]))
+            if spec["calibrate_rows"]:
+                # one episode of a few rows, all workers together: the parent sizes the timed episodes from its duration
+                t0, t1, _ = _episodes(dict(cfg, batch_size=spec["calibrate_rows"]), log, catalog, weights, spec["seq"],
+                                      spec["simulator"], 1, 0, sync=sync)
+                out.put((idx, t1[0] - t0[0], None))
+                go.wait(timeout=spec["timeout_s"])
+                cfg = dict(cfg, batch_size=int(rows.value))
+            res = _episodes(cfg, log, catalog, weights, spec["seq"], spec["simulator"], spec["episodes"], spec["warmup"], sync=sync)
         out.put((idx, res, None))
     except Exception as e:                                   # noqa: BLE001 -- reported to the parent, which falls back
-        try:
-            barrier.abort()
-        except Exception:
-            pass
+        for b in (barrier, go):
+            try:
+                b.abort()
+            except Exception:
+                pass
         out.put((idx, None, "%s: %s" % (type(e).__name__, e)))
 
 
@@ -134,6 +142,22 @@ def workers_cap(per_worker_bytes=300e6, share=0.5):
     return None if lim is None else max(1, int(lim * share / per_worker_bytes))
 
 
+def cpu_quota():
+    """CPUs' worth of run time the cgroup allows (cpu.max / cfs_quota), or None: a container can SEE 128 hardware threads
+    and be allowed 16 of them; more single-threaded workers than that only time-slice."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def host_cores():
     try:
         return sorted(os.sched_getaffinity(0))
@@ -146,6 +170,9 @@ def plan(threads=None, workers=None):
     cores = host_cores()
     n = len(cores)
     threads = max(1, min(threads or 4, n))
+    quota = cpu_quota()
+    if quota is not None:
+        n = max(threads, min(n, int(quota + 0.5)))
     workers = max(1, min(workers or n // threads, n // threads))
     return workers, threads, [cores[w * threads:(w + 1) * threads] for w in range(workers)]
 
@@ -171,15 +198,19 @@ def run_single(cfg, log, catalog, weights, seq, simulator, episodes, warmup, thr
                     len(host_cores()))
 
 
-def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=None, timeout_s=900.0):
-    """All host cores: W processes x `threads` cores, cfg['batch_size'] rows per worker and episode."""
+def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=None, timeout_s=900.0, budget_s=None):
+    """All host cores: W processes x `threads` cores, at most cfg['batch_size'] rows per worker and episode.
+    budget_s: wall-clock target for the warm-up + timed episodes together; the workers then run one calibration episode
+    of a few rows first and the rows per worker are cut (never raised) so that an episode takes about
+    budget_s / (episodes + warmup), within [2 s, 20 s] -- the bench contract asks for K steps in a few minutes on any host."""
     W, threads, blocks = plan(threads, workers)
     B, T = cfg["batch_size"], cfg["max_steps"]
+    cal_rows = min(B, 8) if budget_s else 0
     spec = {"cfg": cfg, "seq": seq, "simulator": simulator, "episodes": episodes, "warmup": warmup,
-            "threads": threads, "n_log": max(4 * B, 2048), "timeout_s": timeout_s}
+            "threads": threads, "n_log": max(4 * B, 2048), "timeout_s": timeout_s, "calibrate_rows": cal_rows}
     ctx = mp.get_context("spawn")
-    barrier, out = ctx.Barrier(W), ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(w, blocks[w], spec, barrier, out), daemon=True) for w in range(W)]
+    barrier, out, go, rows = ctx.Barrier(W), ctx.Queue(), ctx.Barrier(W + 1), ctx.Value("i", B)
+    procs = [ctx.Process(target=_worker, args=(w, blocks[w], spec, barrier, out, go, rows), daemon=True) for w in range(W)]
     # the children size their BLAS pools when numpy loads: tell them before they start (W x host_cores threads otherwise)
     names = ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS")
     saved = {k: os.environ.get(k) for k in names}
@@ -193,16 +224,33 @@ def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=No
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
-    results, err = {}, None
+    results, err, note = {}, None, None
     try:
+        if cal_rows:
+            cal = []
+            for _ in range(W):
+                idx, t, e = out.get(timeout=timeout_s)
+                if e is not None:
+                    raise RuntimeError("worker %d: %s" % (idx, e))
+                cal.append(t)
+            per_row = max(cal) / cal_rows                        # seconds per env row and episode, slowest worker
+            target = min(20.0, max(2.0, budget_s / float(episodes + warmup)))
+            rows.value = B = max(1, min(B, int(target / per_row)))
+            note = "rows per worker sized from a %d-row calibration episode (%.2f s): target %.1f s per episode" % (cal_rows, max(cal), target)
+            go.wait(timeout=timeout_s)
         for _ in range(W):
             idx, res, e = out.get(timeout=timeout_s)
             if e is not None:
                 err = err or "worker %d: %s" % (idx, e)
             else:
                 results[idx] = res
-    except Exception as e:                                   # noqa: BLE001 -- queue timeout
-        err = "no result within %.0f s (%s)" % (timeout_s, type(e).__name__)
+    except Exception as e:                                   # noqa: BLE001 -- queue timeout, a worker's error, a broken barrier
+        err = err or "%s: %s" % (type(e).__name__, e)
+        for b in (barrier, go):
+            try:
+                b.abort()
+            except Exception:
+                pass
     for p in procs:
         p.join(timeout=5)
         if p.is_alive():
@@ -213,4 +261,4 @@ def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=No
     ep = [max(results[w][1][e] for w in range(W)) - min(results[w][0][e] for w in range(W)) for e in range(episodes)]
     busy = sum(b - a for w in range(W) for a, b in zip(results[w][0], results[w][1]))
     nn = sum(sum(results[w][2]) for w in range(W))
-    return _summary(B, T, W, threads, ep, float(nn / max(busy, 1e-9)), len(host_cores()))
+    return _summary(B, T, W, threads, ep, float(nn / max(busy, 1e-9)), len(host_cores()), note)

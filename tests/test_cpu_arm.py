@@ -29,3 +29,22 @@ def test_parallel_arm_two_workers_dnn():
     assert 0.0 < r["nn_share"] <= 1.0
     # the thread limits handed to the children do not stay in the parent's environment
     assert {k: os.environ.get(k) for k in names} == before
+
+
+def test_parallel_arm_sizes_its_episodes_from_a_calibration_run():
+    """budget_s: one calibration episode, then rows per worker cut so that warm-up + timed episodes fit the budget."""
+    import bench
+    cfg = dict(bench.base_config(64, False, simulator="dnn"), is_eval=False, cache_size=256)
+    W = min(2, len(cpu_arm.host_cores()))
+    r = cpu_arm.run_parallel(cfg, False, "dnn", episodes=2, warmup=1, threads=1, workers=W, budget_s=6.0)
+    assert 1 <= r["rows_per_episode"] // r["workers"] <= 64 and "calibration" in r["note"]
+    assert r["transitions_per_episode"] == r["rows_per_episode"] * 9 and len(r["episode_s"]) == 2
+
+
+def test_cpu_quota_is_read_from_the_cgroup(monkeypatch, tmp_path):
+    q = cpu_arm.cpu_quota()
+    assert q is None or q > 0
+    cores = cpu_arm.host_cores()
+    monkeypatch.setattr(cpu_arm, "cpu_quota", lambda: 2.0)
+    W, threads, blocks = cpu_arm.plan(1, None)
+    assert W == min(2, len(cores)) and threads == 1
