@@ -147,3 +147,24 @@ def test_dataset_writer_host_loop(oracle_engine, seq, conti, tmp_path):
     np.testing.assert_array_equal(got["terminals"], D)
     assert bool(got["discrete_action"]) == (not conti) and got["terminals"].sum() == epochs * B
     np.testing.assert_array_equal(np.load(path)["actions"], got["actions"])
+
+
+def test_ppo_learns_on_the_env_through_the_host_layer(oracle_engine):
+    """a23 end to end on CPU: the PPO trainer (torch twin of the kernels) driving SlateRecEnv-v0 in the 'torch' format
+    through the product's env classes; the simulator behind them is the oracle.  Six iterations on 16 fixed users lift
+    the greedy episode reward by 20-70 % depending on the seed (measured 262.9 -> 376.8 for seed 0); the test asks for 10 %."""
+    import torch
+    from test_gpu_parity import _synthetic
+    from rl4rs_b200.trainer import get_rl_model
+    torch.manual_seed(0)
+    np.random.seed(0)
+    cfg, cat, log, w = _synthetic(16, False, support_rllib_mask=True)
+    env = make_env(cfg, False, cat, log, w, output_format="torch")
+    tr = get_rl_model("PPO", {"lr": 3e-3, "sgd_minibatch_size": 48}, env=env, device="cpu", seed=0)
+    before = tr.evaluate(1)
+    stats = [tr.train() for _ in range(6)]
+    after = tr.evaluate(1)
+    assert all(np.isfinite(s["episode_reward_mean"]) for s in stats) and stats[-1]["timesteps_total"] == 6 * 16 * 9
+    assert after > 1.1 * before, (before, after)
+    # every action the policy took was legal: the reward of a slate with a violation is zeroed (slate.py:303-306)
+    assert (tr.buf.reward[-1] > 0).all()
