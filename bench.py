@@ -141,7 +141,7 @@ def _cpu_workers_cap():
 
 
 def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=True, log=None, catalog=None, weights=None,
-                           budget_s=None):
+                           budget_s=None, timeout_s=900.0):
     """The reference's CPU path (oracle port, oracle/cpu_arm.py): offline-action replay episodes.  parallel: one
     single-threaded worker process per host thread, B rows each, episodes started together (value = W x B x T / median
     episode); otherwise one process with all its BLAS threads (configs[0], batch 32, the README loop)."""
@@ -150,7 +150,7 @@ def cpu_reference_episodes(B, seq, episodes, warmup, simulator="dien", parallel=
     if parallel:
         try:
             return cpu_arm.run_parallel(cfg, seq, simulator, episodes, warmup, threads=CPU_THREADS_PER_WORKER,
-                                        workers=_cpu_workers_cap(), budget_s=budget_s)
+                                        workers=_cpu_workers_cap(), budget_s=budget_s, timeout_s=timeout_s)
         except Exception as e:                                # noqa: BLE001 -- e.g. no process spawning in a sandbox
             sys.stderr.write("bench: parallel CPU arm failed (%s); single process\n" % e)
     from rl4rs_b200 import synth
@@ -455,11 +455,14 @@ def main():
         line["kernels"] = [{"name": k["name"], "ms": round(k["ms"], 3), "share": round(k["ms"] / tot, 4),
                             "launches": k["launches"]} for k in sorted(kernels, key=lambda k: -k["ms"])]
     if world == 1 and not args.no_cpu_baseline:
-        rows, _, _ = cpu_arm_rows(B, args.cpu_sample_rows)
-        r = cpu_reference_episodes(rows, seq, episodes=3, warmup=1, simulator=args.simulator, budget_s=30.0)
-        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-                                "sample": cpu_sample_text(r, B) + "; %.1f s timed" % r["total_s"],
-                                "episode_s": r["episode_s"], "nn_share": r["nn_share"]}
+        try:
+            rows, _, _ = cpu_arm_rows(B, args.cpu_sample_rows)
+            r = cpu_reference_episodes(rows, seq, episodes=3, warmup=1, simulator=args.simulator, budget_s=30.0, timeout_s=240.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+                                    "sample": cpu_sample_text(r, B) + "; %.1f s timed" % r["total_s"],
+                                    "episode_s": r["episode_s"], "nn_share": r["nn_share"]}
+        except Exception as e:                                # noqa: BLE001 -- the GPU line must be printed whatever the CPU leg does
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %s" % e}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
