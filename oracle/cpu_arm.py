@@ -198,6 +198,21 @@ def run_single(cfg, log, catalog, weights, seq, simulator, episodes, warmup, thr
                     len(host_cores()))
 
 
+def _get(out, procs, timeout_s):
+    """Next message of a worker; gives up at once when a worker died without reporting (e.g. it could not be spawned)."""
+    import queue
+    t_end = time.time() + timeout_s
+    while True:
+        try:
+            return out.get(timeout=2.0)
+        except queue.Empty:
+            dead = [p for p in procs if p.exitcode not in (None, 0)]
+            if dead:
+                raise RuntimeError("%d worker process(es) died (exit code %s)" % (len(dead), dead[0].exitcode))
+            if time.time() > t_end:
+                raise RuntimeError("no result within %.0f s" % timeout_s)
+
+
 def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=None, timeout_s=900.0, budget_s=None):
     """All host cores: W processes x `threads` cores, at most cfg['batch_size'] rows per worker and episode.
     budget_s: wall-clock target for the warm-up + timed episodes together; the workers then run one calibration episode
@@ -229,7 +244,7 @@ def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=No
         if cal_rows:
             cal = []
             for _ in range(W):
-                idx, t, e = out.get(timeout=timeout_s)
+                idx, t, e = _get(out, procs, timeout_s)
                 if e is not None:
                     raise RuntimeError("worker %d: %s" % (idx, e))
                 cal.append(t)
@@ -239,7 +254,7 @@ def run_parallel(cfg, seq, simulator, episodes, warmup, threads=None, workers=No
             note = "rows per worker sized from a %d-row calibration episode (%.2f s): target %.1f s per episode" % (cal_rows, max(cal), target)
             go.wait(timeout=timeout_s)
         for _ in range(W):
-            idx, res, e = out.get(timeout=timeout_s)
+            idx, res, e = _get(out, procs, timeout_s)
             if e is not None:
                 err = err or "worker %d: %s" % (idx, e)
             else:
