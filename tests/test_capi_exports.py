@@ -95,3 +95,21 @@ def test_augru_kernel_choice_rule():
     assert lib.r4_set_option(b"augru_kernel", 1) != 0 and lib.r4_set_option(b"augru_cost_single", 3) != 0   # the deleted kernel
     assert lib.r4_set_option(b"augru_kernel", 7) != 0 and lib.r4_set_option(b"no_such_key", 1) != 0
     assert lib.r4_set_option(b"augru_kernel", 0) == 0
+
+
+def test_c99_caller_compiles_links_and_runs(tmp_path):
+    """the header is self-contained C99 and the library is callable from plain C (no torch, no
+    Python).  tests/c_caller/c_caller.c uses the entry points that need no GPU."""
+    import shutil
+    import subprocess
+    import __graft_entry__ as g
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    lib = g.build()
+    exe = str(tmp_path / "c_caller")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_caller", "c_caller.c"), "-L", os.path.dirname(lib), "-lrl4rs_b200",
+                    "-Wl,-rpath," + os.path.dirname(lib), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "abi 2" in out and "obs_dim dien 256 widedeep 3072" in out
+    assert "create rc -1 env null" in out and "maxlen=64" in out
