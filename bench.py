@@ -39,7 +39,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import time
 
 import numpy as np
 
