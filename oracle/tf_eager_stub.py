@@ -18,6 +18,11 @@ in a TF1 checkpoint (a {variable name: array} dict) under the names Keras would 
     `VecAttGRUCell`; TF1 `GRUCell`), written a third time, layer by layer.  The simulator arithmetic therefore stays
     PARITY UNPINNED in the sense of SURVEY.md section 8c: no vector produced by TensorFlow itself is available.
 
+`full_reference_stack(config)` goes one step further: inside it the reference's SlateRecEnv / SeqSlateRecEnv construct
+themselves with their own __init__ (tf.Graph, get_model, tf.Session, tf.train.Saver().restore of a Saver-format checkpoint
+read by rl4rs_b200.utils.tf_checkpoint, keras.backend.function), so a fixture can be replayed through the reference's
+unmodified Python from RecEnvBase down to the graph definition (tests/test_reference_graph.py).
+
 Nothing under rl4rs_b200/ imports this module; /root/reference exists only in the build container.
 """
 import contextlib
@@ -36,8 +41,8 @@ DT = np.float64
 
 class _Ctx(object):
     def __init__(self, feed, checkpoint):
-        self.feed, self.ckpt = feed, checkpoint
-        self.uids, self.layers, self.created, self.used = {}, [], [], set()
+        self.feed, self.ckpt = feed, (dict(checkpoint) if checkpoint is not None else None)
+        self.uids, self.layers, self.created, self.used, self.inputs, self.requested = {}, [], [], set(), [], {}
 
 
 _CTX = None
@@ -60,12 +65,15 @@ def _variable(scope, inner, shape):
     shape = tuple(int(s) for s in shape)
     top = scope.split("/")[0]
     full = scope + "/" + inner
-    if full not in _CTX.ckpt:
+    if _CTX.ckpt is not None and full not in _CTX.ckpt:
         hits = [k for k, v in _CTX.ckpt.items() if k.split("/")[0] == top and tuple(v.shape) == shape and k not in _CTX.used]
         if len(hits) != 1:
             raise KeyError("graph asks for %s %s: not in the checkpoint, %d same-shape candidates under %r %s (has: %s)"
                            % (full, shape, len(hits), top, hits, sorted(k for k in _CTX.ckpt if k.split("/")[0] == top)))
         full = hits[0]
+    if _CTX.ckpt is None:                       # the build before Saver.restore (base.py:121): structure only
+        _CTX.created.append((top, full, shape))
+        return np.zeros(shape, DT)
     v = _CTX.ckpt[full]
     if tuple(v.shape) != shape:
         raise ValueError("%s has shape %s, the graph builds %s" % (full, v.shape, shape))
@@ -100,7 +108,11 @@ class Layer(object):
 
 # ---- tensorflow.keras.layers (Keras 2.2.4-tf as shipped in TF 1.15) ---------------------------------------------------
 def Input(shape=None, dtype="float32", name=None, **kwargs):
-    x = np.asarray(_CTX.feed[name])
+    _CTX.inputs.append(name)
+    if _CTX.feed is None:                       # structure-probing build: one dummy row
+        x = np.zeros((1,) + tuple(shape))
+    else:
+        x = np.asarray(_CTX.feed[name])
     assert tuple(x.shape[1:]) == tuple(shape), (name, x.shape, shape)
     return x.astype(np.int64) if "int" in dtype else x.astype(DT)
 
@@ -297,7 +309,10 @@ class Model(object):
         self.layers = list(_CTX.layers)
 
     def get_layer(self, name):
-        return [l for l in self.layers if l.name == name][0]
+        layer = [l for l in self.layers if l.name == name][0]
+        if _CTX is not None:
+            _CTX.requested[id(layer.output)] = name          # an activation layer shares its output array with its Dense
+        return layer
 
     def compile(self, **kw):
         pass
@@ -366,7 +381,7 @@ def run_reference_graph(algo, config, checkpoint, seq, dense, cat):
     global _CTX
     feed = {"sequence_feature_input": np.asarray(seq), "dense_feature_input": np.asarray(dense),
             "category_feature_input": np.asarray(cat), "slate_label": np.zeros((len(cat), 9), np.int64)}
-    _CTX = _Ctx(feed, dict(checkpoint))
+    _CTX = _Ctx(feed, checkpoint)
     try:
         with _swapped_modules():
             model = importlib.import_module("rl4rs.nets." + algo).get_model(config)
@@ -375,4 +390,109 @@ def run_reference_graph(algo, config, checkpoint, seq, dense, cat):
                 "variables": list(_CTX.created), "unused": sorted(set(_CTX.ckpt) - _CTX.used),
                 "layers": [l.name for l in model.layers]}
     finally:
+        _CTX = None
+
+
+# ---- the reference's whole stack: RecEnvBase -> SlateRecEnv.__init__ -> RecSimBase.__init__ -> get_model -> Saver.restore ----
+class _Scope(object):
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+class _Graph(object):
+    """tf.Graph(): a fresh graph is a fresh Keras name space (base.py:119) -- layer uids restart here."""
+
+    def __init__(self):
+        global _CTX
+        _CTX = _Ctx(None, None)
+
+    def as_default(self):
+        return _Scope()
+
+
+class _Session(object):
+    def __init__(self, graph=None, config=None):
+        self.graph = graph
+
+    def as_default(self):
+        return _Scope()
+
+
+class _Stack(object):
+    """What the TF runtime would hold for one simulator: the config its graph was built from and the restored values."""
+
+    def __init__(self, config):
+        self.config, self.ckpt, self.restored_from, self.calls = config, None, None, 0
+
+
+class _Saver(object):
+    def __init__(self, stack):
+        self.stack = stack
+
+    def restore(self, sess, model_file):            # base.py:148-151: a tf.train.Saver prefix, read WITHOUT TensorFlow
+        from rl4rs_b200.utils.tf_checkpoint import TensorBundleReader
+        rd = TensorBundleReader(model_file)
+        self.stack.ckpt = {name: np.asarray(rd.get_tensor(name), DT) for name in rd.variables()}    # converted once
+        self.stack.restored_from = model_file
+
+
+class _Function(object):
+    """tf.keras.backend.function(model.input, layer.output) (slate.py:232-237): evaluating it re-runs the reference's
+    get_model eagerly on the fed rows with the restored variables and hands back that layer's output as float32."""
+
+    def __init__(self, stack, output):
+        name = _CTX.requested.get(id(output))
+        assert name is not None and [l for l in _CTX.layers if l.name == name][0].output is output
+        self.stack, self.layer, self.inputs = stack, name, list(_CTX.inputs)
+
+    def __call__(self, feat):
+        global _CTX
+        st = self.stack
+        assert st.ckpt is not None, "Saver.restore has not run"
+        prev, _CTX = _CTX, _Ctx(dict(zip(self.inputs, feat)), st.ckpt)
+        try:
+            algo = st.config.get("algo", "dien")
+            model = importlib.import_module("rl4rs.nets." + algo).get_model(st.config)
+            assert not (set(_CTX.ckpt) - _CTX.used), sorted(set(_CTX.ckpt) - _CTX.used)
+            st.calls += 1
+            return np.asarray(model.get_layer(self.layer).output, np.float32)
+        finally:
+            _CTX = prev
+
+
+@contextlib.contextmanager
+def full_reference_stack(config):
+    """Inside this context `SlateRecEnv(config, SlateState)` / `SeqSlateRecEnv(...)` of the REFERENCE construct themselves
+    with their own __init__ (base.py:114-131, slate.py:223-237): tf.Graph / Session / train.Saver / keras.backend.function
+    are the stand-ins above, `config['model_file']` must be a Saver prefix (rl4rs_b200.utils.tf_checkpoint writes one).
+    Yields (ref_base, ref_slate, ref_seqslate, stack)."""
+    global _CTX
+    from oracle import ref_harness
+    ref_base, ref_slate, ref_seqslate, _ = ref_harness.install_stubs()
+    stack = _Stack(config)
+    tfm = ref_base.tf
+    assert tfm is ref_slate.tf
+    patched = {"Graph": _Graph, "Session": _Session, "ConfigProto": lambda **kw: None,
+               "train": types.SimpleNamespace(Saver=lambda: _Saver(stack))}
+    saved = {k: getattr(tfm, k, None) for k in patched}
+    saved_backend = getattr(tfm.keras, "backend", None)
+    try:
+        for k, v in patched.items():
+            setattr(tfm, k, v)
+        tfm.keras.backend = types.SimpleNamespace(function=lambda inputs, output: _Function(stack, output))
+        with _swapped_modules():
+            yield ref_base, ref_slate, ref_seqslate, stack
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                delattr(tfm, k)
+            else:
+                setattr(tfm, k, v)
+        if saved_backend is None:
+            del tfm.keras.backend
+        else:
+            tfm.keras.backend = saved_backend
         _CTX = None

@@ -49,8 +49,14 @@ def obs_to_arrays(obs, cfg):
 
 
 def run_reference(cfg, records, catalog_text, weights, seq, actions_fn, n_episodes=1, seed=None,
-                  reset_file=False):
-    """Roll the reference env and record everything it exposes, per step."""
+                  reset_file=False, full_stack=False):
+    """Roll the reference env and record everything it exposes, per step.
+
+    full_stack=False (how the committed fixtures were made): RecSimBase.__init__'s TensorFlow half is bypassed and the
+    NumPy oracle network is plugged in as obs_layer / reward_layer (ref_harness.make_reference_env).
+    full_stack=True: the reference constructs ITSELF -- SlateRecEnv.__init__ / RecSimBase.__init__, rl4rs/nets/<algo>.py's
+    get_model, tf.train.Saver().restore of a Saver-format checkpoint written by rl4rs_b200.utils.tf_checkpoint -- over
+    the eager layer stand-ins of oracle/tf_eager_stub.py (tests/test_reference_graph.py replays fixtures this way)."""
     tmp = tempfile.mkdtemp()
     sample_file = os.path.join(tmp, "log.csv")
     item_file = os.path.join(tmp, "item_info.csv")
@@ -59,10 +65,25 @@ def run_reference(cfg, records, catalog_text, weights, seq, actions_fn, n_episod
     with open(item_file, "w") as f:
         f.write(catalog_text)
     cfg = dict(cfg, sample_file=sample_file, iteminfo_file=item_file, model_file="unused")
-    dien = DienOracle(weights, np.float32)
     if seed is not None:
         np.random.seed(seed)
-    env = ref_harness.make_reference_env(cfg, (dien.obs_layer, dien.reward_layer), seq=seq)
+    if not full_stack:
+        dien = DienOracle(weights, np.float32)
+        env = ref_harness.make_reference_env(cfg, (dien.obs_layer, dien.reward_layer), seq=seq)
+        return _roll(env, cfg, actions_fn, n_episodes, reset_file)
+    from oracle import tf_eager_stub
+    from rl4rs_b200.utils import tf_checkpoint
+    cfg["model_file"] = tf_checkpoint.save_dien_checkpoint(os.path.join(tmp, "simulator"), weights, cfg)
+    with tf_eager_stub.full_reference_stack(cfg) as (ref_base, ref_slate, ref_seqslate, stack):
+        sim = (ref_seqslate.SeqSlateRecEnv(cfg, ref_seqslate.SeqSlateState) if seq
+               else ref_slate.SlateRecEnv(cfg, ref_slate.SlateState))
+        assert stack.restored_from == cfg["model_file"]
+        rec = _roll(ref_base.RecEnvBase(sim), cfg, actions_fn, n_episodes, reset_file)
+        assert stack.calls > 0 or cfg.get("rawstate_as_obs", False)
+    return rec
+
+
+def _roll(env, cfg, actions_fn, n_episodes, reset_file):
     futil = env.sim.FeatureUtil
     rec = {}
 

@@ -100,3 +100,38 @@ def test_the_check_has_teeth(golden):
     w = dict(w, emb_cat=w["emb_seq"], emb_seq=w["emb_cat"])
     obs, _ = DienOracle(w, np.float64).forward(g["seq"], g["dense"], g["cat"])
     assert np.abs(obs - g["dien_stress_obs"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("name", ["tutorial_slate_rllib", "slate_rllib_replay", "seqslate27_plain_mixed", "slate_d3rl_replay", "seqslate36_d3rl_conti"])
+def test_the_references_own_stack_reproduces_the_fixtures(name):
+    """The fixtures the CUDA path is held to were made with the TensorFlow half of RecSimBase.__init__ bypassed.  Here the
+    reference builds ITSELF -- RecEnvBase -> (Seq)SlateRecEnv.__init__ -> RecSimBase.__init__ -> rl4rs/nets/dien.py ->
+    tf.train.Saver().restore of a checkpoint written by our n1 writer -> keras.backend.function -> obs_fn / forward --
+    over the layer stand-ins, replays the fixture's actions, and must land on the fixture: integers exactly, observations
+    and rewards at f32 rounding (the stand-ins compute in f64 and hand back float32 like keras.backend.function)."""
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree absent")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import make_golden
+    from golden_util import Golden
+    g = Golden(name)
+    a = g.arr
+    T = g.config["max_steps"]
+    replay = lambda env, ep, t, off: a["action_in"][ep * T + t]
+    rec = make_golden.run_reference(g.config, g.meta["records"], g.meta["catalog_text"], g.weights, g.seq, replay,
+                                    n_episodes=g.n_episodes, seed=g.meta.get("np_seed"), full_stack=True)
+    assert set(rec) == set(a), set(rec) ^ set(a)
+    for key in sorted(a):
+        if key in ("reset_obs", "step_obs", "reward", "click_p"):
+            ref = a[key].astype(np.float64)
+            if key.endswith("obs") and ref.shape[-1] > 256:              # d3rl form: obs | masked_actions | cur_steps
+                np.testing.assert_array_equal(rec[key][..., 256:], ref[..., 256:], err_msg=key)
+                got, ref = rec[key][..., :256], ref[..., :256]
+            else:
+                got = rec[key]
+            scale = np.maximum(np.abs(ref), np.sqrt((ref ** 2).mean(axis=-1, keepdims=True)) if ref.ndim > 1 else 1.0)
+            assert (np.abs(got - ref) / np.maximum(scale, 1e-6)).max() < 3e-5, key
+        elif a[key].dtype.kind == "f":
+            np.testing.assert_allclose(rec[key], a[key], rtol=1e-12, atol=0, err_msg=key)
+        else:
+            np.testing.assert_array_equal(rec[key], a[key], err_msg=key)
