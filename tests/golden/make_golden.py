@@ -73,7 +73,12 @@ def run_reference(cfg, records, catalog_text, weights, seq, actions_fn, n_episod
         return _roll(env, cfg, actions_fn, n_episodes, reset_file)
     from oracle import tf_eager_stub
     from rl4rs_b200.utils import tf_checkpoint
-    cfg["model_file"] = tf_checkpoint.save_dien_checkpoint(os.path.join(tmp, "simulator"), weights, cfg)
+    algo = cfg.get("algo", "dien")                     # slate.py:239-242: rl4rs/nets/<algo>.py
+    names = getattr(tf_checkpoint, algo + "_variable_names")(cfg)
+    tensors = {names[k]: np.asarray(v, np.float32) for k, v in weights.items() if k in names}
+    if algo == "dnn":                                  # nets/dnn.py also builds a sequence embedding that feeds nothing
+        tensors["embedding_1/embeddings"] = np.zeros((cfg["category_hash_size"], cfg["emb_size"]), np.float32)
+    cfg["model_file"] = tf_checkpoint.write_bundle(os.path.join(tmp, "simulator"), tensors)
     with tf_eager_stub.full_reference_stack(cfg) as (ref_base, ref_slate, ref_seqslate, stack):
         sim = (ref_seqslate.SeqSlateRecEnv(cfg, ref_seqslate.SeqSlateState) if seq
                else ref_slate.SlateRecEnv(cfg, ref_slate.SlateState))

@@ -135,3 +135,37 @@ def test_the_references_own_stack_reproduces_the_fixtures(name):
             np.testing.assert_allclose(rec[key], a[key], rtol=1e-12, atol=0, err_msg=key)
         else:
             np.testing.assert_array_equal(rec[key], a[key], err_msg=key)
+
+
+@pytest.mark.parametrize("algo,seq", [("dnn", False), ("widedeep", True), ("lstm", False)])
+def test_the_references_own_stack_with_the_other_simulators(algo, seq):
+    """config['algo'] dispatch (slate.py:239-242) through the reference's own constructors for the other three graphs of
+    rl4rs/nets/: a short logged-policy episode of the self-constructed reference env against the oracle env the GPU tests
+    use for that simulator (tests/test_gpu_dnn.py)."""
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree absent")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import make_golden
+    from oracle.env_np import OracleEnv
+    from rl4rs_b200 import synth
+    B = 4
+    cfg = dict(make_golden.BASE_CFG, batch_size=B, cache_size=B, is_eval=True, support_rllib_mask=True, algo=algo,
+               category_hash_size=600, max_steps=27 if seq else 9)
+    cat = synth.make_catalog()
+    log = synth.make_log(12, pages=4 if seq else 1, catalog=cat, hash_size=600, keep_hist=True)
+    records = synth.render_records(log, cat)
+    maker = {"dnn": synth.make_dnn_weights, "widedeep": synth.make_widedeep_weights, "lstm": synth.make_lstm_weights}[algo]
+    w = maker(cfg, stress=2.0, bias_noise=0.2)
+    rec = make_golden.run_reference(cfg, records, cat.to_text(), w, seq, lambda env, ep, t, off: off, full_stack=True)
+    from rl4rs_b200.utils.datautil import FeatureUtil
+    ora = OracleEnv(cfg, FeatureUtil.parse_log(records, 64), cat, ORACLES[algo](w, np.float32), seq=seq)
+    obs = ora.reset()
+    np.testing.assert_allclose(rec["reset_obs"][0], obs["obs"], rtol=0, atol=3e-5 * max(1.0, np.abs(obs["obs"]).max()))
+    for t in range(cfg["max_steps"]):
+        np.testing.assert_array_equal(rec["offline_action"][t], ora.offline_action)
+        obs, reward, done, _ = ora.step(ora.offline_action)
+        np.testing.assert_array_equal(rec["step_action_mask"][t], obs["action_mask"])
+        np.testing.assert_allclose(rec["step_obs"][t], obs["obs"], rtol=0, atol=3e-5 * max(1.0, np.abs(obs["obs"]).max()))
+        np.testing.assert_allclose(rec["reward"][t], reward, rtol=3e-5, atol=1e-9)
+        np.testing.assert_array_equal(rec["done"][t], done)
+    assert rec["step_obs"].shape[-1] == (3072 if algo == "widedeep" else 256) and (rec["reward"] > 0).any()
