@@ -49,7 +49,7 @@ def obs_to_arrays(obs, cfg):
 
 
 def run_reference(cfg, records, catalog_text, weights, seq, actions_fn, n_episodes=1, seed=None,
-                  reset_file=False, full_stack=False):
+                  reset_file=False, full_stack=False, net=None):
     """Roll the reference env and record everything it exposes, per step.
 
     full_stack=False (how the committed fixtures were made): RecSimBase.__init__'s TensorFlow half is bypassed and the
@@ -68,7 +68,7 @@ def run_reference(cfg, records, catalog_text, weights, seq, actions_fn, n_episod
     if seed is not None:
         np.random.seed(seed)
     if not full_stack:
-        dien = DienOracle(weights, np.float32)
+        dien = net if net is not None else DienOracle(weights, np.float32)     # any obs_layer / reward_layer pair
         env = ref_harness.make_reference_env(cfg, (dien.obs_layer, dien.reward_layer), seq=seq)
         return _roll(env, cfg, actions_fn, n_episodes, reset_file)
     from oracle import tf_eager_stub

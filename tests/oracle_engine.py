@@ -20,12 +20,17 @@ class OracleEngine(object):
         self.conti, self.raw, self.rllib = g("support_conti_env"), g("rawstate_as_obs"), g("support_rllib_mask")
         self.d3rl = g("support_d3rl_mask") and not self.rllib
         self.info_fetch = g("simulator_info_fetch")
+        self._oracle_cfg = dict(config)                   # the oracle state reads the caller's action_emb_size (slate.py:21-25)
         if g("support_onehot_action"):
             config["action_emb_size"] = self.A
         self.emb_dim = self.A if g("support_onehot_action") else int(config.get("action_emb_size", 32))
         self.action_emb = np.eye(self.A) if g("support_onehot_action") else catalog.action_emb(self.emb_dim)
         self.obs_dim = 256
-        self.net = DienOracle(weights, np.float32)
+        if config.get("algo", "dien") == "dnn":           # the env half is the same; the dnn network is much cheaper on a CPU
+            from oracle.dnn_np import DnnOracle
+            self.net = DnnOracle(weights, np.float32)
+        else:
+            self.net = DienOracle(weights, np.float32)
         self.st = None
         self.paid = False
         self.obs = self.mask = self.reward = self.cat = self.dense = self.seqf = self.click_p = self.masked = None
@@ -53,7 +58,7 @@ class OracleEngine(object):
         rows = np.asarray(rows)
         if rows.shape != (self.B,):
             raise ValueError("reset needs %d row indices" % self.B)
-        self.st = OracleState(self.config, self.log, self.catalog, rows, self.seq)
+        self.st = OracleState(self._oracle_cfg, self.log, self.catalog, rows, self.seq)
         self.reward = torch.zeros(self.B, dtype=torch.float64)
         self.paid = False
         self._publish()

@@ -38,23 +38,16 @@ def host(x):
     return x.numpy() if hasattr(x, "is_cuda") else np.asarray(x)
 
 
-@pytest.mark.parametrize("fmt", ["list", "numpy", "torch"])
-@pytest.mark.parametrize("name", golden_names())
-def test_host_layer_replays_reference_fixture(oracle_engine, name, fmt):
-    g = Golden(name)
-    cfg, a = g.config, g.arr
-    if fmt != "list" and name not in ("slate_rllib_replay", "seqslate36_d3rl_conti", "slate_rawstate_replay", "slate_plain_random"):
-        pytest.skip("array formats checked on four fixtures (one per observation layout)")
-    if "np_seed" in g.meta:
-        np.random.seed(g.meta["np_seed"])
-    env = make_env(cfg, g.seq, g.catalog, g.log, g.weights, output_format=fmt)
-    assert env.observation_space is not None and env.action_space is not None
-    T, k = cfg["max_steps"], 0
-    for ep in range(g.n_episodes):
-        obs = env.reset()
+def replay_through_host_layer(env, cfg, a, n_episodes, name, fmt):
+    """Replay recorded actions through the product's env classes and hold what they hand out to the record."""
+    def arrays(obs):
         if fmt == "torch" and not isinstance(obs, dict):
             obs = {"obs": host(obs)}
-        obs = obs_arrays({k_: host(v) for k_, v in obs.items()} if isinstance(obs, dict) else obs)
+        return obs_arrays({k_: host(v) for k_, v in obs.items()} if isinstance(obs, dict) else obs)
+
+    T, k = cfg["max_steps"], 0
+    for ep in range(n_episodes):
+        obs = arrays(env.reset())
         np.testing.assert_array_equal(np.asarray([int(u) for u in env.user_id]), a["reset_user"][ep])
         for key, val in obs.items():
             ref = a["reset_" + key][ep]
@@ -65,9 +58,7 @@ def test_host_layer_replays_reference_fixture(oracle_engine, name, fmt):
         for t in range(T):
             np.testing.assert_array_equal(host(env.offline_action), a["offline_action"][k], err_msg="offline_action %d" % k)
             obs, reward, done, info = env.step(a["action_in"][k])
-            if fmt == "torch" and not isinstance(obs, dict):
-                obs = {"obs": host(obs)}
-            obs = obs_arrays({k_: host(v) for k_, v in obs.items()} if isinstance(obs, dict) else obs)
+            obs = arrays(obs)
             np.testing.assert_array_equal(env.samples.prev_actions, a["prev_actions"][k])
             np.testing.assert_array_equal(env.samples.get_violation(), a["violation"][k])
             np.testing.assert_array_equal(host(done), a["done"][k])
@@ -86,6 +77,19 @@ def test_host_layer_replays_reference_fixture(oracle_engine, name, fmt):
             k += 1
         with pytest.raises(Exception):
             env.step(a["action_in"][k - 1])
+
+
+@pytest.mark.parametrize("fmt", ["list", "numpy", "torch"])
+@pytest.mark.parametrize("name", golden_names())
+def test_host_layer_replays_reference_fixture(oracle_engine, name, fmt):
+    g = Golden(name)
+    if fmt != "list" and name not in ("slate_rllib_replay", "seqslate36_d3rl_conti", "slate_rawstate_replay", "slate_plain_random"):
+        pytest.skip("array formats checked on four fixtures (one per observation layout)")
+    if "np_seed" in g.meta:
+        np.random.seed(g.meta["np_seed"])
+    env = make_env(g.config, g.seq, g.catalog, g.log, g.weights, output_format=fmt)
+    assert env.observation_space is not None and env.action_space is not None
+    replay_through_host_layer(env, g.config, g.arr, g.n_episodes, name, fmt)
 
 
 def test_batch_size_one_in_every_format(oracle_engine):

@@ -16,14 +16,12 @@ def roll_oracle(g, dtype=np.float32):
     return env
 
 
-@pytest.mark.parametrize("name", golden_names())
-def test_oracle_matches_reference_fixture(name):
-    g = Golden(name)
-    cfg, a = g.config, g.arr
-    env = roll_oracle(g)
+def check_oracle_against_record(env, cfg, a, n_episodes, name):
+    """Replay the recorded actions through the oracle env and hold everything it exposes to the record made by the
+    reference's own code: integers / features bit-exact, observations and rewards at the parity tolerance."""
     T = cfg["max_steps"]
     k = 0
-    for ep in range(g.n_episodes):
+    for ep in range(n_episodes):
         obs = env.reset()
         np.testing.assert_array_equal(np.asarray([int(u) for u in env.samples.user]), a["reset_user"][ep])
         for key, val in obs.items():
@@ -33,11 +31,7 @@ def test_oracle_matches_reference_fixture(name):
             else:
                 np.testing.assert_array_equal(val, ref, err_msg="reset " + key)
         for t in range(T):
-            off = env.offline_action
-            if off.dtype.kind == "f":
-                np.testing.assert_array_equal(off, a["offline_action"][k])
-            else:
-                np.testing.assert_array_equal(off, a["offline_action"][k])
+            np.testing.assert_array_equal(env.offline_action, a["offline_action"][k])
             obs, reward, done, info = env.step(a["action_in"][k])
             seqs, dense, cat = env.samples.features()
             np.testing.assert_array_equal(seqs, a["seq"][k], err_msg="seq step %d" % k)
@@ -58,6 +52,12 @@ def test_oracle_matches_reference_fixture(name):
             if "click_p" in a and t == T - 1:
                 assert_close_rel(np.stack([i["click_p"] for i in info]), a["click_p"][ep], what="click_p")
             k += 1
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_reference_fixture(name):
+    g = Golden(name)
+    check_oracle_against_record(roll_oracle(g), g.config, g.arr, g.n_episodes, name)
 
 
 def test_tutorial_known_answers():

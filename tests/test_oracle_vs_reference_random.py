@@ -1,0 +1,103 @@
+"""CPU, build container only: the oracle env (oracle/env_np.py) against the reference's OWN env classes on RANDOM
+scenarios -- env kind, episode length, mask mode, continuous / one-hot actions, raw-state observations, sampling mode,
+batch size, and per-step actions (logged, random, repeated, out-of-layer) are drawn from a seed; the reference is rolled
+through oracle/ref_harness.py exactly like the committed fixtures were, and everything it exposes per step must equal
+what the oracle computes (integers and feature rows bit-exact).  The ten committed fixtures pin ten hand-picked corners;
+this sweeps the product of the flags.  Skipped where /root/reference is absent (the GPU box)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import ref_harness
+from oracle.dnn_np import DnnOracle
+from oracle.env_np import OracleEnv
+from rl4rs_b200 import synth
+from rl4rs_b200.utils.datautil import FeatureUtil
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree absent")
+
+
+def draw_scenario(seed):
+    rs = np.random.RandomState(1000 + seed)
+    seq = bool(rs.rand() < 0.5)
+    B = int(rs.randint(2, 7))
+    cfg = {"epoch": 1, "maxlen": 64, "action_size": 284, "class_num": 2, "dense_feature_num": 432,
+           "category_feature_num": 21, "category_hash_size": 5000, "seq_num": 2, "emb_size": 128, "page_items": 9,
+           "hidden_units": 128, "action_emb_size": 32, "batch_size": B, "algo": "dnn",     # the cheap network: the env half is under test
+           "max_steps": int(rs.choice([9, 18, 27, 36])) if seq else 9}
+    mode = rs.choice(["plain", "rllib", "d3rl", "both"])
+    if mode in ("rllib", "both"):
+        cfg["support_rllib_mask"] = True
+    if mode in ("d3rl", "both"):
+        cfg["support_d3rl_mask"] = True
+    if rs.rand() < 0.35:
+        cfg["support_conti_env"] = True
+        if rs.rand() < 0.3:
+            cfg["support_onehot_action"] = True
+    if rs.rand() < 0.25:
+        cfg["rawstate_as_obs"] = True
+    if rs.rand() < 0.4:
+        cfg["simulator_info_fetch"] = True
+    train_mode = bool(rs.rand() < 0.4)
+    cfg["is_eval"] = not train_mode
+    cfg["cache_size"] = int(rs.randint(B, 3 * B + 1)) if train_mode else B
+    n_rows = int(rs.randint(cfg["cache_size"], 3 * cfg["cache_size"] + 2))     # small logs wrap around (base.py:85-88)
+    episodes = int(rs.randint(1, 4))
+    return cfg, seq, n_rows, episodes, int(rs.randint(1 << 30)), train_mode
+
+
+def action_source(cfg, seed):
+    rs = np.random.RandomState(seed)
+    B = cfg["batch_size"]
+    emb = cfg["action_size"] if cfg.get("support_onehot_action") else 32
+
+    def pick(env, ep, t, off):
+        if cfg.get("support_conti_env"):
+            a = rs.uniform(-1, 1, (B, emb))
+            a[rs.rand(B) < 0.15] = 0.0                              # all-zero rows: every score ties
+            keep = rs.rand(B) < 0.3
+            a[keep] = np.asarray(off, dtype=np.float64)[keep]       # the logged item's own embedding
+            return a
+        off = np.asarray(off)
+        r = rs.rand(B)
+        rand = rs.randint(0, cfg["action_size"], B)                 # often outside the layer, or a repeat
+        prev = env.samples.prev_actions[:, max(t - 1, 0)]
+        return np.where(r < 0.6, off, np.where(r < 0.85, rand, prev)).astype(np.int64)
+    return pick
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_oracle_env_equals_the_reference_env_on_a_random_scenario(seed):
+    import make_golden
+    from test_oracle_golden import check_oracle_against_record
+    cfg, seq, n_rows, episodes, aseed, train_mode = draw_scenario(seed)
+    cat = synth.make_catalog()
+    log = synth.make_log(n_rows, pages=4 if seq else 1, catalog=cat, hash_size=5000, corrupt_frac=0.25, keep_hist=True,
+                         seed=synth.LOG_SEED + seed)
+    records = synth.render_records(log, cat)
+    w = synth.make_dnn_weights(cfg, stress=2.0, bias_noise=0.2)
+    np_seed = 77 + seed if train_mode else None
+    rec = make_golden.run_reference(dict(cfg), records, cat.to_text(), w, seq, action_source(cfg, aseed),
+                                    n_episodes=episodes, seed=np_seed, net=DnnOracle(w, np.float32))
+    if np_seed is not None:
+        np.random.seed(np_seed)
+    env = OracleEnv(dict(cfg), FeatureUtil.parse_log(records, 64), cat, DnnOracle(w, np.float32), seq=seq)
+    check_oracle_against_record(env, cfg, rec, episodes, "random scenario %d" % seed)
+    # ... and the product's own env classes (gym layer, sampler, obs / reward formatting) over the engine stand-in
+    import rl4rs_b200.engine as engine_mod
+    from oracle_engine import OracleEngine
+    from test_host_layer_cpu import make_env, replay_through_host_layer
+    real = engine_mod.Engine
+    engine_mod.Engine = OracleEngine
+    try:
+        fmt = ("list", "numpy", "torch")[seed % 3]
+        if np_seed is not None:
+            np.random.seed(np_seed)
+        host_env = make_env(dict(cfg), seq, cat, FeatureUtil.parse_log(records, 64), w, output_format=fmt)
+        replay_through_host_layer(host_env, cfg, rec, episodes, "random scenario %d (host layer, %s)" % (seed, fmt), fmt)
+    finally:
+        engine_mod.Engine = real
