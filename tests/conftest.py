@@ -8,8 +8,31 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+_KEEP = []
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The CPU suite is hundreds of small NumPy / torch products (the oracles).  With a BLAS thread per core they spend
+    # their time handing 100-microsecond products to spinning worker threads, and glibc returns every temporary above
+    # 128 KB to the kernel: on the 8-core build container the same suite takes 24 minutes that way and about 4 with two
+    # threads and a heap that keeps its blocks (oracle/cpu_arm.py measured the same effect on the CPU arm).  Numerics are
+    # unaffected; the GPU suite does no CPU BLAS work worth threading.
+    try:
+        from threadpoolctl import threadpool_limits
+        _KEEP.append(threadpool_limits(limits=2))
+    except Exception:
+        pass
+    try:
+        import torch
+        torch.set_num_threads(2)
+    except Exception:
+        pass
+    try:
+        from oracle.cpu_arm import _tune_malloc
+        _tune_malloc()
+    except Exception:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
