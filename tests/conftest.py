@@ -19,13 +19,14 @@ def pytest_configure(config):
     # threads and a heap that keeps its blocks (oracle/cpu_arm.py measured the same effect on the CPU arm).  Numerics are
     # unaffected; the GPU suite does no CPU BLAS work worth threading.
     try:
-        from threadpoolctl import threadpool_limits
-        _KEEP.append(threadpool_limits(limits=2))
+        import numpy  # noqa: F401  -- the limits below apply to the BLAS libraries that are loaded when they are set
+        import torch
+        torch.set_num_threads(2)
     except Exception:
         pass
     try:
-        import torch
-        torch.set_num_threads(2)
+        from threadpoolctl import threadpool_limits
+        _KEEP.append(threadpool_limits(limits=2))
     except Exception:
         pass
     try:
