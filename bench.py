@@ -51,7 +51,7 @@ UNIT = "transitions/s"
 BYTES_PER_TRANSITION = {9: 176768, 27: 170565, 36: 169790}     # SURVEY.md section 8(d), dien: 83 732 B per row-forward
 G_DNN = 12564                                                   # dnn: algorithmic bytes per row-forward (section 8d)
 ROW_FORWARDS_PER_TRANSITION = {9: 19.0 / 9, 27: 55.0 / 27, 36: 73.0 / 36}
-CPU_ARM_BUDGET_S = 240.0                                        # --impl reference: warm-up + timed episodes fit in about this
+CPU_ARM_BUDGET_S = 180.0                                        # --impl reference: warm-up + timed episodes fit in about this
 CPU_THREADS_PER_WORKER = 1                                      # CPU arm: one single-threaded worker process per host thread
                                                                 # (8 x 1 beats 1 x 8 BLAS threads 9-fold on these matrix sizes)
 
