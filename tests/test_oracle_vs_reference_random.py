@@ -101,3 +101,46 @@ def test_oracle_env_equals_the_reference_env_on_a_random_scenario(seed):
         replay_through_host_layer(host_env, cfg, rec, episodes, "random scenario %d (host layer, %s)" % (seed, fmt), fmt)
     finally:
         engine_mod.Engine = real
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_ingest_equals_the_reference_preprocessing_on_random_sessions(seed, tmp_path):
+    """n3: rl4rs_b200/utils/ingest.py against the reference's own script/data_preprocess.py (run as its own CLI, like
+    tests/golden/make_ingest_golden.py does) on random session tables: `data_augment` pads sessions of 1-4 pages to 4 with
+    the GLOBAL numpy RNG, `slate2trajectory` joins 4-page sessions and drops the last one."""
+    import runpy
+    from rl4rs_b200.utils import ingest
+    ref_harness.install_stubs()
+    script = os.path.join(ref_harness.REFERENCE_ROOT, "script", "data_preprocess.py")
+
+    def run_stage(stage, lines):
+        src, dst = str(tmp_path / "in.csv"), str(tmp_path / ("out_%s.csv" % stage))
+        open(src, "w").write("\n".join(lines))
+        argv, sys.argv = sys.argv, [script, src, dst, stage]
+        try:
+            runpy.run_path(script, run_name="__main__")
+        finally:
+            sys.argv = argv
+        return [x for x in open(dst).read().split("\n") if x]
+
+    rs = np.random.RandomState(500 + seed)
+    n_sess = int(rs.randint(3, 10))
+    cat = synth.make_catalog()
+    recs = synth.render_records(synth.make_log(4 * n_sess, pages=1, catalog=cat, keep_hist=True, seed=900 + seed), cat)
+    header = "timestamp@session_id@sequence_id@exposed_items@user_feedback@user_seqfeature@user_protrait@item_feature@behavior_policy_id"
+    ragged = [header]
+    for s in range(n_sess):
+        base = recs[4 * s].split("@")
+        for p in range(int(rs.randint(1, 5))):               # 1..4 pages of this session survive
+            f = recs[4 * s + p].split("@")
+            ragged.append("@".join([str(1000 * s + p), base[1], str(p + 1), f[3], f[4], base[5], base[6], f[7], base[8]]))
+    ragged.append("")
+    np.random.seed(40 + seed)
+    want_aug = run_stage("data_augment", ragged)
+    np.random.seed(40 + seed)
+    got_aug = ingest.data_augment(ragged)
+    assert got_aug == want_aug
+    full = [header] + want_aug[1:] + [""] if want_aug[0] == header else [header] + want_aug + [""]
+    want_traj = run_stage("slate2trajectory", full)
+    assert ingest.slate2trajectory(full) == want_traj
+    assert 1 <= len(want_traj) < n_sess                      # the script drops the last session (and any it merges)
