@@ -2,6 +2,7 @@
  * librl4rs_b200.so, and exercises the entry points that need no GPU -- version, observation widths, the AUGRU kernel
  * rule, and r4_create's argument checking with its error message.  Built and run by tests/test_capi_exports.py. */
 #include <stdio.h>
+#include <stddef.h>
 #include <string.h>
 #include "rl4rs_b200.h"
 
@@ -16,6 +17,7 @@ int main(void) {
   cfg.maxlen = 32;                       /* unsupported on purpose: the kernels are built for maxlen = 64 */
   cfg.seq_num = 2; cfg.dense_feature_num = 432; cfg.category_feature_num = 21; cfg.category_hash_size = 1000;
   cfg.emb_size = 128; cfg.hidden_units = 128; cfg.simulator = R4_SIM_DIEN;
+  printf("sizeof r4_config %d r4_out %d\n", (int)sizeof(r4_config), (int)sizeof(r4_out));
   printf("abi %d\n", r4_abi_version());
   printf("obs_dim dien %d widedeep %d\n", r4_obs_dim(R4_SIM_DIEN), r4_obs_dim(R4_SIM_WIDEDEEP));
   printf("augru_kernel_for 64/148 %d 592/148 %d\n", r4_augru_kernel_for(64, 148), r4_augru_kernel_for(592, 148));

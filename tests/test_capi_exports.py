@@ -113,3 +113,6 @@ def test_c99_caller_compiles_links_and_runs(tmp_path):
     out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
     assert "abi 2" in out and "obs_dim dien 256 widedeep 3072" in out
     assert "create rc -1 env null" in out and "maxlen=64" in out
+    # the ctypes mirrors of the two structs (rl4rs_b200/_capi.py) have the C layout
+    import ctypes as C
+    assert "sizeof r4_config %d r4_out %d" % (C.sizeof(_capi.R4Config), C.sizeof(_capi.R4Out)) in out
