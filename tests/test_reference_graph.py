@@ -12,6 +12,7 @@ import pytest
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
 import make_nets_golden as mk                                   # noqa: E402
 
+from golden_util import golden_names                            # noqa: E402
 from oracle import ref_harness                                  # noqa: E402
 from oracle.dien_np import DienOracle                           # noqa: E402
 from oracle.dnn_np import DnnOracle                             # noqa: E402
@@ -102,7 +103,7 @@ def test_the_check_has_teeth(golden):
     assert np.abs(obs - g["dien_stress_obs"]).max() > 1e-3
 
 
-@pytest.mark.parametrize("name", ["tutorial_slate_rllib", "slate_rllib_replay", "seqslate27_plain_mixed", "slate_d3rl_replay", "seqslate36_d3rl_conti"])
+@pytest.mark.parametrize("name", golden_names())
 def test_the_references_own_stack_reproduces_the_fixtures(name):
     """The fixtures the CUDA path is held to were made with the TensorFlow half of RecSimBase.__init__ bypassed.  Here the
     reference builds ITSELF -- RecEnvBase -> (Seq)SlateRecEnv.__init__ -> RecSimBase.__init__ -> rl4rs/nets/dien.py ->
