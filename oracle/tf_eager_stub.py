@@ -496,3 +496,126 @@ def full_reference_stack(config):
         else:
             tfm.keras.backend = saved_backend
         _CTX = None
+
+
+# ---- the RLlib policy models (rl4rs/nets/rllib/rllib_rawstate_model.py:25-86, rllib_mask_model.py:7-64) -----------------
+class _TFModelV2(object):
+    def __init__(self, obs_space, action_space, num_outputs, model_config, name, *a, **kw):
+        self.obs_space, self.action_space, self.num_outputs = obs_space, action_space, num_outputs
+        self.model_config, self.name = model_config, name
+
+
+class _ParametricActionsModel(_TFModelV2):
+    """ray.rllib.examples.models.parametric_actions_model.ParametricActionsModel: owns `action_embed_model`, an RLlib
+    FullyConnectedNetwork over the true observation.  Here that sub-model is whatever the test plugs in."""
+
+    def __init__(self, obs_space, action_space, num_outputs, model_config, name, true_obs_shape=None, action_embed_size=None, **kw):
+        super().__init__(obs_space, action_space, num_outputs, model_config, name)
+        self.action_embed_model = types.SimpleNamespace(model_config=model_config)
+
+
+@contextlib.contextmanager
+def _rllib_stand_ins():
+    """sys.modules entries for the ray / tensorflow names the two RLlib model files import; yields the tf stand-in."""
+    mods = _modules()
+    tf = mods["tensorflow"]
+    tf.keras.Model = Model
+    tf.reshape = lambda x, shape: np.reshape(x, shape)
+    tf.maximum = np.maximum
+    def _log(x):
+        with np.errstate(divide="ignore"):            # log(0) = -inf is the point of the mask (rllib_mask_model.py:61)
+            return np.log(np.asarray(x, np.float32))
+    tf.math.log = _log
+    tf.float32 = types.SimpleNamespace(min=np.finfo(np.float32).min)
+    Model.summary = lambda self: None
+
+    def module(name, **attrs):
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        m.__dict__.update(attrs)
+        return m
+
+    ray = {"ray": module("ray"), "ray.rllib": module("ray.rllib"), "ray.rllib.models": module("ray.rllib.models"),
+           "ray.rllib.models.utils": module("ray.rllib.models.utils", get_activation_fn=lambda name, framework="tf": None),
+           "ray.rllib.models.tf": module("ray.rllib.models.tf"),
+           "ray.rllib.models.tf.misc": module("ray.rllib.models.tf.misc", normc_initializer=lambda std=1.0: None),
+           "ray.rllib.models.tf.tf_modelv2": module("ray.rllib.models.tf.tf_modelv2", TFModelV2=_TFModelV2),
+           "ray.rllib.utils": module("ray.rllib.utils"),
+           "ray.rllib.utils.framework": module("ray.rllib.utils.framework", try_import_tf=lambda: (tf, tf, 1),
+                                               try_import_torch=lambda: (None, None)),
+           "ray.rllib.examples": module("ray.rllib.examples"), "ray.rllib.examples.models": module("ray.rllib.examples.models"),
+           "ray.rllib.examples.models.parametric_actions_model":
+               module("ray.rllib.examples.models.parametric_actions_model", ParametricActionsModel=_ParametricActionsModel)}
+    saved = {k: sys.modules.get(k) for k in ray}
+    try:
+        with _swapped_modules():
+            sys.modules.update(ray)
+            sys.modules["tensorflow"] = tf                # the module try_import_tf hands out IS the stand-in
+            yield tf
+    finally:
+        for k in [k for k in sys.modules if k.startswith("rl4rs.nets")]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+def run_reference_rawstate_model(config, checkpoint, category, dense, sequence, num_outputs):
+    """Builds the reference's own TFModelWithRawState on the fed raw-state rows (its Keras graph is assembled -- and,
+    here, evaluated -- in __init__) under stand-ins for the ray / gym names it imports.
+    -> dict(logits = 'fc_out' (before the action mask), value = 'value_out', variables, layers)."""
+    global _CTX
+    from oracle import ref_harness
+    ref_harness.install_stubs()
+    gym = sys.modules["gym"]
+
+    class Space(object):
+        def __init__(self, shape):
+            self.shape = tuple(shape)
+
+    class DictSpace(gym.spaces.Dict):                    # isinstance(obs_space, gym.spaces.Dict) + item access + .original_space
+        def __getitem__(self, key):
+            return self.spaces[key]
+
+        @property
+        def original_space(self):
+            return self
+
+    obs_space = DictSpace({"category_feature": Space(np.shape(category)[1:]), "dense_feature": Space(np.shape(dense)[1:]),
+                           "sequence_feature": Space(np.shape(sequence)[1:])})
+    feed = {"obs_category_input": np.asarray(category), "obs_dense_input": np.asarray(dense),
+            "obs_sequence_input": np.asarray(sequence)}
+    _CTX = _Ctx(feed, checkpoint)
+    try:
+        with _rllib_stand_ins():
+            mod = importlib.import_module("rl4rs.nets.rllib.rllib_rawstate_model")
+            model = mod.TFModelWithRawState(obs_space, None, num_outputs, {}, "rawstate", config)
+            by_name = {l.name: l for l in _CTX.layers}
+            return {"logits": by_name["fc_out"].output, "value": np.reshape(by_name["value_out"].output, [-1]),
+                    "variables": list(_CTX.created), "unused": sorted(set(_CTX.ckpt) - _CTX.used),
+                    "layers": [l.name for l in _CTX.layers], "model": type(model).__name__}
+    finally:
+        _CTX = None
+
+
+def run_reference_mask_forward(action_embed_fn, obs, action_mask, action_size):
+    """MyMaskActionsModel.forward (rllib_mask_model.py:41-62) of the reference on a batch: `action_embed_fn(obs)` stands
+    for RLlib's FullyConnectedNetwork (the `action_embed_model` the parent class owns); what is the reference's own is
+    the masking  logits + max(log(action_mask), float32.min).  -> masked logits."""
+    global _CTX
+    from oracle import ref_harness
+    ref_harness.install_stubs()
+    _CTX = _Ctx(None, None)
+    try:
+        with _rllib_stand_ins():
+            mod = importlib.import_module("rl4rs.nets.rllib.rllib_mask_model")
+            cls = mod.getMaskActionsModel((np.shape(obs)[1],), action_size)
+            model = cls(None, None, action_size, {}, "mask_model")
+            assert model.model_config["fcnet_hiddens"] == [64] and model.model_config["vf_share_layers"] is True
+            model.action_embed_model = lambda d: (action_embed_fn(d["obs"]), None)
+            out, state = model.forward({"obs": {"obs": obs, "action_mask": np.asarray(action_mask, np.float32)}}, [], None)
+            return np.asarray(out)
+    finally:
+        _CTX = None

@@ -170,3 +170,52 @@ def test_the_references_own_stack_with_the_other_simulators(algo, seq):
         np.testing.assert_allclose(rec["reward"][t], reward, rtol=3e-5, atol=1e-9)
         np.testing.assert_array_equal(rec["done"][t], done)
     assert rec["step_obs"].shape[-1] == (3072 if algo == "widedeep" else 256) and (rec["reward"] > 0).any()
+
+
+def test_rllib_policy_models_of_the_reference_against_the_torch_twins():
+    """a22 / n4: rl4rs/nets/rllib/rllib_rawstate_model.py's TFModelWithRawState (its own Keras graph over nets/utils.py)
+    and rllib_mask_model.py's MyMaskActionsModel.forward (the action masking), run from the reference tree over the
+    stand-ins, against rl4rs_b200/policy.py -- the twins the kernels k_policy_act / k_policy_grad are themselves held to."""
+    if not ref_harness.reference_available():
+        pytest.skip("reference tree absent")
+    import torch
+    from oracle import tf_eager_stub as stub
+    from rl4rs_b200.policy import MaskedPolicy, RawStatePolicy
+    cfg = {"category_hash_size": 600, "emb_size": 128, "hidden_units": 128, "category_feature_num": 21,
+           "dense_feature_num": 432, "seq_num": 2, "maxlen": 64, "batch_size": 6}
+    rs = np.random.RandomState(0)
+    R, A = 6, 284
+    mask = (rs.rand(R, A) < 0.4).astype(np.float32)
+    mask[:, 7] = 1.0
+    # raw-state policy: embeddings -> pools -> dense tower -> context 256 -> logits / value
+    pol = RawStatePolicy(A, "cpu", seed=3, config=cfg)
+    with torch.no_grad():
+        pol.flat.add_(0.05 * torch.randn(pol.flat.shape, generator=torch.Generator().manual_seed(1)))
+    p = {k: v.detach().numpy() for k, v in pol.params().items()}
+    ck = {"embedding/embeddings": p["emb_cat"], "dense/kernel": p["dw1"], "dense/bias": p["db1"], "dense_1/kernel": p["dw2"],
+          "dense_1/bias": p["db2"], "embedding_1/embeddings": p["emb_seq"], "dense_2/kernel": p["wc"], "dense_2/bias": p["bc"],
+          "fc_out/kernel": p["w2"], "fc_out/bias": p["b2"], "value_out/kernel": p["wv"], "value_out/bias": p["bv"]}
+    cat, dense, seq = rs.randint(0, 600, (R, 21)), rs.normal(0, 2, (R, 432)).astype(np.float32), rs.randint(0, 284, (R, 2, 64))
+    out = stub.run_reference_rawstate_model(cfg, ck, cat.astype(np.float32), dense, seq.astype(np.float32), A)
+    scopes = [v[0] for v in out["variables"]]
+    assert not out["unused"]
+    assert [s_ for i, s_ in enumerate(scopes) if i == 0 or s_ != scopes[i - 1]] == \
+        ["embedding", "dense", "dense_1", "embedding_1", "dense_2", "fc_out", "value_out"]       # Keras creation order
+    obs = pol.pack({"category_feature": torch.as_tensor(cat), "dense_feature": torch.as_tensor(dense), "sequence_feature": torch.as_tensor(seq)})
+    with torch.no_grad():
+        logits, value = pol.forward(obs, torch.ones(R, A))
+        masked, _ = pol.forward(obs, torch.as_tensor(mask))
+    np.testing.assert_allclose(out["logits"], logits.numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(out["value"], value.numpy(), rtol=0, atol=2e-5)
+    # the masking itself, by the reference's forward(): fed the twin's unmasked logits as the action_embed_model output
+    got = stub.run_reference_mask_forward(lambda o: logits.numpy(), obs.numpy(), mask, A)
+    np.testing.assert_array_equal(got, masked.numpy())
+    # and for the 256-d observation policy of the benchmark configs
+    mp = MaskedPolicy(A, "cpu", seed=5)
+    o256 = torch.as_tensor(rs.normal(0, 1, (R, 256)).astype(np.float32))
+    with torch.no_grad():
+        raw, _ = mp.forward(o256, torch.ones(R, A))
+        want, _ = mp.forward(o256, torch.as_tensor(mask))
+    got = stub.run_reference_mask_forward(lambda o: raw.numpy(), o256.numpy(), mask, A)
+    np.testing.assert_array_equal(got, want.numpy())
+    assert (got[mask == 0] < -1e38).all()
