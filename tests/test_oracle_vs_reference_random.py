@@ -144,3 +144,46 @@ def test_ingest_equals_the_reference_preprocessing_on_random_sessions(seed, tmp_
     want_traj = run_stage("slate2trajectory", full)
     assert ingest.slate2trajectory(full) == want_traj
     assert 1 <= len(want_traj) < n_sess                      # the script drops the last session (and any it merges)
+
+
+def test_trainer_defaults_are_the_reference_scripts_hyper_parameters():
+    """a23: the RLlib config dicts of script/modelfree_train.py (PPO :179-217, A2C :248-268, common :390-415), read out of
+    the script's own source with `ast`, against the defaults rl4rs_b200/trainer.py trains with."""
+    import ast
+    from rl4rs_b200 import trainer
+    src = open(os.path.join(ref_harness.REFERENCE_ROOT, "script", "modelfree_train.py")).read()
+    tree = ast.parse(src)
+
+    def literal(node):
+        """A dict literal with non-literal values (config[...] expressions) left out."""
+        out = {}
+        for k, v in zip(node.keys, node.values):
+            if k is None:
+                continue
+            try:
+                out[ast.literal_eval(k)] = ast.literal_eval(v)
+            except Exception:
+                pass
+        return out
+
+    branches = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and isinstance(node.test, ast.Compare) and isinstance(node.test.left, ast.Constant) \
+                and node.test.left.value in ("PPO", "A2C"):
+            first = node.body[0]
+            assert isinstance(first, ast.Assign) and first.targets[0].id == "cfg"
+            branches[node.test.left.value] = literal(first.value)
+    assert set(branches) == {"PPO", "A2C"}
+    for algo, ours in (("PPO", trainer.PPO_DEFAULTS), ("A2C", trainer.A2C_DEFAULTS)):
+        ref = branches[algo]
+        shared = sorted(set(ref) & set(ours))
+        assert len(shared) >= 5, shared
+        for k in shared:
+            assert ours[k] == ref[k], (algo, k, ours[k], ref[k])
+    assert trainer.PPO_DEFAULTS["grad_clip"] is None and "grad_clip" not in branches["PPO"]       # commented out there
+    # the dict every algorithm is merged into: gamma 1, SoftQ exploration, complete episodes
+    common = [literal(n) for n in ast.walk(tree) if isinstance(n, ast.Dict)]
+    common = [d for d in common if d.get("batch_mode") == "complete_episodes"]
+    assert len(common) == 1 and common[0]["gamma"] == 1 and common[0]["explore"] is True
+    assert trainer.PPO_DEFAULTS["gamma"] == trainer.A2C_DEFAULTS["gamma"] == 1.0
+    assert '"type": "SoftQ"' in src
