@@ -187,3 +187,34 @@ def test_trainer_defaults_are_the_reference_scripts_hyper_parameters():
     assert len(common) == 1 and common[0]["gamma"] == 1 and common[0]["explore"] is True
     assert trainer.PPO_DEFAULTS["gamma"] == trainer.A2C_DEFAULTS["gamma"] == 1.0
     assert '"type": "SoftQ"' in src
+
+
+def test_static_helpers_on_the_real_catalog_and_random_knn_queries():
+    """slate.py:28-65,180-191: the item table, action embeddings, location mask and special items read from the
+    reference's own dataset/item_info.csv, and the two nearest-neighbour statics on random queries (incl. ties and
+    fully masked rows), reference class against mirror class."""
+    from rl4rs_b200.env.slate import SlateState
+    ref_slate = ref_harness.install_stubs()[1]
+    item_file = os.path.join(ref_harness.REFERENCE_ROOT, "dataset", "item_info.csv")
+    info_r, emb_r = ref_slate.SlateState.get_iteminfo_from_file(item_file, 284)
+    info_o, emb_o = SlateState.get_iteminfo_from_file(item_file, 284)
+    np.testing.assert_array_equal(emb_o, emb_r)
+    assert set(info_o) == set(info_r)
+    for k in info_r:
+        assert info_o[k]["price"] == info_r[k]["price"] and info_o[k]["location"] == info_r[k]["location"], k
+        np.testing.assert_array_equal(np.asarray(info_o[k]["item_vec"], float), np.asarray(info_r[k]["item_vec"], float))
+    loc_r, sp_r = ref_slate.SlateState.get_mask_from_file(item_file, 284)
+    loc_o, sp_o = SlateState.get_mask_from_file(item_file, 284)
+    np.testing.assert_array_equal(loc_o, loc_r)
+    assert list(sp_o) == list(sp_r) and len(sp_r) > 0
+    rs = np.random.RandomState(4)
+    for trial in range(20):
+        q = rs.uniform(-1, 1, (16, 32))
+        q[0] = 0.0                                            # every score ties at 0: lowest index wins
+        q[1] = emb_r[1 + trial]                               # an item's own embedding
+        mask = (rs.rand(16, 284) < 0.3).astype(np.int64)
+        mask[2] = 0                                           # nothing allowed: all scores -2**31, index 0
+        np.testing.assert_array_equal(SlateState.get_nearest_neighbor(q, emb_o),
+                                      ref_slate.SlateState.get_nearest_neighbor(q, emb_r))
+        np.testing.assert_array_equal(SlateState.get_nearest_neighbor_with_mask(q, emb_o, mask),
+                                      ref_slate.SlateState.get_nearest_neighbor_with_mask(q, emb_r, mask))
