@@ -8,6 +8,7 @@ import numpy as np
 
 from .base import RecSimBase, RecState
 from ..synth import Catalog
+from ..utils.datautil import FeatureUtil
 
 
 class StateView(object):
@@ -212,6 +213,7 @@ class SlateRecEnv(RecSimBase):
     def __init__(self, config, state_cls=SlateState):
         self.max_steps = config["max_steps"]
         self.batch_size = config["batch_size"]
+        self.FeatureUtil = FeatureUtil(config)               # slate.py:226 (plug-ins call self.FeatureUtil.feature_extraction)
         super().__init__(config, state_cls)
         self.obs_dim = self.engine.obs_dim                   # 256; 3072 for widedeep ('simulator_obs' is its concat layer)
         if config.get("support_d3rl_mask", False) and not config.get("support_rllib_mask", False) \

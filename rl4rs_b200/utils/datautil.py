@@ -38,6 +38,30 @@ class FeatureUtil(object):
                 [float(x) for x in f[7].replace(";", ",").split(",")],
                 int(f[8]))
 
+    def feature_extraction(self, data):
+        """Raw 6-field state rows -> ((sequence i32 [n, seq_num, maxlen], dense f32 [n, dense_feature_num], category i32
+        [n, category_feature_num], slate_label), labels) exactly like datautil.py:34-69: each behaviour sequence pre-padded
+        with 0 / cut to its LAST maxlen ids, dense and category rows post-padded / post-truncated.  The env itself never
+        calls this -- its feature rows are assembled on the GPU (k_assemble, k_seq_ids) -- it exists for `obs_fn` plug-ins
+        written against the reference (slate.py:244-249 calls it on `state['state']`), e.g. over `samples.state`."""
+        n = len(data)
+        seqs = np.zeros((n, self.seq_num, self.maxlen), np.int32)
+        dense = np.zeros((n, self.dense_feature_num), np.float32)
+        cat = np.zeros((n, self.category_feature_num), np.int32)
+        slate_labels, labels = [], []
+        for i, (role_id, sequence_feature, dense_feature, category_feature, slate_label, label) in enumerate(data):
+            for j, s in enumerate(list(sequence_feature)[:self.seq_num]):
+                s = np.asarray(s, dtype=np.int64)[-self.maxlen:]
+                if len(s):
+                    seqs[i, j, self.maxlen - len(s):] = s
+            d = np.asarray(dense_feature, dtype=np.float32)[:self.dense_feature_num]
+            dense[i, :len(d)] = d
+            c = np.asarray([int(x) for x in category_feature], dtype=np.int64)[:self.category_feature_num]
+            cat[i, :len(c)] = c
+            slate_labels.append(slate_label)
+            labels.append(label)
+        return (seqs, dense, cat, np.array(slate_labels)), labels
+
     @staticmethod
     def parse_log(lines, maxlen=64):
         """Text records -> LogSoA.  Only the fields the env reads are kept (SURVEY.md Appendix A:

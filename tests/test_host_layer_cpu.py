@@ -110,21 +110,30 @@ def test_batch_size_one_in_every_format(oracle_engine):
 
 
 def test_custom_obs_fn_plugin_reads_the_raw_state_rows(oracle_engine):
-    """base.py:160,174: a RecSimBase subclass with its own obs_fn(state) gets the reference's raw 6-field rows."""
+    """base.py:160,174 + slate.py:244-249: a RecSimBase subclass with its own obs_fn(state) gets the reference's raw
+    6-field rows and can run them through self.FeatureUtil.feature_extraction exactly like the reference's obs_fn does;
+    what comes out are the feature rows the engine assembled for that state."""
     from rl4rs_b200 import gymshim
     from rl4rs_b200.env.slate import SlateRecEnv, SlateState
 
-    class RawRowsEnv(SlateRecEnv):
+    class PluginEnv(SlateRecEnv):
         def obs_fn(self, state):
-            rows = state["state"]
-            return [[len(r), int(np.sum(r[3])), float(np.sum(r[2]))] for r in rows]
+            feat, _ = self.FeatureUtil.feature_extraction(state["state"])        # the reference's own first line
+            self.last_feat = feat
+            return [[len(r), int(np.sum(r[3])), float(np.sum(r[2]))] for r in state["state"]]
 
     g = Golden("slate_rllib_replay")
     cfg = dict(g.config, catalog=g.catalog, log=g.log, weights=g.weights)
-    env = gymshim.make("SlateRecEnv-v0", recsim=RawRowsEnv(cfg, state_cls=SlateState))
+    sim = PluginEnv(cfg, state_cls=SlateState)
+    env = gymshim.make("SlateRecEnv-v0", recsim=sim)
     env.reset()
-    obs, _, _, _ = env.step(g.arr["action_in"][0])
-    assert len(obs) == cfg["batch_size"] and all(o[0] == 6 for o in obs)
+    for t in range(3):
+        obs, _, _, _ = env.step(g.arr["action_in"][t])
+        assert len(obs) == cfg["batch_size"] and all(o[0] == 6 for o in obs)
+        seqs, dense, cat, _ = sim.last_feat
+        np.testing.assert_array_equal(seqs, g.arr["seq"][t])
+        np.testing.assert_array_equal(dense, g.arr["dense"][t])
+        np.testing.assert_array_equal(cat, g.arr["cat"][t])
 
 
 @pytest.mark.parametrize("seq,conti", [(False, False), (False, True), (True, False)])

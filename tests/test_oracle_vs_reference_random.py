@@ -218,3 +218,26 @@ def test_static_helpers_on_the_real_catalog_and_random_knn_queries():
                                       ref_slate.SlateState.get_nearest_neighbor(q, emb_r))
         np.testing.assert_array_equal(SlateState.get_nearest_neighbor_with_mask(q, emb_o, mask),
                                       ref_slate.SlateState.get_nearest_neighbor_with_mask(q, emb_r, mask))
+
+
+def test_feature_extraction_mirror_on_random_ragged_rows():
+    """datautil.py:34-69: FeatureUtil.feature_extraction, reference method against the host mirror, on raw state rows
+    with empty / short / over-long sequences, short and over-long dense and category lists."""
+    from rl4rs_b200.utils.datautil import FeatureUtil
+    ref_datautil = ref_harness.install_stubs()[3]
+    cfg = {"maxlen": 64, "batch_size": 5, "class_num": 2, "dense_feature_num": 432, "category_feature_num": 21,
+           "category_hash_size": 100000, "seq_num": 2}
+    ours, ref = FeatureUtil(cfg), ref_datautil.FeatureUtil(cfg)
+    rs = np.random.RandomState(8)
+    for trial in range(12):
+        rows = []
+        for i in range(5):
+            seqs = [list(rs.randint(1, 284, rs.choice([0, 1, 7, 64, 65, 130]))) for _ in range(2)]
+            dense = list(rs.normal(0, 1, rs.choice([32, 72, 432, 440])).astype(np.float64))
+            cat = list(rs.randint(0, 100000, rs.choice([10, 12, 21, 25])).astype(np.float64))       # floats in the reference too
+            rows.append([0, seqs, dense, cat, [0] * 9, int(rs.randint(2))])
+        (s1, d1, c1, l1), y1 = ours.feature_extraction(rows)
+        (s2, d2, c2, l2), y2 = ref.feature_extraction(rows)
+        np.testing.assert_array_equal(s1, s2); np.testing.assert_array_equal(d1, d2); np.testing.assert_array_equal(c1, c2)
+        np.testing.assert_array_equal(l1, l2)
+        assert y1 == y2 and d1.dtype == d2.dtype and c1.dtype == c2.dtype and s1.shape == (5, 2, 64)
