@@ -180,7 +180,11 @@ int r4_augru_kernel_for(int ctas, int sms);
  *                      step's reward pass -- the state the step leaves (rl4rs/env/slate.py:203-213, seqslate.py:104-122) is the
  *                      last of the page's complete states (slate.py:117-131, seqslate.py:27-50), so the reference runs the same
  *                      feature row through the simulator twice; 0: launch the separate observation pass as well
- * The environment variables R4_AUGRU_PAIR / R4_AUGRU_PP / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE / R4_NO_PAY_OBS_REUSE give the initial
+ *   "scores_impl"      DIN attention scores (nets/utils.py:121-122): 2 (default) = k_scores_tc2, both attention layers on the
+ *                      tensor pipe with the second GEMM's A operand in tensor memory; 1 = k_scores_tc (second layer as FMAs)
+ *   "scores_shared_pct" share of an even CTA split given to a sequence whose cached rows are shared by all feature rows
+ *                      (Slate's constant second sequence), 10..100 per cent
+ * The environment variables R4_AUGRU_PAIR / R4_AUGRU_PP / R4_AUGRU_PAIR_IMPL / R4_AUGRU_RULE / R4_NO_PAY_OBS_REUSE / R4_SCORES_IMPL give the initial
  * values.  Returns 0, or R4_ERR_ARG for an unknown key / out-of-range value. */
 int r4_set_option(const char* key, int value);
 
