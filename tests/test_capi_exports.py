@@ -139,3 +139,15 @@ def test_set_option_accepts_what_the_header_documents():
             assert lib.r4_set_option(k.encode(), v) == 0, k
     assert lib.r4_set_option(b"no_such_option", 1) == -1 and b"no_such_option" in lib.r4_last_error(None)
     assert lib.r4_set_option(b"augru_cluster", 3) == -1 and lib.r4_set_option(b"scores_shared_pct", 5) == -1
+
+
+def test_host_only_entry_points_agree_with_the_python_side():
+    """Pure host arithmetic behind the ABI: parameter count of the policy (flat layout of rl4rs_b200/policy.py), observation
+    widths per simulator."""
+    import ctypes as C
+    from rl4rs_b200.policy import MaskedPolicy
+    lib = _capi.load_library()
+    lib.r4_policy_num_params.restype = C.c_int
+    for A in (284, 50):
+        assert lib.r4_policy_num_params(A) == MaskedPolicy(A, "cpu").n_params == 256 * 64 + 64 + 64 * A + A + 64 + 1
+    assert [lib.r4_obs_dim(_capi.SIMULATORS[k]) for k in ("dien", "dnn", "widedeep", "lstm")] == [256, 256, 3072, 256]
